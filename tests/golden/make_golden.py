@@ -1,0 +1,125 @@
+"""Generate the golden fixtures that pin ``oracle/`` to the reference implementation.
+
+Run ONLY in the build container (needs the read-only reference checkout):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+It imports the unmodified reference package from /root/reference, runs the reference
+functions of the hot path on seeded synthetic inputs and stores their outputs as small
+``.npz`` files next to this script.  The inputs are NOT stored: tests regenerate them from
+the same seeds through ``oracle.synth`` / ``oracle.net.init_params`` (a checksum of each
+regenerated input is stored so a drifting RNG is detected rather than mis-reported).
+Nothing here is read at test time except the ``.npz`` files.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("POSENET_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+import posenet as ref                      # noqa: E402  (the reference, NOT the product package)
+import posenet.decode_multi as ref_dm      # noqa: E402
+
+from oracle import net as onet             # noqa: E402
+from oracle import synth                   # noqa: E402
+sys.path.insert(0, HERE)
+from make_golden_cases import DEC_CASES, NET_CASES, PRE_CASES, heads_for as _heads  # noqa: E402
+
+assert os.path.realpath(ref.__file__).startswith(os.path.realpath(REF)), ref.__file__
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ----------------------------------------------------------------------------- preprocess
+def make_preprocess():
+    out = {"cases": np.array([(h, w, sf, os_, seed) for h, w, sf, os_, seed, _ in PRE_CASES], dtype=np.float64)}
+    for i, (h, w, sf, os_, seed, full) in enumerate(PRE_CASES):
+        img = synth.noise_image(h, w, seed)
+        x, src, scale = ref.utils._process_input(img, sf, os_)
+        assert src is img
+        out["in_sha_%d" % i] = np.array(sha(img))
+        out["shape_%d" % i] = np.array(x.shape)
+        out["sha_%d" % i] = np.array(sha(x))
+        out["scale_%d" % i] = scale
+        out["vres_%d" % i] = np.array(ref.valid_resolution(w * sf, h * sf, os_))
+        if full:
+            out["x_%d" % i] = x
+    np.savez_compressed(os.path.join(HERE, "preprocess.npz"), **out)
+    print("preprocess: %d cases" % len(PRE_CASES))
+
+
+# ----------------------------------------------------------------------------- network
+def make_net():
+    out = {"cases": np.array([(m, o, h, w, n, 0 if s == "default" else 1, g, sd)
+                              for m, o, h, w, n, s, g, sd in NET_CASES], dtype=np.float64)}
+    for i, (mid, os_, H, W, N, scheme, gain, seed) in enumerate(NET_CASES):
+        sd = onet.init_params(mid, seed, scheme, gain)
+        model = ref.MobileNetV1(mid, output_stride=os_)
+        model.load_state_dict(sd, strict=True)      # same key names/shapes as the reference
+        model.eval()
+        x = torch.from_numpy(np.stack([
+            ref.utils._process_input(synth.smooth_image(H, W, 100 * seed + b), 1.0, os_)[0][0]
+            for b in range(N)]))
+        assert tuple(x.shape) == (N, 3, H, W), x.shape
+        with torch.no_grad():
+            heads = model(x)
+        # layer table as the reference module realised it
+        tab = []
+        for name, m in model.features.named_children():
+            conv = m.conv if hasattr(m, "conv") else m.depthwise
+            tab.append((conv.stride[0], conv.dilation[0], conv.padding[0]))
+        out["table_%d" % i] = np.array(tab)
+        out["w_sha_%d" % i] = np.array(sha(np.concatenate([v.numpy().ravel() for v in sd.values()])))
+        out["x_sha_%d" % i] = np.array(sha(x.numpy()))
+        for nm, t in zip(("heat", "off", "fwd", "bwd"), heads):
+            out["%s_%d" % (nm, i)] = t.numpy()
+    np.savez_compressed(os.path.join(HERE, "net.npz"), **out)
+    print("net: %d cases" % len(NET_CASES))
+
+
+# ----------------------------------------------------------------------------- decode
+def make_decode():
+    out = {"n": np.array(len(DEC_CASES))}
+    real_argsort = torch.argsort
+    for i, (kind, h, w, stride, people, seed, P, thr, rad, minp, patch, extra) in enumerate(DEC_CASES):
+        heat, off, fwd, bwd = _heads(kind, h, w, stride, people, seed, extra)
+        # The reference's argsort is unstable (decode_multi.py:33): where scores tie, the fixture is
+        # produced with the sort forced stable (ties -> ascending flat index), the order the oracle defines.
+        cs, _ = ref_dm.build_part_with_score_torch(thr, 1, torch.from_numpy(heat))
+        ties = len(np.unique(cs.numpy())) != len(cs)
+        assert ties or not patch, "case %d was expected to contain ties" % i
+        if ties:
+            torch.argsort = lambda t, descending=False, **kw: real_argsort(t, descending=descending, stable=True)
+        try:
+            cs, ci = ref_dm.build_part_with_score_torch(thr, 1, torch.from_numpy(heat))
+            res = ref_dm.decode_multiple_poses(
+                torch.from_numpy(heat), torch.from_numpy(off), torch.from_numpy(fwd), torch.from_numpy(bwd),
+                output_stride=stride, max_pose_detections=P, score_threshold=thr, nms_radius=rad,
+                min_pose_score=minp)
+        finally:
+            torch.argsort = real_argsort
+        out["in_sha_%d" % i] = np.array(sha(np.concatenate([heat.ravel(), off.ravel(), fwd.ravel(), bwd.ravel()])))
+        out["cand_s_%d" % i] = cs.numpy()
+        out["cand_i_%d" % i] = ci.numpy()
+        for nm, a in zip(("ps", "ks", "kc", "ko"), res):
+            assert a.dtype == np.float64
+            out["%s_%d" % (nm, i)] = a
+        out["ties_%d" % i] = np.array(ties)
+        print("decode case %2d: %4d candidates, %2d poses, ties=%s" % (i, len(cs), int((res[0] != 0).sum()), ties))
+    np.savez_compressed(os.path.join(HERE, "decode.npz"), **out)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    make_preprocess()
+    make_net()
+    make_decode()
