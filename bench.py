@@ -1,0 +1,314 @@
+"""bench.py -- images/sec of the PoseNet hot path (backbone + heads + multi-pose decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4]
+
+One "step" = one pass of  uint8 images -> (fused preprocess) stem -> 13 separable blocks -> heads ->
+part candidates -> greedy decode  over one batch.  Default workload = BASELINE.json configs[1]:
+MobileNetV1 model 101, 513x513, output stride 16, batch 64 per GPU, bf16, random-init weights, synthetic images.
+Rank 0 prints ONE JSON line (see the keys below).  ``--impl reference`` times the CPU oracle port
+(the reference's algorithm: torch-CPU fp32 convs + numpy float64 decode) on the host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "posenet-pytorch_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (model, H, W, output_stride, batch per GPU, description)
+    "c2": (101, 513, 513, 16, 64, "MobileNetV1-101 513x513 OS16 batch 64/GPU bf16 (BASELINE configs[1])"),
+    "c3": (50, 721, 1281, 8, 32, "MobileNetV1-50 1280x720->721x1281 OS8 batch 32/GPU bf16 (BASELINE configs[2])"),
+    "c4": (75, 257, 257, 32, 512, "MobileNetV1-75 257x257 OS32 batch 512/GPU bf16 (BASELINE configs[3])"),
+}
+METRIC = "images/sec (backbone+decode)"
+DECODE_KW = dict(max_pose_detections=10, score_threshold=0.5, nms_radius=20, min_pose_score=0.25)  # benchmark.py:37-44
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")   # B200_PROFILING.md
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_run(workload, images_per_step, steps, warmup):
+    """The reference's algorithm on the host cores: batch 1 per image like benchmark.py:32-44 --
+    preprocess (utils.py:13-26), forward (mobilenet_v1.py:156-162, torch CPU fp32), decode (decode_multi.py:61-148)."""
+    from oracle import decode as odec, net as onet, preprocess as opre, synth
+    mid, H, W, os_, _, _ = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = onet.init_params(mid, seed=0)
+    imgs = [synth.noise_image(H, W, s) for s in range(4)]
+
+    def one(i):
+        x, _, _ = opre.process_input(imgs[i % len(imgs)], 1.0, os_)
+        heads = onet.forward(sd, mid, os_, torch.from_numpy(x))
+        return odec.decode_multiple_poses(*[t.squeeze(0).numpy() for t in heads], os_, **DECODE_KW)
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        for i in range(images_per_step):
+            one(s * images_per_step + i)
+    dt = time.perf_counter() - t0
+    return dict(value=steps * images_per_step / dt, ms_per_step=dt / steps * 1e3, cores=cores,
+                sample="%d steps x %d images, batch 1, torch-CPU fp32 forward + numpy f64 decode" % (steps, images_per_step))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mid, H, W, os_, batch, desc = WORKLOADS[args.workload]
+    r = cpu_reference_run(args.workload, images_per_step=4, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/sec", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "images_per_step": 4, "batch": 1},
+            "cpu_baseline": {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def layer_costs(model, n, H, W):
+    """Algorithmic bytes / flops per launch: depthwise bytes = (in + out pixels) * C * 2 (+ weights),
+    pointwise flops = 2 M K N and bytes = (M K + M N + K N) * 2."""
+    rows, h, w = [], H, W
+    for L in model._layers:
+        s, d = L["stride"], L["rate"]
+        pad = ((s - 1) + 2 * d) // 2
+        ho, wo = (h + 2 * pad - 2 * d - 1) // s + 1, (w + 2 * pad - 2 * d - 1) // s + 1
+        m = n * ho * wo
+        if L["block_id"] == 0:
+            rows.append(("stem", n * h * w * 3 + m * L["outp"] * 2, 2 * 27 * m * L["outp"]))
+        else:
+            c = L["inp"]
+            rows.append(("dw%d" % L["block_id"], (n * h * w + m) * c * 2 + 40 * c, 18 * m * c))
+            rows.append(("pw%d" % L["block_id"], (m * c + m * L["outp"] + c * L["outp"]) * 2, 2 * m * c * L["outp"]))
+        h, w = ho, wo
+    m = n * h * w
+    c = model._layers[-1]["outp"]
+    rows.append(("heads", (m * c + 128 * c) * 2 + m * 115 * 4, 2 * m * c * 115))
+    # candidates read the heatmap (17 h w fp32); the greedy decode touches at most all four head maps
+    rows.append(("candidates+decode", m * 17 * 4 + m * 115 * 4, 0))
+    return rows, (h, w)
+
+
+def per_kernel_times(model, imgs_list, reps=5):
+    """Device time of every launch of one forward, measured IN SITU: pn_plan_profile enqueues the same
+    launches as a normal forward with a CUDA event between consecutive kernels on the launching stream
+    (so each kernel sees the cache state its producer left).  Median over `reps` forwards; plus the
+    candidate + decode kernels timed the same way around the public decode call."""
+    import posenet
+    n, H, W, _ = imgs_list[0].shape
+    plan = model._plan(n, H, W, True)
+    heads = [torch.empty((n, ch, plan.out_h, plan.out_w), dtype=torch.float32, device=imgs_list[0].device) for ch in (17, 34, 32, 32)]
+    runs = []
+    for r in range(reps + 1):
+        runs.append(plan.profile(imgs_list[r % len(imgs_list)], heads))
+    runs = runs[1:]
+    times = {name: sorted(run[i][1] for run in runs)[reps // 2] for i, (name, _) in enumerate(runs[0])}
+    ws, dec = {}, []
+    for r in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        posenet.decode_multiple_poses_batch(*heads, output_stride=model.output_stride, workspace=ws, **DECODE_KW)
+        e1.record()
+        torch.cuda.synchronize()
+        dec.append(e0.elapsed_time(e1))
+    times["candidates+decode"] = sorted(dec[1:])[reps // 2]
+    return times
+
+
+def run_b200(args):
+    import posenet
+    from posenet import _native as nat
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    mid, H, W, os_, batch, desc = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    torch.manual_seed(0)
+    model = posenet.MobileNetV1(mid, output_stride=os_).cuda().set_compute_dtype("bf16")   # default torch init, seeded
+    n_sets = 4                                                   # rotate inputs: 4 x 50 MB u8 > 126 MB L2
+    rng = np.random.default_rng(1234 + rank)
+    host = [torch.from_numpy(rng.integers(0, 256, (batch, H, W, 3), dtype=np.uint8)).pin_memory() for _ in range(n_sets)]
+    imgs = [h.to(dev) for h in host]
+    ws = {}
+
+    def step(x):
+        heads = model.forward_u8(x)
+        return posenet.decode_multiple_poses_batch(*heads, output_stride=os_, workspace=ws, **DECODE_KW)
+
+    # ---- device-resident throughput: one CUDA graph per input set
+    for x in imgs:
+        step(x)
+    torch.cuda.synchronize()
+    graphs = []
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for x in imgs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                out = step(x)
+            graphs.append((g, out))
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        graphs[i % n_sets][0].replay()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        graphs[i % n_sets][0].replay()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t)
+    value = world * batch * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API: pinned host uint8 -> H2D -> model -> decode -> D2H pose records
+    def e2e_step(i):
+        x = host[i % n_sets].to(dev, non_blocking=True)
+        ps, ks, kc, ko, cnt = step(x)
+        return torch.cat([ps.reshape(-1), ks.reshape(-1), kc.reshape(-1), ko.reshape(-1)]).cpu()
+    for i in range(max(3, args.warmup)):
+        rec = e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        rec = e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(t)
+    e2e = {"value": world * batch * args.steps / e2e_s, "unit": "images/sec", "h2d_bytes_per_step": int(host[0].numel()),
+           "d2h_bytes_per_step": int(rec.numel() * 8)}
+
+    if rank != 0:
+        return
+    # ---- per-kernel roofline (rank 0, live CUDA events on the launching stream)
+    pk = peaks()
+    times = per_kernel_times(model, imgs)
+    costs, _ = layer_costs(model, batch, H, W)
+    total_ms = sum(times.values())
+    kernels = []
+    for name, nbytes, flops in costs:
+        t = times[name] * 1e-3
+        ai = flops / nbytes
+        tensor_bound = name.startswith(("pw", "heads")) and ai > pk["bf16_sustained"] * 1e3 / pk["hbm"]
+        kernels.append({"name": name, "ms": round(times[name], 4), "share": round(times[name] / total_ms, 4),
+                        "gbs": round(nbytes / t / 1e9, 1), "tflops": round(flops / t / 1e12, 2),
+                        "bound": "tensor" if tensor_bound else "hbm",
+                        "frac": round((flops / t / 1e12) / pk["bf16_sustained"] if tensor_bound else (nbytes / t / 1e9) / pk["hbm"], 4)})
+    top = max(kernels, key=lambda k: k["ms"])
+    roofline = {"kernel": top["name"], "bound": top["bound"],
+                "achieved": top["tflops"] if top["bound"] == "tensor" else top["gbs"],
+                "peak": pk["bf16_sustained"] if top["bound"] == "tensor" else pk["hbm"],
+                "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": None,
+                "peak_source": pk["src"] + (" (sustained)" if top["bound"] == "tensor" else "")}
+    cpu = cpu_reference_run("c2" if args.workload == "c2" else args.workload, images_per_step=4, steps=3, warmup=1) \
+        if world == 1 else None
+    launches = model.num_launches(batch, H, W, True) + 2
+    line = {"metric": METRIC, "value": round(value, 1), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": batch, "decode": DECODE_KW, "weights": "random-init (torch default, seed 0)",
+                       "l2": "inputs rotate over %d batches (%d MB > 126 MB L2); per-step activation traffic >> L2" % (
+                           n_sets, n_sets * host[0].numel() // 2 ** 20), "cuda_graph": True},
+            "e2e": e2e, "gpu_launches": launches * args.steps, "clocks": clocks, "roofline": roofline,
+            "kernels": kernels, "forward_ms_sum_of_kernels": round(total_ms, 3)}
+    if cpu:
+        line["cpu_baseline"] = {"value": round(cpu["value"], 2), "unit": "images/sec", "cores": cpu["cores"], "kind": "port",
+                                "sample": cpu["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

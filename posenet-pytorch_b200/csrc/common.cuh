@@ -1,0 +1,120 @@
+// Shared host/device helpers for libposenet_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/posenet_b200.h"
+
+namespace pn {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+
+#define PN_CHECK_ARG(cond, ...)           \
+    do {                                  \
+        if (!(cond)) {                    \
+            pn::set_error(__VA_ARGS__);   \
+            return PN_ERR_ARG;            \
+        }                                 \
+    } while (0)
+
+#define PN_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            pn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PN_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+#define PN_CHECK_LAUNCH() PN_CHECK_CUDA(cudaGetLastError())
+
+inline cudaStream_t as_stream(pn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+int num_sms();
+
+// ---- shared epilogue description for both GEMM paths -------------------------------------------
+// EPI_RELU6: y[m, n] = clamp(acc + bias[n], 0, 6) stored row-major [M, N] in the activation dtype.
+// EPI_HEADS: the 115 head channels scattered to four fp32 NCHW tensors, sigmoid on the heatmap.
+enum { EPI_RELU6 = 0, EPI_HEADS = 1 };
+
+struct EpiParams {
+    const float *bias;
+    void *y;        // EPI_RELU6
+    float *heat, *off, *fwd, *bwd;  // EPI_HEADS
+    int hw;         // EPI_HEADS: pixels per image
+};
+
+__device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.f), 6.f); }
+
+// Head column -> (tensor, channel).  Layout of the packed head rows: heat 0..16, offset 17..50,
+// displacement_fwd 51..82, displacement_bwd 83..114 (mobilenet_v1.py:151-154).
+__device__ __forceinline__ void store_head(const EpiParams &ep, int m, int col, float v) {
+    int img = m / ep.hw;
+    int p = m - img * ep.hw;
+    if (col < 17) {
+        ep.heat[((size_t)img * 17 + col) * ep.hw + p] = 1.f / (1.f + expf(-v));   // mobilenet_v1.py:158
+    } else if (col < 51) {
+        ep.off[((size_t)img * 34 + (col - 17)) * ep.hw + p] = v;
+    } else if (col < 83) {
+        ep.fwd[((size_t)img * 32 + (col - 51)) * ep.hw + p] = v;
+    } else if (col < 115) {
+        ep.bwd[((size_t)img * 32 + (col - 83)) * ep.hw + p] = v;
+    }
+}
+
+// ---- typed activation load/store (fp32 | bf16), 8 channels at a time -------------------------
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void load(const float *p, float (&v)[8]) {
+        float4 a = *reinterpret_cast<const float4 *>(p);
+        float4 b = *reinterpret_cast<const float4 *>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&v)[8]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8]) {
+        uint4 r = *reinterpret_cast<const uint4 *>(p);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // bf16 -> f32 is a 16-bit shift
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+// ---- launchers implemented one per .cu file ----------------------------------------------------
+int launch_preprocess(const uint8_t *src, int n, int sh, int sw, int dh, int dw, float *dst, cudaStream_t s);
+int launch_stem(const void *x, bool x_is_u8, const float *w, const float *b, void *y, int n, int h, int wd,
+                int cout, int stride, int out_dtype, cudaStream_t s);
+int launch_dwconv(const void *x, const float *w, const float *b, void *y, int n, int h, int wd, int c,
+                  int stride, int dilation, int dtype, cudaStream_t s);
+int launch_gemm_simt(const float *a, const float *w, int m, int k, int n, int epi, const EpiParams &ep,
+                     cudaStream_t s);
+
+// tcgen05 path: tensor maps are encoded once (per plan, or per standalone call) then reused.
+struct GemmTc {
+    alignas(64) unsigned char tmap_a[128];
+    alignas(64) unsigned char tmap_b[128];
+    int m, k, n, block_n, epi;
+};
+int gemm_tc_prepare(GemmTc *g, const void *a, const void *w, int m, int k, int n, int epi);
+int gemm_tc_launch(const GemmTc *g, const EpiParams &ep, cudaStream_t s);
+
+}  // namespace pn

@@ -1,0 +1,361 @@
+// C1 + D1..D4 -- part candidates and the greedy multi-pose decoder, on the device.
+// Replaces posenet/decode_multi.py:27-34 (build_part_with_score_torch), :61-148 (decode_multiple_poses),
+// :8-24 (NMS / instance score) and posenet/decode.py:9-63,131-182 (traverse_to_targ_keypoint,
+// decode_pose) of the reference, including the six .cpu().numpy() round trips they imply.
+//
+// Bit-exactness: the reference decodes in numpy float64 from fp32 maps.  Everything below uses the
+// same IEEE operations in the same order (explicit _rn intrinsics so nothing is contracted into an
+// FMA), round-half-even (rint), numpy's pairwise summation order for the instance score, and the
+// "score == 0.0 means not yet decoded" flag.  The one defined difference: the reference's candidate
+// sort is unstable (torch.argsort); here the order is (score desc, flat (part,y,x) index asc).
+#include "common.cuh"
+
+namespace pn {
+
+__constant__ int c_parent[PN_NUM_EDGES] = {0, 1, 0, 2, 0, 5, 7, 5, 11, 13, 0, 6, 8, 6, 12, 14};
+__constant__ int c_child[PN_NUM_EDGES] = {1, 3, 2, 4, 5, 7, 9, 11, 13, 15, 6, 8, 10, 12, 14, 16};
+
+__device__ __forceinline__ float map_at(const pn_map &m, int img, int ch, int y, int x) {
+    return __ldg(m.ptr + img * m.s_img + ch * m.s_ch + y * m.s_y + x * m.s_x);
+}
+
+// ---------------------------------------------------------------------------------- C1: candidates
+// Sort key: high word = ~orderable(score) so that ascending key == descending score; low word = flat
+// index, which both breaks ties the way the oracle defines and identifies the cell.
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t flat) {
+    uint32_t u = (score == 0.0f) ? 0u : __float_as_uint(score);   // -0.0 and +0.0 tie, as they do for argsort
+    u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;       // monotone float -> uint
+    return ((uint64_t)(~u) << 32) | flat;
+}
+
+__global__ void __launch_bounds__(256) candidates_kernel(pn_map heat, int h, int w, float thr,
+                                                          uint64_t *__restrict__ keys, int capacity,
+                                                          int *__restrict__ counts) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int part = blockIdx.y;
+    const int img = blockIdx.z;
+    bool keep = false;
+    float v = 0.f;
+    if (p < h * w) {
+        const int y = p / w, x = p - y * w;
+        v = map_at(heat, img, part, y, x);
+        if (v >= thr) {                                // decode_multi.py:30 (threshold already fp32)
+            keep = true;
+            // 3x3 window, -inf padding (decode_multi.py:29): a cell survives iff no in-bounds neighbour
+            // is larger.  !(nb <= v) also rejects NaN neighbours like max_pool2d's NaN propagation.
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = y + dy;
+                if (yy < 0 || yy >= h) continue;
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int xx = x + dx;
+                    if (xx < 0 || xx >= w || (dx == 0 && dy == 0)) continue;
+                    if (!(map_at(heat, img, part, yy, xx) <= v)) keep = false;
+                }
+            }
+        }
+    }
+    // warp-aggregated compaction: one atomic per warp, ballot/popc prefix inside it
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, keep);
+    if (mask) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(mask) - 1) base = atomicAdd(&counts[img], __popc(mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mask) - 1);
+        if (keep) {
+            const int pos = base + __popc(mask & ((1u << lane) - 1));
+            if (pos < capacity) keys[(size_t)img * capacity + pos] = make_key(v, (uint32_t)(part * h * w + p));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- D: greedy decode
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_KBUF = 4096;          // candidate keys sorted per round in shared memory (32 KB)
+
+struct DecodeArgs {
+    pn_map heat, off, fwd, bwd;
+    int h, w;
+    const uint64_t *keys;
+    int capacity;
+    const int *counts;
+    pn_decode_params prm;
+    double *pose_scores, *kp_scores, *kp_coords, *kp_offsets;
+    int *pose_counts;
+};
+
+struct DecodeShared {
+    uint64_t keys[DEC_KBUF];
+    unsigned hist[256];
+    double ks[PN_NUM_PARTS];
+    double kc[PN_NUM_PARTS][2];
+    double ko[PN_NUM_PARTS][2];
+    double vals[PN_NUM_PARTS];
+    uint64_t pivot;
+    int cnt;
+    int npose;
+    int done;
+};
+
+// decode.py:15-16 / :50-51 -- np.clip(np.round(p / stride), 0, hi).astype(int32): f64 divide, half-even.
+__device__ __forceinline__ int to_cell(double p, double stride, int hi) {
+    double r = rint(__ddiv_rn(p, stride));
+    r = fmin(fmax(r, 0.0), (double)hi);
+    return (int)r;
+}
+
+// numpy's pairwise float64 sum for n <= 128 contiguous values (verified against np.sum for n = 0..17).
+__device__ double np_sum(const double *a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+// decode.py:9-63: one displacement hop source -> target along edge e (lane 0 of warp 0 only).
+__device__ __forceinline__ void hop(const DecodeArgs &a, DecodeShared &S, int img, const pn_map &disp, int e, int src,
+                                    int tgt) {
+    const double stride = (double)a.prm.output_stride;
+    const double sy = S.kc[src][0], sx = S.kc[src][1];
+    const int iy = to_cell(sy, stride, a.h - 1), ix = to_cell(sx, stride, a.w - 1);
+    const double py = __dadd_rn(sy, (double)map_at(disp, img, e, iy, ix));                    // decode.py:39-40
+    const double px = __dadd_rn(sx, (double)map_at(disp, img, PN_NUM_EDGES + e, iy, ix));
+    const int ty = to_cell(py, stride, a.h - 1), tx = to_cell(px, stride, a.w - 1);
+    const float sc = map_at(a.heat, img, tgt, ty, tx);                                        // decode.py:53
+    const float oy = map_at(a.off, img, tgt, ty, tx), ox = map_at(a.off, img, PN_NUM_PARTS + tgt, ty, tx);
+    S.ks[tgt] = (double)sc;
+    S.kc[tgt][0] = __dadd_rn((double)(ty * a.prm.output_stride), (double)oy);                 // decode.py:55-56
+    S.kc[tgt][1] = __dadd_rn((double)(tx * a.prm.output_stride), (double)ox);
+    S.ko[tgt][0] = (double)oy;
+    S.ko[tgt][1] = (double)ox;
+}
+
+__device__ __forceinline__ double sqdist(double ay, double ax, double by, double bx) {
+    const double dy = __dsub_rn(ay, by), dx = __dsub_rn(ax, bx);
+    return __dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx));
+}
+
+__global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
+    __shared__ DecodeShared S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int img = blockIdx.x;
+    const int P = a.prm.max_pose_detections;
+    const int n = min(a.counts[img], a.capacity);
+    const uint64_t *keys = a.keys + (size_t)img * a.capacity;
+    const int hw = a.h * a.w;
+    const double r2 = a.prm.squared_nms_radius;
+    double *out_ps = a.pose_scores + (size_t)img * P;
+    double *out_ks = a.kp_scores + (size_t)img * P * PN_NUM_PARTS;
+    double *out_kc = a.kp_coords + (size_t)img * P * PN_NUM_PARTS * 2;
+    double *out_ko = a.kp_offsets + (size_t)img * P * PN_NUM_PARTS * 2;
+
+    uint64_t lo = 0;            // every key consumed so far is <= lo (real keys are never 0)
+    int remaining = n;
+    int npose = 0;
+
+    while (remaining > 0 && npose < P) {
+        // ---- 1. pick a pivot so that (lo, pivot] holds between 1 and DEC_KBUF of the best keys
+        uint64_t pivot = ~0ull;
+        if (remaining > DEC_KBUF) {
+            // MSB-first radix descent, 8 bits per level, among keys > lo.  Keys are unique (low word is
+            // the cell index), so the descent always terminates with a non-empty prefix set.
+            uint64_t prefix = 0;
+            int bits = 0;
+            for (;;) {
+                for (int i = tid; i < 256; i += DEC_THREADS) S.hist[i] = 0;
+                __syncthreads();
+                const int shift = 56 - bits;
+                for (int i = tid; i < n; i += DEC_THREADS) {
+                    const uint64_t k = keys[i];
+                    if (k > lo && (bits == 0 || (k >> (64 - bits)) == prefix)) atomicAdd(&S.hist[(k >> shift) & 255], 1u);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    unsigned cum = 0;
+                    int sel = -1, first = -1;
+                    for (int d = 0; d < 256; ++d) {
+                        const unsigned c = S.hist[d];
+                        if (c && first < 0) first = d;
+                        if (cum + c > (unsigned)DEC_KBUF) break;
+                        cum += c;
+                        if (c) sel = d;
+                    }
+                    if (sel >= 0) {
+                        const uint64_t low_ones = shift ? ((1ull << shift) - 1) : 0ull;
+                        S.pivot = (((prefix << 8) | (uint64_t)sel) << shift) | low_ones;
+                        S.done = 1;
+                    } else {
+                        S.pivot = (prefix << 8) | (uint64_t)first;   // descend into the first non-empty bucket
+                        S.done = 0;
+                    }
+                }
+                __syncthreads();
+                const int done = S.done;
+                const uint64_t pv = S.pivot;
+                __syncthreads();
+                if (done) { pivot = pv; break; }
+                prefix = pv;
+                bits += 8;
+            }
+        }
+        // ---- 2. gather (lo, pivot] into shared memory and sort ascending (bitonic)
+        if (tid == 0) S.cnt = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += DEC_THREADS) {
+            const uint64_t k = keys[i];
+            if (k > lo && k <= pivot) S.keys[atomicAdd(&S.cnt, 1)] = k;
+        }
+        __syncthreads();
+        const int cnt = S.cnt;
+        int m = 2;
+        while (m < cnt) m <<= 1;
+        for (int i = cnt + tid; i < m; i += DEC_THREADS) S.keys[i] = ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < m; i += DEC_THREADS) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint64_t x = S.keys[i], y = S.keys[ixj];
+                        const bool up = ((i & k) == 0);
+                        if ((x > y) == up) { S.keys[i] = y; S.keys[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // ---- 3. greedy pass over this chunk (warp 0; the chain of dependent gathers is serial)
+        if (warp == 0) {
+            for (int ci = 0; ci < cnt && npose < P; ++ci) {
+                const uint32_t flat = (uint32_t)S.keys[ci];
+                const int part = flat / hw;
+                const int rem = flat - part * hw;
+                const int y = rem / a.w, x = rem - y * a.w;
+                const float rscore = map_at(a.heat, img, part, y, x);
+                // decode_multi.py:106-109: int64 cell * stride + fp32 offset -> float64
+                const double ry = __dadd_rn((double)(y * a.prm.output_stride), (double)map_at(a.off, img, part, y, x));
+                const double rx = __dadd_rn((double)(x * a.prm.output_stride),
+                                            (double)map_at(a.off, img, PN_NUM_PARTS + part, y, x));
+                // decode_multi.py:8-11,111-113: same part of any accepted pose within the radius (<=)
+                bool hit = false;
+                for (int p = lane; p < npose; p += 32) {
+                    const double cy = __ldcg(out_kc + ((size_t)p * PN_NUM_PARTS + part) * 2);
+                    const double cx = __ldcg(out_kc + ((size_t)p * PN_NUM_PARTS + part) * 2 + 1);
+                    if (sqdist(cy, cx, ry, rx) <= r2) hit = true;
+                }
+                if (__any_sync(0xFFFFFFFFu, hit)) continue;
+
+                // decode.py:131-182
+                if (lane < PN_NUM_PARTS) {
+                    S.ks[lane] = 0.0;
+                    S.kc[lane][0] = 0.0; S.kc[lane][1] = 0.0;
+                    S.ko[lane][0] = 0.0; S.ko[lane][1] = 0.0;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    S.ks[part] = (double)rscore;
+                    S.kc[part][0] = ry;
+                    S.kc[part][1] = rx;
+                    for (int e = PN_NUM_EDGES - 1; e >= 0; --e) {           // backward: child -> parent
+                        const int tgt = c_parent[e], src = c_child[e];
+                        if (S.ks[src] > 0.0 && S.ks[tgt] == 0.0) hop(a, S, img, a.bwd, e, src, tgt);
+                    }
+                    for (int e = 0; e < PN_NUM_EDGES; ++e) {                // forward: parent -> child
+                        const int src = c_parent[e], tgt = c_child[e];
+                        if (S.ks[src] > 0.0 && S.ks[tgt] == 0.0) hop(a, S, img, a.fwd, e, src, tgt);
+                    }
+                }
+                __syncwarp();
+
+                // decode_multi.py:14-24: keep the parts that are strictly farther than the radius from
+                // that part of EVERY accepted pose; sum in numpy's order; always divide by 17.
+                bool far = lane < PN_NUM_PARTS;
+                if (lane < PN_NUM_PARTS) {
+                    const double ky = S.kc[lane][0], kx = S.kc[lane][1];
+                    for (int p = 0; p < npose; ++p) {
+                        const double cy = __ldcg(out_kc + ((size_t)p * PN_NUM_PARTS + lane) * 2);
+                        const double cx = __ldcg(out_kc + ((size_t)p * PN_NUM_PARTS + lane) * 2 + 1);
+                        if (!(sqdist(cy, cx, ky, kx) > r2)) far = false;
+                    }
+                }
+                const unsigned fmask = __ballot_sync(0xFFFFFFFFu, far);
+                if (far) S.vals[__popc(fmask & ((1u << lane) - 1))] = S.ks[lane];
+                __syncwarp();
+                double score = 0.0;
+                if (lane == 0) score = __ddiv_rn(np_sum(S.vals, __popc(fmask)), (double)PN_NUM_PARTS);
+                score = __shfl_sync(0xFFFFFFFFu, score, 0);
+
+                if (a.prm.min_pose_score == 0.0 || score >= a.prm.min_pose_score) {    // decode_multi.py:128
+                    if (lane == 0) out_ps[npose] = score;
+                    if (lane < PN_NUM_PARTS) {
+                        const size_t o = (size_t)npose * PN_NUM_PARTS + lane;
+                        out_ks[o] = S.ks[lane];
+                        out_kc[o * 2] = S.kc[lane][0];
+                        out_kc[o * 2 + 1] = S.kc[lane][1];
+                        out_ko[o * 2] = S.ko[lane][0];
+                        out_ko[o * 2 + 1] = S.ko[lane][1];
+                    }
+                    ++npose;
+                    __threadfence_block();
+                }
+                __syncwarp();
+            }
+            if (lane == 0) S.npose = npose;
+        }
+        __syncthreads();
+        npose = S.npose;
+        lo = pivot;
+        remaining -= cnt;
+        __syncthreads();
+    }
+    if (tid == 0) a.pose_counts[img] = npose;
+}
+
+}  // namespace pn
+
+// ---- C ABI ---------------------------------------------------------------------------------------
+using namespace pn;
+
+extern "C" int pn_candidates(const pn_map *heat, int n_img, int h, int wd, float score_threshold, uint64_t *keys,
+                             int capacity, int *counts, pn_stream_t stream) {
+    PN_CHECK_ARG(heat && heat->ptr && keys && counts, "pn_candidates: null pointer");
+    PN_CHECK_ARG(n_img > 0 && h > 0 && wd > 0 && capacity > 0, "pn_candidates: bad shape");
+    PN_CHECK_ARG((long long)PN_NUM_PARTS * h * wd < (1ll << 31), "pn_candidates: map too large");
+    PN_CHECK_ARG(n_img <= 65535, "pn_candidates: at most 65535 images per call");
+    cudaStream_t st = as_stream(stream);
+    PN_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * n_img, st));
+    dim3 grid(ceil_div(h * wd, 256), PN_NUM_PARTS, n_img);
+    candidates_kernel<<<grid, 256, 0, st>>>(*heat, h, wd, score_threshold, keys, capacity, counts);
+    PN_CHECK_LAUNCH();
+    return PN_OK;
+}
+
+extern "C" int pn_decode_greedy(const pn_map *heat, const pn_map *off, const pn_map *fwd, const pn_map *bwd, int n_img,
+                                int h, int wd, const uint64_t *keys, int capacity, const int *counts,
+                                const pn_decode_params *params, double *pose_scores, double *kp_scores,
+                                double *kp_coords, double *kp_offsets, int *pose_counts, pn_stream_t stream) {
+    PN_CHECK_ARG(heat && off && fwd && bwd && heat->ptr && off->ptr && fwd->ptr && bwd->ptr, "pn_decode_greedy: null map");
+    PN_CHECK_ARG(keys && counts && params && pose_scores && kp_scores && kp_coords && kp_offsets && pose_counts,
+                 "pn_decode_greedy: null pointer");
+    PN_CHECK_ARG(n_img > 0 && h > 0 && wd > 0 && capacity > 0, "pn_decode_greedy: bad shape");
+    PN_CHECK_ARG(params->max_pose_detections >= 0 && params->output_stride > 0, "pn_decode_greedy: bad params");
+    DecodeArgs a;
+    a.heat = *heat; a.off = *off; a.fwd = *fwd; a.bwd = *bwd;
+    a.h = h; a.w = wd; a.keys = keys; a.capacity = capacity; a.counts = counts; a.prm = *params;
+    a.pose_scores = pose_scores; a.kp_scores = kp_scores; a.kp_coords = kp_coords; a.kp_offsets = kp_offsets;
+    a.pose_counts = pose_counts;
+    decode_kernel<<<n_img, DEC_THREADS, 0, as_stream(stream)>>>(a);
+    PN_CHECK_LAUNCH();
+    return PN_OK;
+}

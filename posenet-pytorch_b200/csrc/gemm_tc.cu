@@ -1,0 +1,373 @@
+// B4 / H1, bf16 production path -- pointwise 1x1 convolutions and the fused 4-head projection as
+// tcgen05 tensor-core GEMMs:  D[M,N] = A[M,K] . W[N,K]^T  (bf16 in, fp32 accumulate in TMEM).
+// Replaces SeperableConv.pointwise + relu6 (posenet/models/mobilenet_v1.py:63,67) and the four head
+// convs + sigmoid (:151-154,158-161) of the reference.
+//
+// Shape of the kernel (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer   cp.async.bulk.tensor 2D loads of a 128 x 64 A tile (activations, pixel-
+//                              major == K-major) and a BLOCK_N x 64 W tile (OIHW 1x1 weight == K-major)
+//                              into a STAGES-deep 128B-swizzled shared-memory ring; OOB rows / K tail
+//                              are zero-filled by TMA, so ragged M (n*h*w) and K in {16,24,...} are free.
+//   warp 1      MMA issuer     one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128,
+//                              N=BLOCK_N, K=16) x 4 per stage, tcgen05.commit frees the stage / publishes
+//                              the accumulator.
+//   warp 2      TMEM allocator 2 x BLOCK_N fp32 columns: the accumulator is double-buffered so the
+//                              epilogue of tile i overlaps the mainloop of tile i+1.
+//   warps 4..7  epilogue       tcgen05.ld 32x32b (one accumulator row per thread), + bias, ReLU6 -> bf16
+//                              row-major store; or the head scatter (sigmoid on the 17 heatmap columns)
+//                              into four fp32 NCHW tensors, coalesced across the warp's 32 pixels.
+// All mbarrier waits are bounded: a protocol error traps instead of hanging the GPU.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pn {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;      // 64 bf16 = 128 B = one SWIZZLE_128B span
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_THREADS = 256;
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+
+__host__ __device__ constexpr int tc_stage_bytes(int block_n) { return (TC_BLOCK_M + block_n) * TC_BLOCK_K * 2; }
+__host__ __device__ constexpr int tc_stages(int block_n) {
+    return TC_SMEM_BUDGET / tc_stage_bytes(block_n) > 8 ? 8 : TC_SMEM_BUDGET / tc_stage_bytes(block_n);
+}
+__host__ __device__ constexpr int tc_tmem_cols(int block_n) {
+    return 2 * block_n <= 32 ? 32 : 2 * block_n <= 64 ? 64 : 2 * block_n <= 128 ? 128 : 2 * block_n <= 256 ? 256 : 512;
+}
+__host__ __device__ constexpr int tc_smem_bytes(int block_n) {
+    return tc_stages(block_n) * tc_stage_bytes(block_n) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+}
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000ll) {   // ~2 s: a pipeline protocol bug, never a slow tile
+            printf("posenet_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    // implies tcgen05.fence::before_thread_sync; arrives once on `bar` when all prior MMAs retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1" format):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams ep,
+               int M, int N, int K) {
+    constexpr int STAGES = tc_stages(BLOCK_N);
+    constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
+    constexpr int STAGE_BYTES = tc_stage_bytes(BLOCK_N);
+    constexpr uint32_t IDESC = make_idesc(TC_BLOCK_M, BLOCK_N);
+    static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024 B alignment
+    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;                  // 8 B each
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_m_tiles = (M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    const int num_n_tiles = N / BLOCK_N;
+    const int num_tiles = num_m_tiles * num_n_tiles;
+    const int num_k_blocks = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 128);      // every epilogue thread arrives
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)tc_tmem_cols(BLOCK_N))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    tma_load_2d(sa, &tmap_a, full_bar(stage), kb * TC_BLOCK_K, m_tile * TC_BLOCK_M);
+                    tma_load_2d(sa + A_BYTES, &tmap_b, full_bar(stage), kb * TC_BLOCK_K, n_tile * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                        // advancing 16 bf16 = 32 B along K inside the 128 B swizzle span
+                        const uint64_t adesc = make_smem_desc(sa + k * TC_UMMA_K * 2);
+                        const uint64_t bdesc = make_smem_desc(sb + k * TC_UMMA_K * 2);
+                        tc_mma_bf16(d_tmem, adesc, bdesc, IDESC, (uint32_t)((kb | k) != 0));
+                    }
+                    tc_commit(empty_bar(stage));                     // smem stage reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(acc));                           // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                                      // TMEM lane quarter this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = m_tile * TC_BLOCK_M + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 16) {
+                uint32_t v[16];
+                tc_ld16(taddr + (uint32_t)c, v);
+                tc_ld_wait();
+                const int col0 = n_tile * BLOCK_N + c;
+                if (row < M) {
+                    if (EPI == EPI_RELU6) {
+                        const float4 *bp = reinterpret_cast<const float4 *>(ep.bias + col0);
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b = __ldg(bp + j);
+                            const float o0 = relu6f(__uint_as_float(v[4 * j + 0]) + b.x);
+                            const float o1 = relu6f(__uint_as_float(v[4 * j + 1]) + b.y);
+                            const float o2 = relu6f(__uint_as_float(v[4 * j + 2]) + b.z);
+                            const float o3 = relu6f(__uint_as_float(v[4 * j + 3]) + b.w);
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1);
+                            __nv_bfloat162 h1 = __floats2bfloat162_rn(o2, o3);
+                            packed[2 * j] = *reinterpret_cast<uint32_t *>(&h0);
+                            packed[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h1);
+                        }
+                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(ep.y) + (size_t)row * N + col0);
+                        dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            store_head(ep, row, col0 + j, __uint_as_float(v[j]) + __ldg(ep.bias + col0 + j));
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)tc_tmem_cols(BLOCK_N))
+                     : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !p) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 2D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle, zero OOB fill.
+static int encode_2d(void *out, const void *base, int rows, int cols, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+        return PN_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %d cols %d box %d)", (int)r, rows, cols, box_rows);
+        return PN_ERR_CUDA;
+    }
+    return PN_OK;
+}
+
+// Largest supported tile width that divides N.
+static int pick_block_n(int n) {
+    static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
+    for (int c : cand)
+        if (n % c == 0) return c;
+    return 0;
+}
+
+int gemm_tc_prepare(GemmTc *g, const void *a, const void *w, int m, int k, int n, int epi) {
+    PN_CHECK_ARG(a && w && m > 0 && k > 0 && n > 0, "gemm(bf16): bad argument");
+    PN_CHECK_ARG(k % 8 == 0, "gemm(bf16): K must be a multiple of 8 (TMA 16-byte row pitch), got %d", k);
+    PN_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)w & 15) == 0, "gemm(bf16): operands must be 16-byte aligned");
+    const int bn = pick_block_n(n);
+    PN_CHECK_ARG(bn != 0, "gemm(bf16): N must be a multiple of 16 (got %d)", n);
+    g->m = m; g->k = k; g->n = n; g->block_n = bn; g->epi = epi;
+    int rc = encode_2d(g->tmap_a, a, m, k, TC_BLOCK_M);
+    if (rc != PN_OK) return rc;
+    return encode_2d(g->tmap_b, w, n, k, bn);
+}
+
+template <int BLOCK_N, int EPI>
+static int launch_tc(const GemmTc *g, const EpiParams &ep, cudaStream_t st) {
+    static bool configured = false;
+    auto kern = gemm_tc_kernel<BLOCK_N, EPI>;
+    constexpr int smem = tc_smem_bytes(BLOCK_N);
+    if (!configured) {
+        PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int tiles = ceil_div(g->m, TC_BLOCK_M) * (g->n / BLOCK_N);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, TC_THREADS, smem, st>>>(*reinterpret_cast<const CUtensorMap *>(g->tmap_a),
+                                         *reinterpret_cast<const CUtensorMap *>(g->tmap_b), ep, g->m, g->n, g->k);
+    PN_CHECK_LAUNCH();
+    return PN_OK;
+}
+
+int gemm_tc_launch(const GemmTc *g, const EpiParams &ep, cudaStream_t st) {
+#define PN_TC_CASE(BN)                                                       \
+    if (g->block_n == BN)                                                    \
+        return g->epi == EPI_RELU6 ? launch_tc<BN, EPI_RELU6>(g, ep, st) : launch_tc<BN, EPI_HEADS>(g, ep, st);
+    PN_TC_CASE(256)
+    PN_TC_CASE(192)
+    PN_TC_CASE(128)
+    PN_TC_CASE(96)
+    PN_TC_CASE(64)
+    PN_TC_CASE(48)
+    PN_TC_CASE(32)
+    PN_TC_CASE(16)
+#undef PN_TC_CASE
+    set_error("gemm(bf16): no kernel for block_n %d", g->block_n);
+    return PN_ERR_UNSUPPORTED;
+}
+
+}  // namespace pn

@@ -1,0 +1,102 @@
+"""Candidate extraction and greedy decode on the B200 must be BIT-EXACT against the oracle
+(which is pinned to the reference by tests/golden/decode.npz) when fed the same head tensors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import abi  # noqa: E402
+import posenet  # noqa: E402
+from golden.make_golden_cases import DEC_CASES, heads_for  # noqa: E402
+from oracle import decode as odec  # noqa: E402
+from oracle import synth  # noqa: E402
+
+DEV = "cuda"
+
+
+def gpu_decode(heads, stride, **kw):
+    return posenet.decode_multiple_poses(*[torch.from_numpy(t).to(DEV) for t in heads], output_stride=stride, **kw)
+
+
+def assert_same(res, ref, what=""):
+    for nm, a, b in zip(("pose_scores", "keypoint_scores", "keypoint_coords", "pose_offsets"), res, ref):
+        assert a.dtype == np.float64 and a.shape == b.shape, nm
+        assert np.array_equal(a, b), "%s %s: max diff %g" % (what, nm, np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("i", range(len(DEC_CASES)))
+def test_candidates_exact(i):
+    kind, h, w, stride, people, seed, P, thr, rad, minp, _patch, extra = DEC_CASES[i]
+    heat = heads_for(kind, h, w, stride, people, seed, extra)[0]
+    cs, ci = odec.part_candidates(heat, thr)
+    keys, counts = abi.candidates(torch.from_numpy(heat).unsqueeze(0).to(DEV), thr)
+    n = int(counts[0])
+    assert n == len(cs)
+    k = np.sort(keys[0, :n].cpu().numpy().view(np.uint64))
+    flat = (k & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    got = np.stack([flat // (h * w), (flat % (h * w)) // w, flat % w], axis=1).reshape(-1, 3)
+    assert np.array_equal(got, ci.reshape(-1, 3))          # same cells, same (score desc, index asc) order
+
+
+@pytest.mark.parametrize("i", range(len(DEC_CASES)))
+def test_decode_golden(golden_dir, i):
+    kind, h, w, stride, people, seed, P, thr, rad, minp, _patch, extra = DEC_CASES[i]
+    g = np.load(os.path.join(golden_dir, "decode.npz"))
+    heads = heads_for(kind, h, w, stride, people, seed, extra)
+    res = gpu_decode(heads, stride, max_pose_detections=P, score_threshold=thr, nms_radius=rad, min_pose_score=minp)
+    assert_same(res, [g["%s_%d" % (nm, i)] for nm in ("ps", "ks", "kc", "ko")], "golden case %d" % i)
+    assert all(a.flags.writeable for a in res)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_decode_random_vs_oracle(seed):
+    rng = np.random.default_rng(1000 + seed)
+    h, w = int(rng.integers(3, 40)), int(rng.integers(3, 40))
+    stride = int(rng.choice([8, 16, 32]))
+    heads = synth.random_heads(h, w, seed=seed, disp_scale=float(rng.uniform(5, 120)), off_scale=float(rng.uniform(1, 30)),
+                               zero_frac=float(rng.choice([0.0, 0.1])), tie_levels=int(rng.choice([0, 0, 8, 64])))
+    kw = dict(max_pose_detections=int(rng.integers(1, 40)), score_threshold=float(rng.uniform(0.0, 0.95)),
+              nms_radius=float(rng.choice([5, 20, 33.3])), min_pose_score=float(rng.choice([0.0, 0.1, 0.3])))
+    assert_same(gpu_decode(heads, stride, **kw), odec.decode_multiple_poses(*heads, stride, **kw), "seed %d %r" % (seed, kw))
+
+
+def test_decode_many_candidates_radix_path():
+    # plateaus: > 4096 candidates per image forces the multi-round radix selection
+    heads = synth.random_heads(61, 83, seed=3, tie_levels=6, disp_scale=60.0)
+    kw = dict(max_pose_detections=25, score_threshold=0.3, nms_radius=20, min_pose_score=0.45)
+    cs, _ = odec.part_candidates(heads[0], 0.3)
+    assert len(cs) > 3 * 4096
+    assert_same(gpu_decode(heads, 8, **kw), odec.decode_multiple_poses(*heads, 8, **kw))
+
+
+def test_decode_stress_config5():
+    # BASELINE config 5: 91x161 map, OS8, 50 people, max_pose_detections=50
+    heads = synth.people_heads(91, 161, 8, 50, seed=4)[:4]
+    kw = dict(max_pose_detections=50, score_threshold=0.5, nms_radius=20, min_pose_score=0.25)
+    assert_same(gpu_decode(heads, 8, **kw), odec.decode_multiple_poses(*heads, 8, **kw))
+
+
+def test_decode_channels_last_views_and_batch():
+    # the model returns NCHW tensors; callers may also hand over channels-last strided views
+    sets = [synth.people_heads(33, 33, 16, 4, seed=s)[:4] for s in range(3)]
+    batched = [torch.from_numpy(np.stack([s[j] for s in sets])).to(DEV) for j in range(4)]
+    strided = [t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2) for t in batched]
+    assert not strided[0].is_contiguous()
+    for variant in (batched, strided):
+        ps, ks, kc, ko, cnt = posenet.decode_multiple_poses_batch(*variant, output_stride=16, min_pose_score=0.25)
+        for b in range(3):
+            ref = odec.decode_multiple_poses(*sets[b], 16, min_pose_score=0.25)
+            assert_same([ps[b].cpu().numpy(), ks[b].cpu().numpy(), kc[b].cpu().numpy(), ko[b].cpu().numpy()], ref)
+            assert int(cnt[b]) == int((ref[0] != 0).sum())
+
+
+def test_decode_accepts_cpu_tensors_and_image_demo_usage():
+    heads = synth.people_heads(33, 33, 16, 3, seed=0)[:4]
+    res = posenet.decode_multi.decode_multiple_poses(*[torch.from_numpy(t) for t in heads], output_stride=16,
+                                                     max_pose_detections=10, min_pose_score=0.25)
+    assert len(res) == 4                                  # this fork returns a 4-tuple
+    res[2][...] *= np.array([1.5, 0.5])                   # image_demo.py:50 scales the coords in place
+    assert_same(res[:2], odec.decode_multiple_poses(*heads, 16, max_pose_detections=10, min_pose_score=0.25)[:2])
