@@ -239,11 +239,12 @@ def run_b200(args):
         x = host[i % n_sets].to(dev, non_blocking=True)
         ps, ks, kc, ko, cnt = step(x)
         return torch.cat([ps.reshape(-1), ks.reshape(-1), kc.reshape(-1), ko.reshape(-1)]).cpu()
-    for i in range(max(3, args.warmup)):
+    e2e_steps = 1 if args.skip_e2e else args.steps
+    for i in range(1 if args.skip_e2e else max(3, args.warmup)):
         rec = e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(e2e_steps):
         rec = e2e_step(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -251,7 +252,7 @@ def run_b200(args):
         t = torch.tensor([e2e_s], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_s = float(t)
-    e2e = {"value": world * batch * args.steps / e2e_s, "unit": "images/sec", "h2d_bytes_per_step": int(host[0].numel()),
+    e2e = {"value": world * batch * e2e_steps / e2e_s, "unit": "images/sec", "h2d_bytes_per_step": int(host[0].numel()),
            "d2h_bytes_per_step": int(rec.numel() * 8)}
 
     if rank != 0:
@@ -277,7 +278,7 @@ def run_b200(args):
                 "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": None,
                 "peak_source": pk["src"] + (" (sustained)" if top["bound"] == "tensor" else "")}
     cpu = cpu_reference_run("c2" if args.workload == "c2" else args.workload, images_per_step=4, steps=3, warmup=1) \
-        if world == 1 else None
+        if (world == 1 and not args.skip_cpu) else None
     launches = model.num_launches(batch, H, W, True) + 2
     line = {"metric": METRIC, "value": round(value, 1), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
@@ -303,6 +304,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug)")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
