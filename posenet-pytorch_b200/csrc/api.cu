@@ -104,7 +104,7 @@ int pn_pwconv_gemm(const void *a, const void *w, const float *bias, void *y, int
     if (dtype == PN_F32) return launch_gemm_simt((const float *)a, (const float *)w, m, k, n, EPI_RELU6, ep, as_stream(stream));
     PN_CHECK_ARG(dtype == PN_BF16, "pn_pwconv_gemm: bad dtype %d", dtype);
     GemmTc g;
-    int rc = gemm_tc_prepare(&g, a, w, m, k, n, EPI_RELU6);
+    int rc = gemm_tc_prepare(&g, a, w, y, m, k, n, EPI_RELU6);
     if (rc != PN_OK) return rc;
     return gemm_tc_launch(&g, ep, as_stream(stream));
 }
@@ -121,7 +121,7 @@ int pn_heads_gemm(const void *a, const void *w, const float *bias, float *heat, 
         return launch_gemm_simt((const float *)a, (const float *)w, m, k, PN_HEAD_ROWS, EPI_HEADS, ep, as_stream(stream));
     PN_CHECK_ARG(dtype == PN_BF16, "pn_heads_gemm: bad dtype %d", dtype);
     GemmTc g;
-    int rc = gemm_tc_prepare(&g, a, w, m, k, PN_HEAD_ROWS, EPI_HEADS);
+    int rc = gemm_tc_prepare(&g, a, w, nullptr, m, k, PN_HEAD_ROWS, EPI_HEADS);
     if (rc != PN_OK) return rc;
     return gemm_tc_launch(&g, ep, as_stream(stream));
 }
@@ -185,14 +185,14 @@ int pn_plan_create(const pn_net_desc *desc, void *arena, size_t arena_bytes, pn_
         p->launches += 2;
         if (desc->dtype == PN_BF16) {
             const int m = desc->n * p->steps[i].h_out * p->steps[i].w_out;
-            rc = gemm_tc_prepare(&p->steps[i].tc, p->buf[1], L.pw_w, m, L.cin, L.cout, EPI_RELU6);
+            rc = gemm_tc_prepare(&p->steps[i].tc, p->buf[1], L.pw_w, p->buf[0], m, L.cin, L.cout, EPI_RELU6);
             if (rc != PN_OK) { delete p; return rc; }
         }
     }
     PN_CHECK_ARG(desc->head_w && desc->head_b, "pn_plan_create: null head weights");
     if (desc->dtype == PN_BF16) {
         const int m = desc->n * p->out_h * p->out_w;
-        rc = gemm_tc_prepare(&p->head_tc, p->buf[0], desc->head_w, m, desc->layers[desc->num_layers - 1].cout, PN_HEAD_ROWS, EPI_HEADS);
+        rc = gemm_tc_prepare(&p->head_tc, p->buf[0], desc->head_w, nullptr, m, desc->layers[desc->num_layers - 1].cout, PN_HEAD_ROWS, EPI_HEADS);
         if (rc != PN_OK) { delete p; return rc; }
     }
     p->launches += 1;

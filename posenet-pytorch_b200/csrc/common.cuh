@@ -112,9 +112,10 @@ int launch_gemm_simt(const float *a, const float *w, int m, int k, int n, int ep
 struct GemmTc {
     alignas(64) unsigned char tmap_a[128];
     alignas(64) unsigned char tmap_b[128];
+    alignas(64) unsigned char tmap_c[128];   // output map (TMA-store epilogue), bound to one output buffer
     int m, k, n, block_n, epi;
 };
-int gemm_tc_prepare(GemmTc *g, const void *a, const void *w, int m, int k, int n, int epi);
+int gemm_tc_prepare(GemmTc *g, const void *a, const void *w, void *y, int m, int k, int n, int epi);
 int gemm_tc_launch(const GemmTc *g, const EpiParams &ep, cudaStream_t s);
 
 }  // namespace pn

@@ -13,11 +13,15 @@
 //                              the accumulator.
 //   warp 2      TMEM allocator 2 x BLOCK_N fp32 columns: the accumulator is double-buffered so the
 //                              epilogue of tile i overlaps the mainloop of tile i+1.
-//   warps 4..7  epilogue       tcgen05.ld 32x32b (one accumulator row per thread), + bias, ReLU6 -> bf16
-//                              row-major store; or the head scatter (sigmoid on the 17 heatmap columns)
-//                              into four fp32 NCHW tensors, coalesced across the warp's 32 pixels.
+//   warps 4..7  epilogue       tcgen05.ld 32x32b (one accumulator row per thread), + bias, ReLU6 -> bf16,
+//                              staged through 128B-swizzled shared memory in 128 x 64 panels and written
+//                              with TMA stores (full-line writes; the M tail is clipped by the tensor map);
+//                              the TMEM accumulator is released as soon as its last column is in registers.
+//                              Heads: scatter (sigmoid on the 17 heatmap columns) into four fp32 NCHW
+//                              tensors, coalesced across the warp's 32 pixels.
 // All mbarrier waits are bounded: a protocol error traps instead of hanging the GPU.
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -27,7 +31,9 @@ constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;      // 64 bf16 = 128 B = one SWIZZLE_128B span
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_THREADS = 256;
-constexpr int TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_SMEM_MAX = 232448;           // 227 KB dynamic shared memory per CTA
+constexpr int TC_STAGING_BYTES = 2 * 16384;   // two 128 x 64 bf16 output panels (ping-pong)
+constexpr int TC_SMEM_BUDGET = TC_SMEM_MAX - 1024 /*alignment slack*/ - 256 /*barriers*/ - TC_STAGING_BYTES;
 
 __host__ __device__ constexpr int tc_stage_bytes(int block_n) { return (TC_BLOCK_M + block_n) * TC_BLOCK_K * 2; }
 __host__ __device__ constexpr int tc_stages(int block_n) {
@@ -37,7 +43,7 @@ __host__ __device__ constexpr int tc_tmem_cols(int block_n) {
     return 2 * block_n <= 32 ? 32 : 2 * block_n <= 64 ? 64 : 2 * block_n <= 128 ? 128 : 2 * block_n <= 256 ? 256 : 512;
 }
 __host__ __device__ constexpr int tc_smem_bytes(int block_n) {
-    return tc_stages(block_n) * tc_stage_bytes(block_n) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    return tc_stages(block_n) * tc_stage_bytes(block_n) + TC_STAGING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -100,6 +106,31 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1" format):
@@ -117,24 +148,27 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 // ---- the kernel ----------------------------------------------------------------------------------
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams ep,
-               int M, int N, int K) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c, EpiParams ep, int M, int N, int K) {
     constexpr int STAGES = tc_stages(BLOCK_N);
     constexpr int A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
     constexpr int STAGE_BYTES = tc_stage_bytes(BLOCK_N);
     constexpr uint32_t IDESC = make_idesc(TC_BLOCK_M, BLOCK_N);
     static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
+    constexpr bool TMA_STORE = (EPI == EPI_RELU6) && (BLOCK_N % 64 == 0);
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024 B alignment
-    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;                  // 8 B each
+    const uint32_t staging = smem_base + STAGES * STAGE_BYTES;              // 2 x 16 KB, 1024 B aligned
+    const uint32_t bars = staging + TC_STAGING_BYTES;                        // 8 B each
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem_gen + STAGES * STAGE_BYTES + TC_STAGING_BYTES + 8 * (2 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -146,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        if (TMA_STORE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -220,50 +255,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;                                      // TMEM lane quarter this warp may read
-        int acc = 0;
+        const int row_in_tile = q * 32 + lane;
+        const bool issuer = (threadIdx.x == 128);                    // one thread owns the bulk-store groups
+        int acc = 0, buf = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_tile = tile / num_n_tiles, n_tile = tile % num_n_tiles;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const int row = m_tile * TC_BLOCK_M + q * 32 + lane;
+            const int row = m_tile * TC_BLOCK_M + row_in_tile;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            if constexpr (TMA_STORE) {
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 16) {
-                uint32_t v[16];
-                tc_ld16(taddr + (uint32_t)c, v);
-                tc_ld_wait();
-                const int col0 = n_tile * BLOCK_N + c;
-                if (row < M) {
-                    if (EPI == EPI_RELU6) {
-                        const float4 *bp = reinterpret_cast<const float4 *>(ep.bias + col0);
-                        uint32_t packed[8];
+                for (int p = 0; p < BLOCK_N / 64; ++p) {
+                    uint32_t v[64];
+                    tc_ld32(taddr + (uint32_t)(p * 64), v);
+                    tc_ld32(taddr + (uint32_t)(p * 64 + 32), v + 32);
+                    tc_ld_wait();
+                    if (p == BLOCK_N / 64 - 1) {                     // accumulator fully in registers: hand it back
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+                    if (issuer) bulk_wait_read<1>();                 // the store that last read this buffer is done
+                    epi_bar_sync();
+                    const int col0 = n_tile * BLOCK_N + p * 64;
+                    const float4 *bp = reinterpret_cast<const float4 *>(ep.bias + col0);
+                    const uint32_t srow = staging + (uint32_t)buf * 16384u + (uint32_t)row_in_tile * 128u;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b = __ldg(bp + j);
-                            const float o0 = relu6f(__uint_as_float(v[4 * j + 0]) + b.x);
-                            const float o1 = relu6f(__uint_as_float(v[4 * j + 1]) + b.y);
-                            const float o2 = relu6f(__uint_as_float(v[4 * j + 2]) + b.z);
-                            const float o3 = relu6f(__uint_as_float(v[4 * j + 3]) + b.w);
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1);
-                            __nv_bfloat162 h1 = __floats2bfloat162_rn(o2, o3);
-                            packed[2 * j] = *reinterpret_cast<uint32_t *>(&h0);
-                            packed[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h1);
+                    for (int c = 0; c < 8; ++c) {                    // 8 columns -> one 16 B chunk, 128B-swizzled
+                        const float4 b0 = __ldg(bp + 2 * c), b1 = __ldg(bp + 2 * c + 1);
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 0]) + b0.x),
+                                                                        relu6f(__uint_as_float(v[8 * c + 1]) + b0.y));
+                        const __nv_bfloat162 h1 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 2]) + b0.z),
+                                                                        relu6f(__uint_as_float(v[8 * c + 3]) + b0.w));
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 4]) + b1.x),
+                                                                        relu6f(__uint_as_float(v[8 * c + 5]) + b1.y));
+                        const __nv_bfloat162 h3 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 6]) + b1.z),
+                                                                        relu6f(__uint_as_float(v[8 * c + 7]) + b1.w));
+                        st_shared_v4(srow + (uint32_t)((c ^ (row_in_tile & 7)) << 4), *reinterpret_cast<const uint32_t *>(&h0),
+                                     *reinterpret_cast<const uint32_t *>(&h1), *reinterpret_cast<const uint32_t *>(&h2),
+                                     *reinterpret_cast<const uint32_t *>(&h3));
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
+                    epi_bar_sync();
+                    if (issuer) {
+                        tma_store_2d(&tmap_c, staging + (uint32_t)buf * 16384u, col0, m_tile * TC_BLOCK_M);
+                        bulk_commit();
+                    }
+                    buf ^= 1;
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 16) {
+                    uint32_t v[16];
+                    tc_ld16(taddr + (uint32_t)c, v);
+                    tc_ld_wait();
+                    const int col0 = n_tile * BLOCK_N + c;
+                    if (row < M) {
+                        if (EPI == EPI_RELU6) {
+                            const float4 *bp = reinterpret_cast<const float4 *>(ep.bias + col0);
+                            uint32_t packed[8];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 b = __ldg(bp + j);
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[4 * j + 0]) + b.x),
+                                                                          relu6f(__uint_as_float(v[4 * j + 1]) + b.y));
+                                __nv_bfloat162 h1 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[4 * j + 2]) + b.z),
+                                                                          relu6f(__uint_as_float(v[4 * j + 3]) + b.w));
+                                packed[2 * j] = *reinterpret_cast<uint32_t *>(&h0);
+                                packed[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h1);
+                            }
+                            uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(ep.y) + (size_t)row * N + col0);
+                            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                store_head(ep, row, col0 + j, __uint_as_float(v[j]) + __ldg(ep.bias + col0 + j));
                         }
-                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(ep.y) + (size_t)row * N + col0);
-                        dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                        dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            store_head(ep, row, col0 + j, __uint_as_float(v[j]) + __ldg(ep.bias + col0 + j));
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));
             }
-            tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (TMA_STORE && issuer) bulk_wait_all();                    // smem must outlive the last bulk store
     }
 
     tc_fence_before();
@@ -324,7 +401,7 @@ static int pick_block_n(int n) {
     return 0;
 }
 
-int gemm_tc_prepare(GemmTc *g, const void *a, const void *w, int m, int k, int n, int epi) {
+int gemm_tc_prepare(GemmTc *g, const void *a, const void *w, void *y, int m, int k, int n, int epi) {
     PN_CHECK_ARG(a && w && m > 0 && k > 0 && n > 0, "gemm(bf16): bad argument");
     PN_CHECK_ARG(k % 8 == 0, "gemm(bf16): K must be a multiple of 8 (TMA 16-byte row pitch), got %d", k);
     PN_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)w & 15) == 0, "gemm(bf16): operands must be 16-byte aligned");
@@ -333,7 +410,14 @@ int gemm_tc_prepare(GemmTc *g, const void *a, const void *w, int m, int k, int n
     g->m = m; g->k = k; g->n = n; g->block_n = bn; g->epi = epi;
     int rc = encode_2d(g->tmap_a, a, m, k, TC_BLOCK_M);
     if (rc != PN_OK) return rc;
-    return encode_2d(g->tmap_b, w, n, k, bn);
+    rc = encode_2d(g->tmap_b, w, n, k, bn);
+    if (rc != PN_OK) return rc;
+    if (epi == EPI_RELU6 && bn % 64 == 0) {          // output written with TMA stores in 128 x 64 panels
+        PN_CHECK_ARG(y && ((uintptr_t)y & 15) == 0, "gemm(bf16): output must be 16-byte aligned");
+        return encode_2d(g->tmap_c, y, m, n, TC_BLOCK_M);
+    }
+    memcpy(g->tmap_c, g->tmap_a, sizeof(g->tmap_c));  // unused by this instantiation; keep it a valid map
+    return PN_OK;
 }
 
 template <int BLOCK_N, int EPI>
@@ -348,7 +432,8 @@ static int launch_tc(const GemmTc *g, const EpiParams &ep, cudaStream_t st) {
     const int tiles = ceil_div(g->m, TC_BLOCK_M) * (g->n / BLOCK_N);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     kern<<<grid, TC_THREADS, smem, st>>>(*reinterpret_cast<const CUtensorMap *>(g->tmap_a),
-                                         *reinterpret_cast<const CUtensorMap *>(g->tmap_b), ep, g->m, g->n, g->k);
+                                         *reinterpret_cast<const CUtensorMap *>(g->tmap_b),
+                                         *reinterpret_cast<const CUtensorMap *>(g->tmap_c), ep, g->m, g->n, g->k);
     PN_CHECK_LAUNCH();
     return PN_OK;
 }
