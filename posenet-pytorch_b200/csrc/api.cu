@@ -47,6 +47,7 @@ struct pn_plan {
     struct Step {
         int h_in, w_in, h_out, w_out;
         GemmTc tc;          // bf16 only
+        DwOp dw;
     } steps[16];
     GemmTc head_tc;
     int launches;
@@ -183,6 +184,9 @@ int pn_plan_create(const pn_net_desc *desc, void *arena, size_t arena_bytes, pn_
         PN_CHECK_ARG(L.pw_w && L.pw_b && (i == 0 || (L.dw_w && L.dw_b)), "pn_plan_create: layer %d has null weights", i);
         if (i == 0) { p->launches += 1; continue; }
         p->launches += 2;
+        rc = dw_prepare(&p->steps[i].dw, p->buf[0], desc->n, p->steps[i].h_in, p->steps[i].w_in, L.cin, L.stride, L.dilation,
+                        desc->dtype);
+        if (rc != PN_OK) { delete p; return rc; }
         if (desc->dtype == PN_BF16) {
             const int m = desc->n * p->steps[i].h_out * p->steps[i].w_out;
             rc = gemm_tc_prepare(&p->steps[i].tc, p->buf[1], L.pw_w, p->buf[0], m, L.cin, L.cout, EPI_RELU6);
@@ -220,7 +224,7 @@ static int plan_run(pn_plan *p, const void *input, float *heat, float *off, floa
             PN_MARK();
             continue;
         }
-        rc = launch_dwconv(p->buf[0], L.dw_w, L.dw_b, p->buf[1], d.n, S.h_in, S.w_in, L.cin, L.stride, L.dilation, d.dtype, st);
+        rc = dw_launch(&S.dw, L.dw_w, L.dw_b, p->buf[1], st);
         if (rc != PN_OK) return rc;
         PN_MARK();
         EpiParams ep = {};

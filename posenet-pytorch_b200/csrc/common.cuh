@@ -105,6 +105,16 @@ int launch_stem(const void *x, bool x_is_u8, const float *w, const float *b, voi
                 int cout, int stride, int out_dtype, cudaStream_t s);
 int launch_dwconv(const void *x, const float *w, const float *b, void *y, int n, int h, int wd, int c,
                   int stride, int dilation, int dtype, cudaStream_t s);
+// depthwise op bound to one input buffer: tensor map + tile geometry are computed once (per plan, or per call)
+struct DwOp {
+    alignas(64) unsigned char tmap[128];
+    alignas(8) unsigned char geom[128];
+    const void *x;
+    int n, h, w, c, stride, dil, dtype, ho, wo;
+    bool use_tma;
+};
+int dw_prepare(DwOp *op, const void *x, int n, int h, int wd, int c, int stride, int dil, int dtype);
+int dw_launch(const DwOp *op, const float *w, const float *b, void *y, cudaStream_t s);
 int launch_gemm_simt(const float *a, const float *w, int m, int k, int n, int epi, const EpiParams &ep,
                      cudaStream_t s);
 

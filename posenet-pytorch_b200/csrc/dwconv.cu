@@ -3,257 +3,372 @@
 // stride / dilation / padding rule of _to_output_strided_layers and _get_padding (:8-44):
 // pad = ((s-1) + 2d) / 2, symmetric zero padding, out = (in + 2p - 2d - 1)/s + 1.
 //
-// HBM-bound (9 MAC per element moved), so the kernel is organised around instruction count:
-// a thread owns CH = 4 consecutive channels and a PX = 4 pixel wide column strip of TH output rows.
-//   * stride 1, dilation 1 (most layers): the thread marches DOWN its strip.  Each input row is
-//     loaded once (6 vectors), converted to fp32 once, and scattered into three rotating
-//     accumulator rows (ky = 0, 1, 2), so every input element is fetched once per thread instead of
-//     9 times, and the next row is prefetched while the current one is being consumed.
-//   * strided / atrous layers: same strip ownership (weights stay in registers), three rows gathered
-//     per output row.
-// Consecutive lanes take consecutive channel groups, so every warp-level load / store is a run of
-// contiguous NHWC bytes; the work list is flattened over (image, row block, strip, channel group),
-// so the odd map sizes (257, 129, 65, 33 ...) cost at most one partial strip per row.
-#include <type_traits>
+// HBM-bound (9 MAC per element moved), so the kernel is a TMA-fed streaming pipeline:
+//   * the input is described by ONE 4-D tensor map (C, W, H, N).  A work item is an output tile of
+//     TH x TW pixels x CB channels of one image; its input patch (with the 3x3 halo) is one
+//     cp.async.bulk.tensor.4d box.  Out-of-bounds box elements are zero-filled by the TMA unit, which
+//     IS the convolution's zero padding, so there is no border code at all.
+//   * persistent CTAs (1 per SM): one producer warp keeps a 2-4 deep mbarrier ring of patches in
+//     flight (~100+ KB per SM outstanding with no register cost), fifteen consumer warps compute.
+//   * a group of CB/8 (bf16) lanes owns one pixel's channel block, 16 B per lane; a group computes a
+//     strip of 4 (stride 1) or 2 (stride 2) adjacent output pixels so that each shared-memory vector
+//     is loaded once per strip and tap row, math is packed FFMA2 (fma.rn.f32x2), and the result
+//     leaves as 16 B stores that cover whole 32 B sectors.
+// The tile shape is chosen per layer on the host (odd map sizes 257, 129, 65, 33, 17 ...).
+#include <string.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace pn {
 
-constexpr int DW_PX = 4;
-constexpr int DW_CH = 4;
+constexpr int DW_CONSUMER_WARPS = 15;           // + 1 producer = 512 threads -> 128 registers each
+constexpr int DW_CONSUMERS = DW_CONSUMER_WARPS * 32;
+constexpr int DW_THREADS = DW_CONSUMERS + 32;        // + the producer warp
+constexpr int DW_MAX_STAGES = 4;
+constexpr int DW_SMEM_PER_CTA = 200 * 1024;          // one CTA per SM
 
-template <typename T> struct Vec4;
-template <> struct Vec4<float> {
-    typedef float4 raw;
-    static __device__ __forceinline__ raw zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-    static __device__ __forceinline__ raw load(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-    static __device__ __forceinline__ void unpack(const raw &r, float (&v)[4]) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
-    static __device__ __forceinline__ void store_relu6(float *p, const float (&v)[4]) {
-        *reinterpret_cast<float4 *>(p) = make_float4(relu6f(v[0]), relu6f(v[1]), relu6f(v[2]), relu6f(v[3]));
+template <typename T> struct Vec16;                  // one 16-byte channel vector
+template <> struct Vec16<float> {
+    static constexpr int VE = 4;
+    static __device__ __forceinline__ void unpack(const uint4 &r, float2 (&v)[2]) {
+        v[0] = make_float2(__uint_as_float(r.x), __uint_as_float(r.y));
+        v[1] = make_float2(__uint_as_float(r.z), __uint_as_float(r.w));
+    }
+    static __device__ __forceinline__ void store_relu6(float *p, const float2 (&v)[2]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(relu6f(v[0].x), relu6f(v[0].y), relu6f(v[1].x), relu6f(v[1].y));
     }
 };
-template <> struct Vec4<__nv_bfloat16> {
-    typedef uint2 raw;
-    static __device__ __forceinline__ raw zero() { return make_uint2(0u, 0u); }
-    static __device__ __forceinline__ raw load(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
-    static __device__ __forceinline__ void unpack(const raw &r, float (&v)[4]) {   // bf16 -> f32 is a 16-bit shift
-        v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
-        v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+template <> struct Vec16<__nv_bfloat16> {
+    static constexpr int VE = 8;
+    static __device__ __forceinline__ void unpack(const uint4 &r, float2 (&v)[4]) {   // bf16 -> f32 is a 16-bit shift
+        v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+        v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+        v[2] = make_float2(__uint_as_float(r.z << 16), __uint_as_float(r.z & 0xffff0000u));
+        v[3] = make_float2(__uint_as_float(r.w << 16), __uint_as_float(r.w & 0xffff0000u));
     }
-    static __device__ __forceinline__ void store_relu6(__nv_bfloat16 *p, const float (&v)[4]) {
+    static __device__ __forceinline__ void store_relu6(__nv_bfloat16 *p, const float2 (&v)[4]) {
         // round first, clamp after: 0 and 6 are exact in bf16 and rounding is monotone, so this equals
         // clamp-then-round while the clamp runs on packed pairs
         const __nv_bfloat162 lo = __floats2bfloat162_rn(0.f, 0.f), hi = __floats2bfloat162_rn(6.f, 6.f);
-        __nv_bfloat162 a = __hmin2(__hmax2(__floats2bfloat162_rn(v[0], v[1]), lo), hi);
-        __nv_bfloat162 b = __hmin2(__hmax2(__floats2bfloat162_rn(v[2], v[3]), lo), hi);
-        *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h = __hmin2(__hmax2(__floats2bfloat162_rn(v[j].x, v[j].y), lo), hi);
+            o[j] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 };
 
 struct DwGeom {
-    int n, h, w, c, ho, wo, dil, pad, th, strips, yblocks;
+    int n, h, w, c, ho, wo, pad;
+    int cb, lpp;               // channels per block, lanes per pixel (cb / VE)
+    int th, tw;                // output tile
+    int thi, twi;              // input box (twi possibly padded to stagger shared-memory banks)
+    int spr, nstrips;          // strips per tile row, strips per tile
+    int tiles_x, tiles_y, cblocks;
+    int stages;
+    unsigned stage_bytes;      // distance between stages (128 B aligned)
+    unsigned box_bytes;        // bytes one TMA box delivers
+    long long items;
 };
 
-// flat thread id -> (channel group, strip, row block, image)
-__device__ __forceinline__ bool dw_decompose(const DwGeom &g, int &c0, int &ox0, int &oy0, int &img) {
-    const int cg = g.c / DW_CH;
-    const long long total = (long long)g.n * g.yblocks * g.strips * cg;
+// item -> (channel block, tile x, tile y, image); channel blocks fastest so that neighbouring CTAs share halos in L2
+__device__ __forceinline__ void dw_item(const DwGeom &g, long long it, int &cbk, int &tx, int &ty, int &img) {
+    cbk = (int)(it % g.cblocks);
+    long long r = it / g.cblocks;
+    tx = (int)(r % g.tiles_x);
+    r /= g.tiles_x;
+    ty = (int)(r % g.tiles_y);
+    img = (int)(r / g.tiles_y);
+}
+
+template <typename T, int S, int D>
+__global__ void __launch_bounds__(DW_THREADS, 1)
+dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ w, const float *__restrict__ bias,
+                  T *__restrict__ y, const DwGeom g) {
+    constexpr int VE = Vec16<T>::VE;
+    constexpr int VP = VE / 2;                            // float2 pairs per vector
+    constexpr int PXT = (S == 1) ? 4 : 2;                 // output pixels per strip
+    constexpr int NCOLS = (PXT - 1) * S + 2 * D + 1;      // input columns a strip touches
+
+    extern __shared__ uint8_t dw_smem_raw[];
+    const uint32_t base = (smem_u32(dw_smem_raw) + 127u) & ~127u;
+    auto full_bar = [&](int s) { return base + 8u * s; };
+    auto empty_bar = [&](int s) { return base + 8u * (DW_MAX_STAGES + s); };
+    auto stage_addr = [&](int s) { return base + 128u + (uint32_t)s * g.stage_bytes; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), DW_CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == DW_CONSUMER_WARPS) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long it = blockIdx.x; it < g.items; it += gridDim.x) {
+                int cbk, tx, ty, img;
+                dw_item(g, it, cbk, tx, ty, img);
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), g.box_bytes);
+                tma_load_4d(stage_addr(s), &tmap, full_bar(s), cbk * g.cb, tx * g.tw * S - g.pad, ty * g.th * S - g.pad, img);
+                if (++s == g.stages) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    const int cl = threadIdx.x % g.lpp;                   // which 16 B of the pixel's channel block
+    const int group = threadIdx.x / g.lpp;
+    const int ngroups = DW_CONSUMERS / g.lpp;
+    const uint32_t pixb = (uint32_t)g.cb * sizeof(T);     // bytes per pixel in the patch
+    const uint32_t rowb = (uint32_t)g.twi * pixb;
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long it = blockIdx.x; it < g.items; it += gridDim.x) {
+        int cbk, tx, ty, img;
+        dw_item(g, it, cbk, tx, ty, img);
+        const int c0 = cbk * g.cb + cl * VE;
+        float2 bs[VP];
+#pragma unroll
+        for (int j = 0; j < VP; j += 2) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + 2 * j));
+            bs[j] = make_float2(b4.x, b4.y);
+            bs[j + 1] = make_float2(b4.z, b4.w);
+        }
+        mbar_wait(full_bar(s), ph);
+        const uint32_t patch = stage_addr(s) + (uint32_t)cl * 16u;
+
+        for (int q = group; q < g.nstrips; q += ngroups) {
+            const int r = q % g.th, sg = q / g.th;        // row-fastest: neighbouring groups sit on neighbouring rows
+            const int oy = ty * g.th + r, ox0 = tx * g.tw + sg * PXT;
+            if (oy >= g.ho || ox0 >= g.wo) continue;
+            float2 acc[PXT][VP];
+#pragma unroll
+            for (int p = 0; p < PXT; ++p)
+#pragma unroll
+                for (int j = 0; j < VP; ++j) acc[p][j] = bs[j];
+            const uint32_t strip = patch + (uint32_t)(r * S) * rowb + (uint32_t)(sg * PXT * S) * pixb;
+#pragma unroll 1
+            for (int ky = 0; ky < 3; ++ky) {                  // not unrolled: keeps one tap row of weights live
+                float2 wv[3][VP];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int j = 0; j < VP; j += 2) {
+                        const float4 w4 = __ldg(reinterpret_cast<const float4 *>(w + (size_t)(ky * 3 + kx) * g.c + c0 + 2 * j));
+                        wv[kx][j] = make_float2(w4.x, w4.y);
+                        wv[kx][j + 1] = make_float2(w4.z, w4.w);
+                    }
+                const uint32_t rowp = strip + (uint32_t)(ky * D) * rowb;
+#pragma unroll
+                for (int col = 0; col < NCOLS; ++col) {
+                    bool used = false;
+#pragma unroll
+                    for (int p = 0; p < PXT; ++p)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) used |= (p * S + kx * D == col);
+                    if (!used) continue;
+                    float2 v[VP];
+                    Vec16<T>::unpack(ld_shared_v4(rowp + (uint32_t)col * pixb), v);
+#pragma unroll
+                    for (int p = 0; p < PXT; ++p)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+                            if (p * S + kx * D == col) {
+#pragma unroll
+                                for (int j = 0; j < VP; ++j) acc[p][j] = ffma2(v[j], wv[kx][j], acc[p][j]);
+                            }
+                }
+            }
+            T *op = y + (((size_t)img * g.ho + oy) * g.wo + ox0) * g.c + c0;
+#pragma unroll
+            for (int p = 0; p < PXT; ++p)
+                if (ox0 + p < g.wo) Vec16<T>::store_relu6(op + (size_t)p * g.c, acc[p]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));         // this warp no longer reads the patch
+        if (++s == g.stages) { s = 0; ph ^= 1; }
+    }
+}
+
+// ---- fallback for (stride, dilation) pairs the network tables never produce: direct global gathers ----------
+template <typename T>
+__global__ void __launch_bounds__(128) dwconv_direct_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                                                            const float *__restrict__ bias, T *__restrict__ y, int n, int h,
+                                                            int wd, int c, int ho, int wo, int stride, int dil, int pad) {
+    constexpr int VE = Vec16<T>::VE, VP = VE / 2;
+    const int cg = c / VE;
+    const long long total = (long long)n * ho * wo * cg;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return false;
-    c0 = (int)(t % cg) * DW_CH;
+    if (t >= total) return;
+    const int c0 = (int)(t % cg) * VE;
     long long r = t / cg;
-    ox0 = (int)(r % g.strips) * DW_PX;
-    r /= g.strips;
-    oy0 = (int)(r % g.yblocks) * g.th;
-    img = (int)(r / g.yblocks);
-    return true;
-}
-
-__device__ __forceinline__ void dw_load_weights(const float *__restrict__ w, const float *__restrict__ bias, int c, int c0,
-                                                float (&wt)[9][DW_CH], float (&bs)[DW_CH]) {
+    const int ox = (int)(r % wo);
+    r /= wo;
+    const int oy = (int)(r % ho), img = (int)(r / ho);
+    float2 acc[VP];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(w + (size_t)k * c + c0));
-        wt[k][0] = a.x; wt[k][1] = a.y; wt[k][2] = a.z; wt[k][3] = a.w;
-    }
-    const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + c0));
-    bs[0] = b.x; bs[1] = b.y; bs[2] = b.z; bs[3] = b.w;
-}
-
-// ---- stride 1, dilation 1: marching column strip with rotating accumulator rows ------------------------
-template <typename T>
-__global__ void __launch_bounds__(128) dwconv_s1_kernel(const T *__restrict__ x, const float *__restrict__ w,
-                                                        const float *__restrict__ bias, T *__restrict__ y, DwGeom g) {
-    typedef typename Vec4<T>::raw Raw;
-    constexpr int NC = DW_PX + 2;                 // input columns ox0-1 .. ox0+PX
-    int c0, ox0, oy0, img;
-    if (!dw_decompose(g, c0, ox0, oy0, img)) return;
-    float wt[9][DW_CH], bs[DW_CH];
-    dw_load_weights(w, bias, g.c, c0, wt, bs);
-
-    const T *ximg = x + (size_t)img * g.h * g.w * g.c + c0;
-    T *yimg = y + (size_t)img * g.ho * g.wo * g.c + c0;
-    bool colok[NC];
+    for (int j = 0; j < VP; ++j) acc[j] = make_float2(bias[c0 + 2 * j], bias[c0 + 2 * j + 1]);
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * stride - pad + ky * dil;
+        if (iy < 0 || iy >= h) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * stride - pad + kx * dil;
+            if (ix < 0 || ix >= wd) continue;
+            float2 v[VP];
+            Vec16<T>::unpack(__ldg(reinterpret_cast<const uint4 *>(x + (((size_t)img * h + iy) * wd + ix) * c + c0)), v);
+            const float *wp = w + (size_t)(ky * 3 + kx) * c + c0;
 #pragma unroll
-    for (int cc = 0; cc < NC; ++cc) colok[cc] = (ox0 - 1 + cc) >= 0 && (ox0 - 1 + cc) < g.w;
-    const int ylast = min(oy0 + g.th, g.ho) - 1;  // last output row of this strip
-    const T *colbase = ximg + (ptrdiff_t)(ox0 - 1) * g.c;
-
-    auto load_row = [&](int iy, Raw (&r)[NC]) {
-        const bool rowok = iy >= 0 && iy < g.h;
-        const T *rp = colbase + (ptrdiff_t)iy * g.w * g.c;
-#pragma unroll
-        for (int cc = 0; cc < NC; ++cc) r[cc] = (rowok && colok[cc]) ? Vec4<T>::load(rp + (ptrdiff_t)cc * g.c) : Vec4<T>::zero();
-    };
-
-    float acc[3][DW_PX][DW_CH];
-    Raw cur[NC], nxt[NC];
-    load_row(oy0 - 1, cur);
-
-    // One step consumes input row iy: it finishes output row iy-1 (ky = 2), continues row iy (ky = 1) and
-    // opens row iy+1 (ky = 0, initialised with the bias).  PH rotates which accumulator plays which role.
-    auto step = [&](auto ph, int iy) {
-        constexpr int PH = decltype(ph)::value;
-        constexpr int A = PH % 3, B = (PH + 1) % 3, C = (PH + 2) % 3;
-        load_row(iy + 1, nxt);                                        // prefetch while computing
-#pragma unroll
-        for (int p = 0; p < DW_PX; ++p)
-#pragma unroll
-            for (int j = 0; j < DW_CH; ++j) acc[C][p][j] = bs[j];
-#pragma unroll
-        for (int cc = 0; cc < NC; ++cc) {
-            float v[DW_CH];
-            Vec4<T>::unpack(cur[cc], v);
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int p = cc - kx;
-                if (p < 0 || p >= DW_PX) continue;
-#pragma unroll
-                for (int j = 0; j < DW_CH; ++j) {
-                    acc[A][p][j] = fmaf(v[j], wt[6 + kx][j], acc[A][p][j]);
-                    acc[B][p][j] = fmaf(v[j], wt[3 + kx][j], acc[B][p][j]);
-                    acc[C][p][j] = fmaf(v[j], wt[kx][j], acc[C][p][j]);
-                }
+            for (int j = 0; j < VP; ++j) {
+                acc[j].x = fmaf(v[j].x, wp[2 * j], acc[j].x);
+                acc[j].y = fmaf(v[j].y, wp[2 * j + 1], acc[j].y);
             }
         }
-        const int oy = iy - 1;
-        if (oy >= oy0) {
-            T *op = yimg + ((size_t)oy * g.wo + ox0) * g.c;
-#pragma unroll
-            for (int p = 0; p < DW_PX; ++p)
-                if (ox0 + p < g.wo) Vec4<T>::store_relu6(op + (size_t)p * g.c, acc[A][p]);
-        }
-#pragma unroll
-        for (int cc = 0; cc < NC; ++cc) cur[cc] = nxt[cc];
-    };
-
-    // rows oy0-1 .. ylast+1; accumulators that receive contributions before being opened are harmless
-    // (row oy0-2 / oy0-1 garbage is never stored), but keep them finite:
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int p = 0; p < DW_PX; ++p)
-#pragma unroll
-            for (int j = 0; j < DW_CH; ++j) acc[a][p][j] = 0.f;
-
-    int iy = oy0 - 1;
-#pragma unroll 1
-    for (;;) {
-        step(std::integral_constant<int, 0>(), iy); if (++iy > ylast + 1) break;
-        step(std::integral_constant<int, 1>(), iy); if (++iy > ylast + 1) break;
-        step(std::integral_constant<int, 2>(), iy); if (++iy > ylast + 1) break;
     }
+    Vec16<T>::store_relu6(y + (((size_t)img * ho + oy) * wo + ox) * c + c0, acc);
 }
 
-// ---- strided / atrous layers: strip ownership without vertical reuse ------------------------------------
-template <typename T, int STRIDE>
-__global__ void __launch_bounds__(128) dwconv_gen_kernel(const T *__restrict__ x, const float *__restrict__ w,
-                                                         const float *__restrict__ bias, T *__restrict__ y, DwGeom g) {
-    int c0, ox0, oy0, img;
-    if (!dw_decompose(g, c0, ox0, oy0, img)) return;
-    float wt[9][DW_CH], bs[DW_CH];
-    dw_load_weights(w, bias, g.c, c0, wt, bs);
-    const T *ximg = x + (size_t)img * g.h * g.w * g.c + c0;
-    T *yimg = y + (size_t)img * g.ho * g.wo * g.c + c0;
-    const int ylast = min(oy0 + g.th, g.ho) - 1;
-#pragma unroll 1
-    for (int oy = oy0; oy <= ylast; ++oy) {
-        float acc[DW_PX][DW_CH];
-#pragma unroll
-        for (int p = 0; p < DW_PX; ++p)
-#pragma unroll
-            for (int j = 0; j < DW_CH; ++j) acc[p][j] = bs[j];
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = oy * STRIDE - g.pad + ky * g.dil;
-            if (iy < 0 || iy >= g.h) continue;
-            const T *rp = ximg + (size_t)iy * g.w * g.c;
-#pragma unroll
-            for (int p = 0; p < DW_PX; ++p) {
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ix = (ox0 + p) * STRIDE - g.pad + kx * g.dil;
-                    if (ix < 0 || ix >= g.w) continue;
-                    float v[DW_CH];
-                    Vec4<T>::unpack(Vec4<T>::load(rp + (size_t)ix * g.c), v);
-#pragma unroll
-                    for (int j = 0; j < DW_CH; ++j) acc[p][j] = fmaf(v[j], wt[ky * 3 + kx][j], acc[p][j]);
-                }
-            }
-        }
-        T *op = yimg + ((size_t)oy * g.wo + ox0) * g.c;
-#pragma unroll
-        for (int p = 0; p < DW_PX; ++p)
-            if (ox0 + p < g.wo) Vec4<T>::store_relu6(op + (size_t)p * g.c, acc[p]);
-    }
+// ---- host side: tile selection ---------------------------------------------------------------------------
+static bool dw_tma_supported(int stride, int dil) {
+    return (stride == 1 && (dil == 1 || dil == 2 || dil == 4)) || (stride == 2 && dil == 1);
 }
 
-// rows per strip: the divisor-ish of `ho` in [6, 13] that wastes the fewest rows
-static int pick_th(int ho) {
-    int best = 8, best_waste = 1 << 30;
-    for (int th = 13; th >= 6; --th) {
-        const int waste = ceil_div(ho, th) * th - ho;
-        if (waste < best_waste) { best_waste = waste; best = th; }
-    }
-    return ho < 6 ? ho : best;
-}
-
-template <typename T>
-static int launch_t(const T *x, const float *w, const float *b, T *y, int n, int h, int wd, int c, int stride,
-                    int dil, cudaStream_t st) {
+int dw_prepare(DwOp *op, const void *x, int n, int h, int wd, int c, int stride, int dil, int dtype) {
+    PN_CHECK_ARG(x && n > 0 && h > 0 && wd > 0, "pn_dwconv3x3: bad argument");
+    PN_CHECK_ARG(dtype == PN_BF16 || dtype == PN_F32, "pn_dwconv3x3: bad dtype %d", dtype);
+    PN_CHECK_ARG(c > 0 && c % 8 == 0, "pn_dwconv3x3: channels must be a multiple of 8 (got %d)", c);
+    PN_CHECK_ARG(stride == 1 || stride == 2, "pn_dwconv3x3: stride must be 1 or 2 (got %d)", stride);
+    PN_CHECK_ARG(dil >= 1, "pn_dwconv3x3: dilation must be >= 1");
+    PN_CHECK_ARG(((uintptr_t)x & 15) == 0, "pn_dwconv3x3: input must be 16-byte aligned");
+    memset(op, 0, sizeof(*op));
+    op->x = x; op->n = n; op->h = h; op->w = wd; op->c = c; op->stride = stride; op->dil = dil; op->dtype = dtype;
     DwGeom g;
-    g.n = n; g.h = h; g.w = wd; g.c = c; g.dil = dil;
+    memset(&g, 0, sizeof(g));
+    g.n = n; g.h = h; g.w = wd; g.c = c;
     g.pad = ((stride - 1) + dil * 2) / 2;
     g.ho = (h + 2 * g.pad - 2 * dil - 1) / stride + 1;
     g.wo = (wd + 2 * g.pad - 2 * dil - 1) / stride + 1;
-    g.th = pick_th(g.ho);
-    g.strips = ceil_div(g.wo, DW_PX);
-    g.yblocks = ceil_div(g.ho, g.th);
-    const long long total = (long long)n * g.yblocks * g.strips * (c / DW_CH);
-    const long long blocks = (total + 127) / 128;
-    PN_CHECK_ARG(blocks < (1ll << 31), "pn_dwconv3x3: problem too large");
-    if (stride == 1 && dil == 1)
-        dwconv_s1_kernel<T><<<(unsigned)blocks, 128, 0, st>>>(x, w, b, y, g);
-    else if (stride == 1)
-        dwconv_gen_kernel<T, 1><<<(unsigned)blocks, 128, 0, st>>>(x, w, b, y, g);
-    else
-        dwconv_gen_kernel<T, 2><<<(unsigned)blocks, 128, 0, st>>>(x, w, b, y, g);
+    PN_CHECK_ARG(g.ho > 0 && g.wo > 0, "pn_dwconv3x3: empty output");
+    op->ho = g.ho; op->wo = g.wo;
+    op->use_tma = dw_tma_supported(stride, dil);
+    if (!op->use_tma) return PN_OK;
+
+    const int esize = dtype == PN_BF16 ? 2 : 4, ve = 16 / esize;
+    g.lpp = 8;
+    while (c % (g.lpp * ve) != 0) g.lpp >>= 1;            // c % 8 == 0 guarantees lpp >= 1 (bf16) / 2 (fp32)
+    g.cb = g.lpp * ve;
+    g.cblocks = c / g.cb;
+    const int pixb = g.cb * esize;
+    const int ngroups = DW_CONSUMERS / g.lpp;
+    const int pxt = stride == 1 ? 4 : 2;
+    // Search the tile shape: fewest strip slots (tiles x passes x groups), then fewest staged bytes.
+    const int stage_cap = 64 * 1024;                    // at least three stages per CTA
+    double best = 1e300;
+    for (int th = 1; th <= 64 && th <= g.ho + 7; ++th) {
+        for (int tw = pxt; tw <= 128; tw += pxt) {
+            if (tw - pxt >= g.wo) break;
+            const int thi = (th - 1) * stride + 2 * dil + 1;
+            int twi = (tw - 1) * stride + 2 * dil + 1;
+            if (pixb < 128) {                             // stagger consecutive rows by one pixel's worth of banks
+                const int m = 128 / pixb;
+                while (twi % m != 1 % m) ++twi;
+            }
+            if (thi > 256 || twi > 256) continue;
+            const long long bytes = (long long)thi * twi * pixb;
+            if (bytes > stage_cap) continue;
+            const int spr = tw / pxt, nstrips = th * spr;
+            const int passes = ceil_div(nstrips, ngroups);
+            if (passes > 4) continue;
+            const long long tiles = (long long)ceil_div(g.ho, th) * ceil_div(g.wo, tw);
+            // cost model in SM cycles per tile: a pass issues ~660 cycles of instructions, the patch arrives at
+            // ~40 B/clk (L2-assisted: halos are shared with neighbouring tiles), ~100 cycles of hand-off
+            const double issue = passes * 660.0, fill = bytes / 40.0;
+            const double cost = (double)tiles * ((issue > fill ? issue : fill) + 100.0);
+            if (cost < best) {
+                best = cost;
+                g.th = th; g.tw = tw; g.thi = thi; g.twi = twi; g.spr = spr; g.nstrips = nstrips;
+                g.stage_bytes = (unsigned)bytes;
+            }
+        }
+    }
+    PN_CHECK_ARG(best < 1e300, "pn_dwconv3x3: no tile shape fits (c %d stride %d dilation %d)", c, stride, dil);
+    g.tiles_x = ceil_div(g.wo, g.tw);
+    g.tiles_y = ceil_div(g.ho, g.th);
+    g.items = (long long)n * g.tiles_y * g.tiles_x * g.cblocks;
+    g.box_bytes = g.stage_bytes;
+    g.stage_bytes = (g.stage_bytes + 127u) & ~127u;       // keep every stage 128-byte aligned
+    g.stages = (DW_SMEM_PER_CTA - 256) / (int)g.stage_bytes;
+    if (g.stages > DW_MAX_STAGES) g.stages = DW_MAX_STAGES;
+    PN_CHECK_ARG(g.stages >= 2, "pn_dwconv3x3: stage too large");
+    static_assert(sizeof(DwGeom) <= sizeof(op->geom), "DwOp::geom too small");
+    memcpy(op->geom, &g, sizeof(g));
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)c * esize, (uint64_t)wd * c * esize, (uint64_t)h * wd * c * esize};
+    const uint32_t box[4] = {(uint32_t)g.cb, (uint32_t)g.twi, (uint32_t)g.thi, 1u};
+    return encode_tmap(op->tmap, x, esize, 4, dims, strides, box, 0);
+}
+
+template <typename T, int S, int D>
+static int launch_tma(const DwOp *op, const DwGeom &g, const float *w, const float *b, void *y, cudaStream_t st) {
+    static bool configured = false;
+    auto kern = dwconv_tma_kernel<T, S, D>;
+    if (!configured) {
+        PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_PER_CTA));
+        configured = true;
+    }
+    const int smem = 256 + g.stages * (int)g.stage_bytes;
+    const long long max_ctas = num_sms();
+    const int grid = (int)(g.items < max_ctas ? g.items : max_ctas);
+    kern<<<grid, DW_THREADS, smem, st>>>(*reinterpret_cast<const CUtensorMap *>(op->tmap), w, b, (T *)y, g);
     PN_CHECK_LAUNCH();
     return PN_OK;
 }
 
+template <typename T>
+static int launch_typed(const DwOp *op, const float *w, const float *b, void *y, cudaStream_t st) {
+    if (!op->use_tma) {
+        const int ve = Vec16<T>::VE;
+        const int pad = ((op->stride - 1) + op->dil * 2) / 2;
+        const long long total = (long long)op->n * op->ho * op->wo * (op->c / ve);
+        const long long blocks = (total + 127) / 128;
+        PN_CHECK_ARG(blocks < (1ll << 31), "pn_dwconv3x3: problem too large");
+        dwconv_direct_kernel<T><<<(unsigned)blocks, 128, 0, st>>>((const T *)op->x, w, b, (T *)y, op->n, op->h, op->w, op->c,
+                                                                 op->ho, op->wo, op->stride, op->dil, pad);
+        PN_CHECK_LAUNCH();
+        return PN_OK;
+    }
+    DwGeom g;
+    memcpy(&g, op->geom, sizeof(g));
+    if (op->stride == 2) return launch_tma<T, 2, 1>(op, g, w, b, y, st);
+    if (op->dil == 1) return launch_tma<T, 1, 1>(op, g, w, b, y, st);
+    if (op->dil == 2) return launch_tma<T, 1, 2>(op, g, w, b, y, st);
+    return launch_tma<T, 1, 4>(op, g, w, b, y, st);
+}
+
+int dw_launch(const DwOp *op, const float *w, const float *b, void *y, cudaStream_t st) {
+    PN_CHECK_ARG(op && w && b && y, "pn_dwconv3x3: null pointer");
+    PN_CHECK_ARG(((uintptr_t)y & 15) == 0, "pn_dwconv3x3: output must be 16-byte aligned");
+    return op->dtype == PN_BF16 ? launch_typed<__nv_bfloat16>(op, w, b, y, st) : launch_typed<float>(op, w, b, y, st);
+}
+
 int launch_dwconv(const void *x, const float *w, const float *b, void *y, int n, int h, int wd, int c,
                   int stride, int dilation, int dtype, cudaStream_t st) {
-    PN_CHECK_ARG(x && w && b && y && n > 0 && h > 0 && wd > 0, "pn_dwconv3x3: bad argument");
-    PN_CHECK_ARG(c > 0 && c % 8 == 0, "pn_dwconv3x3: channels must be a multiple of 8 (got %d)", c);
-    PN_CHECK_ARG(stride == 1 || stride == 2, "pn_dwconv3x3: stride must be 1 or 2 (got %d)", stride);
-    PN_CHECK_ARG(dilation >= 1, "pn_dwconv3x3: dilation must be >= 1");
-    if (dtype == PN_BF16)
-        return launch_t<__nv_bfloat16>((const __nv_bfloat16 *)x, w, b, (__nv_bfloat16 *)y, n, h, wd, c, stride, dilation, st);
-    if (dtype == PN_F32) return launch_t<float>((const float *)x, w, b, (float *)y, n, h, wd, c, stride, dilation, st);
-    set_error("pn_dwconv3x3: bad dtype %d", dtype);
-    return PN_ERR_ARG;
+    DwOp op;
+    int rc = dw_prepare(&op, x, n, h, wd, c, stride, dilation, dtype);
+    if (rc != PN_OK) return rc;
+    return dw_launch(&op, w, b, y, st);
 }
 
 }  // namespace pn

@@ -78,7 +78,10 @@ def test_stem_u8_equals_preprocess_then_stem():
 # ------------------------------------------------------------------------------------- B3
 @pytest.mark.parametrize("c,stride,dil,h,w", [(32, 1, 1, 33, 47), (64, 2, 1, 33, 47), (128, 2, 1, 32, 32), (256, 1, 2, 17, 23),
                                               (256, 1, 4, 19, 19), (24, 1, 1, 9, 9), (48, 2, 1, 65, 65), (512, 1, 1, 33, 33),
-                                              (1024, 1, 2, 33, 33), (16, 1, 1, 5, 3), (8, 1, 1, 1, 1)])
+                                              (1024, 1, 2, 33, 33), (16, 1, 1, 5, 3), (8, 1, 1, 1, 1),
+                                              # real layer shapes (tile search on odd maps) + a dilation without a TMA instantiation
+                                              (32, 1, 1, 257, 257), (64, 2, 1, 257, 257), (128, 1, 1, 129, 129), (96, 1, 1, 65, 65),
+                                              (192, 2, 1, 33, 33), (384, 1, 1, 17, 17), (16, 2, 1, 361, 641), (40, 1, 3, 20, 20)])
 @pytest.mark.parametrize("dtype", [nat.PN_F32, nat.PN_BF16])
 def test_dwconv(c, stride, dil, h, w, dtype):
     torch.manual_seed(c + stride + dil)
