@@ -9,6 +9,7 @@ at package level: the reference comments that import out (``__init__.py:2``) alt
 from posenet.constants import *  # noqa: F401,F403
 from posenet import decode  # noqa: F401
 from posenet import decode_multi  # noqa: F401
+from posenet import sharding  # noqa: F401  (multi-GPU: shard images, gather pose records)
 from posenet.decode_multi import decode_multiple_poses, decode_multiple_poses_batch  # noqa: F401
 from posenet.models.model_factory import load_model, write_random_checkpoint  # noqa: F401
 from posenet.models import MobileNetV1, MOBILENET_V1_CHECKPOINTS  # noqa: F401
