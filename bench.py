@@ -133,6 +133,9 @@ def layer_costs(model, n, H, W):
             c = L["inp"]
             rows.append(("dw%d" % L["block_id"], (n * h * w + m) * c * 2 + 40 * c, 18 * m * c))
             rows.append(("pw%d" % L["block_id"], (m * c + m * L["outp"] + c * L["outp"]) * 2, 2 * m * c * L["outp"]))
+            # fused block: input read once, output written once, the depthwise intermediate never leaves the SM
+            rows.append(("sep%d" % L["block_id"], (n * h * w * c + m * L["outp"] + c * L["outp"]) * 2 + 40 * c,
+                         18 * m * c + 2 * m * c * L["outp"]))
         h, w = ho, wo
     m = n * h * w
     c = model._layers[-1]["outp"]
@@ -184,6 +187,7 @@ def run_b200(args):
         batch = args.batch
     torch.manual_seed(0)
     model = posenet.MobileNetV1(mid, output_stride=os_).cuda().set_compute_dtype("bf16")   # default torch init, seeded
+    model.set_fused(not args.unfused)
     n_sets = 4                                                   # rotate inputs: 4 x 50 MB u8 > 126 MB L2
     rng = np.random.default_rng(1234 + rank)
     host = [torch.from_numpy(rng.integers(0, 256, (batch, H, W, 3), dtype=np.uint8)).pin_memory() for _ in range(n_sets)]
@@ -264,9 +268,11 @@ def run_b200(args):
     total_ms = sum(times.values())
     kernels = []
     for name, nbytes, flops in costs:
+        if name not in times:
+            continue                                             # fused plans have sepN, unfused dwN + pwN
         t = times[name] * 1e-3
         ai = flops / nbytes
-        tensor_bound = name.startswith(("pw", "heads")) and ai > pk["bf16_sustained"] * 1e3 / pk["hbm"]
+        tensor_bound = name.startswith(("pw", "sep", "heads")) and ai > pk["bf16_sustained"] * 1e3 / pk["hbm"]
         kernels.append({"name": name, "ms": round(times[name], 4), "share": round(times[name] / total_ms, 4),
                         "gbs": round(nbytes / t / 1e9, 1), "tflops": round(flops / t / 1e12, 2),
                         "bound": "tensor" if tensor_bound else "hbm",
@@ -285,7 +291,8 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": batch, "decode": DECODE_KW, "weights": "random-init (torch default, seed 0)",
                        "l2": "inputs rotate over %d batches (%d MB > 126 MB L2); per-step activation traffic >> L2" % (
-                           n_sets, n_sets * host[0].numel() // 2 ** 20), "cuda_graph": True},
+                           n_sets, n_sets * host[0].numel() // 2 ** 20), "cuda_graph": True,
+                       "fused_blocks": bool(model.fused_blocks)},
             "e2e": e2e, "gpu_launches": launches * args.steps, "clocks": clocks, "roofline": roofline,
             "kernels": kernels, "forward_ms_sum_of_kernels": round(total_ms, 3)}
     if cpu:
@@ -306,6 +313,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
+    ap.add_argument("--unfused", action="store_true", help="run every block as depthwise + pointwise kernels (A/B against the fused blocks)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

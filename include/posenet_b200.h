@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 1
+#define PN_ABI_VERSION 2
 
 typedef void *pn_stream_t; /* cudaStream_t */
 
@@ -69,6 +69,15 @@ int pn_dwconv3x3(const void *x, const float *w, const float *bias, void *y, int 
  * bf16 runs on tcgen05 tensor cores (TMA-fed, TMEM accumulators); fp32 is the FFMA parity path. */
 int pn_pwconv_gemm(const void *a, const void *w, const float *bias, void *y, int m, int k, int n,
                    int dtype, pn_stream_t stream);
+
+/* ---- B3+B4 fused: mobilenet_v1.py:57-68 (SeperableConv.forward: relu6(pointwise(relu6(depthwise(x))))) as ONE
+ * kernel -- the depthwise result is produced straight into the shared-memory A tile of the tcgen05 GEMM and never
+ * reaches HBM.  bf16 only.  x: NHWC [n,h,wd,cin]; dw_w f32 [9,cin]; dw_b f32 [cin]; pw_w bf16 [cout,cin];
+ * pw_b f32 [cout]; y: NHWC [n,ho,wo,cout].  cin % 8 == 0, cout % 16 == 0, (stride,dilation) in (1,1|2|4), (2,1). */
+int pn_sepconv_block(const void *x, const float *dw_w, const float *dw_b, const void *pw_w, const float *pw_b, void *y,
+                     int n, int h, int wd, int cin, int cout, int stride, int dilation, pn_stream_t stream);
+/* Tile shape / pipeline depths pn_sepconv_block would pick for a block (host arithmetic only; diagnostics). */
+int pn_sepconv_describe(int n, int h, int wd, int cin, int cout, int stride, int dilation, char *out_host, int capacity);
 
 /* ---- H1: mobilenet_v1.py:151-154,158-161 (4 head convs + sigmoid on the heatmap) as ONE GEMM.
  * a: [n_img*hw, k] dtype.  w: [PN_HEAD_ROWS, k] dtype, rows heat|offset|fwd|bwd then zero padding.
@@ -123,7 +132,12 @@ typedef struct pn_net_desc {
     pn_layer layers[16];
     const void *head_w;    /* [PN_HEAD_ROWS, c_last] plan dtype */
     const float *head_b;   /* [PN_HEAD_ROWS] */
+    int flags;             /* PN_PLAN_* */
 } pn_net_desc;
+
+/* bf16 plans run every SeperableConv block as one fused kernel (pn_sepconv_block) by default;
+ * PN_PLAN_UNFUSED keeps depthwise and pointwise as two kernels (pn_dwconv3x3 + pn_pwconv_gemm). */
+#define PN_PLAN_UNFUSED 1
 
 typedef struct pn_plan pn_plan;
 
@@ -131,16 +145,18 @@ typedef struct pn_plan pn_plan;
  * head map size (out_h, out_w). */
 int pn_plan_query(const pn_net_desc *desc, size_t *arena_bytes, int *out_h, int *out_w);
 int pn_plan_create(const pn_net_desc *desc, void *arena, size_t arena_bytes, pn_plan **plan);
-/* input: f32 NCHW or uint8 HWC as desc->input_u8 says.  Enqueues the 28 kernels of one forward. */
+/* input: f32 NCHW or uint8 HWC as desc->input_u8 says.  Enqueues the kernels of one forward (15 fused, 28 unfused). */
 int pn_plan_forward(pn_plan *plan, const void *input, float *heat, float *off, float *fwd, float *bwd,
                     pn_stream_t stream);
 /* Same launches as pn_plan_forward with a CUDA event between consecutive kernels; synchronises `stream`
- * and writes the device time of each launch (ms, launch order: stem, dw1, pw1, ..., dw13, pw13, heads)
+ * and writes the device time of each launch (ms, launch order; see pn_plan_launch_name)
  * into ms_host[0 .. pn_plan_num_launches).  Measurement aid for bench.py's roofline; host pointer. */
 int pn_plan_profile(pn_plan *plan, const void *input, float *heat, float *off, float *fwd, float *bwd,
                     float *ms_host, int capacity, pn_stream_t stream);
 /* number of kernel launches one pn_plan_forward enqueues */
 int pn_plan_num_launches(const pn_plan *plan);
+/* name of launch i in launch order: "stem", "dw3" / "pw3" (unfused), "sep3" (fused block 3), "heads" */
+const char *pn_plan_launch_name(const pn_plan *plan, int i);
 int pn_plan_destroy(pn_plan *plan);
 
 #ifdef __cplusplus

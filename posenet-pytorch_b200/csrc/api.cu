@@ -46,11 +46,14 @@ struct pn_plan {
     int out_h, out_w;
     struct Step {
         int h_in, w_in, h_out, w_out;
+        bool fused;         // bf16: the whole block is one sepconv launch
         GemmTc tc;          // bf16 only
         DwOp dw;
+        SepOp sep;
     } steps[16];
     GemmTc head_tc;
     int launches;
+    char names[40][12];
 };
 
 extern "C" {
@@ -108,6 +111,23 @@ int pn_pwconv_gemm(const void *a, const void *w, const float *bias, void *y, int
     int rc = gemm_tc_prepare(&g, a, w, y, m, k, n, EPI_RELU6);
     if (rc != PN_OK) return rc;
     return gemm_tc_launch(&g, ep, as_stream(stream));
+}
+
+int pn_sepconv_block(const void *x, const float *dw_w, const float *dw_b, const void *pw_w, const float *pw_b, void *y, int n,
+                     int h, int wd, int cin, int cout, int stride, int dilation, pn_stream_t stream) {
+    SepOp op;
+    int rc = sep_prepare(&op, x, dw_w, dw_b, pw_w, y, n, h, wd, cin, cout, stride, dilation);
+    if (rc != PN_OK) return rc;
+    return sep_launch(&op, pw_b, as_stream(stream));
+}
+
+int pn_sepconv_describe(int n, int h, int wd, int cin, int cout, int stride, int dilation, char *out_host, int capacity) {
+    PN_CHECK_ARG(out_host && capacity > 0, "pn_sepconv_describe: null buffer");
+    SepOp op;
+    int rc = sep_geometry(&op, n, h, wd, cin, cout, stride, dilation);
+    if (rc != PN_OK) return rc;
+    sep_describe(&op, out_host, (size_t)capacity);
+    return PN_OK;
 }
 
 int pn_heads_gemm(const void *a, const void *w, const float *bias, float *heat, float *off, float *fwd, float *bwd,
@@ -178,28 +198,51 @@ int pn_plan_create(const pn_net_desc *desc, void *arena, size_t arena_bytes, pn_
     p->buf[0] = arena;
     p->buf[1] = (char *)arena + need / 2;
     p->launches = 0;
-    // Buffer schedule: stem -> buf0; block i: dw buf0 -> buf1, pw buf1 -> buf0; heads read buf0.
+    // Buffer schedule: the current activation lives in buf[cur] (stem -> buf0).  A fused block reads buf[cur] and
+    // writes buf[cur^1]; an unfused block runs dw buf[cur] -> buf[cur^1], pw buf[cur^1] -> buf[cur].
+    int cur = 0;
     for (int i = 0; i < desc->num_layers; ++i) {
         const pn_layer &L = desc->layers[i];
-        PN_CHECK_ARG(L.pw_w && L.pw_b && (i == 0 || (L.dw_w && L.dw_b)), "pn_plan_create: layer %d has null weights", i);
-        if (i == 0) { p->launches += 1; continue; }
-        p->launches += 2;
-        rc = dw_prepare(&p->steps[i].dw, p->buf[0], desc->n, p->steps[i].h_in, p->steps[i].w_in, L.cin, L.stride, L.dilation,
-                        desc->dtype);
+        pn_plan::Step &S = p->steps[i];
+        if (!(L.pw_w && L.pw_b && (i == 0 || (L.dw_w && L.dw_b)))) {
+            set_error("pn_plan_create: layer %d has null weights", i);
+            delete p;
+            return PN_ERR_ARG;
+        }
+        if (i == 0) {
+            snprintf(p->names[p->launches++], sizeof(p->names[0]), "stem");
+            continue;
+        }
+        S.fused = desc->dtype == PN_BF16 && !(desc->flags & PN_PLAN_UNFUSED) && sep_supported(L.cin, L.cout, L.stride, L.dilation);
+        if (S.fused) {
+            rc = sep_prepare(&S.sep, p->buf[cur], L.dw_w, L.dw_b, L.pw_w, p->buf[cur ^ 1], desc->n, S.h_in, S.w_in, L.cin, L.cout,
+                             L.stride, L.dilation);
+            if (rc != PN_OK) { delete p; return rc; }
+            snprintf(p->names[p->launches++], sizeof(p->names[0]), "sep%d", i);
+            cur ^= 1;
+            continue;
+        }
+        rc = dw_prepare(&S.dw, p->buf[cur], desc->n, S.h_in, S.w_in, L.cin, L.stride, L.dilation, desc->dtype);
         if (rc != PN_OK) { delete p; return rc; }
         if (desc->dtype == PN_BF16) {
-            const int m = desc->n * p->steps[i].h_out * p->steps[i].w_out;
-            rc = gemm_tc_prepare(&p->steps[i].tc, p->buf[1], L.pw_w, p->buf[0], m, L.cin, L.cout, EPI_RELU6);
+            const int m = desc->n * S.h_out * S.w_out;
+            rc = gemm_tc_prepare(&S.tc, p->buf[cur ^ 1], L.pw_w, p->buf[cur], m, L.cin, L.cout, EPI_RELU6);
             if (rc != PN_OK) { delete p; return rc; }
         }
+        snprintf(p->names[p->launches++], sizeof(p->names[0]), "dw%d", i);
+        snprintf(p->names[p->launches++], sizeof(p->names[0]), "pw%d", i);
     }
-    PN_CHECK_ARG(desc->head_w && desc->head_b, "pn_plan_create: null head weights");
+    if (!(desc->head_w && desc->head_b)) {
+        set_error("pn_plan_create: null head weights");
+        delete p;
+        return PN_ERR_ARG;
+    }
     if (desc->dtype == PN_BF16) {
         const int m = desc->n * p->out_h * p->out_w;
-        rc = gemm_tc_prepare(&p->head_tc, p->buf[0], desc->head_w, nullptr, m, desc->layers[desc->num_layers - 1].cout, PN_HEAD_ROWS, EPI_HEADS);
+        rc = gemm_tc_prepare(&p->head_tc, p->buf[cur], desc->head_w, nullptr, m, desc->layers[desc->num_layers - 1].cout, PN_HEAD_ROWS, EPI_HEADS);
         if (rc != PN_OK) { delete p; return rc; }
     }
-    p->launches += 1;
+    snprintf(p->names[p->launches++], sizeof(p->names[0]), "heads");
     *out = p;
     return PN_OK;
 }
@@ -207,7 +250,7 @@ int pn_plan_create(const pn_net_desc *desc, void *arena, size_t arena_bytes, pn_
 static int plan_run(pn_plan *p, const void *input, float *heat, float *off, float *fwd, float *bwd, cudaStream_t st,
                     cudaEvent_t *ev /* launches + 1 events or NULL */) {
     const pn_net_desc &d = p->d;
-    int rc, li = 0;
+    int rc, li = 0, cur = 0;
 #define PN_MARK()                                              \
     do {                                                       \
         if (ev) PN_CHECK_CUDA(cudaEventRecord(ev[li], st));    \
@@ -224,17 +267,24 @@ static int plan_run(pn_plan *p, const void *input, float *heat, float *off, floa
             PN_MARK();
             continue;
         }
-        rc = dw_launch(&S.dw, L.dw_w, L.dw_b, p->buf[1], st);
+        if (S.fused) {
+            rc = sep_launch(&S.sep, L.pw_b, st);
+            if (rc != PN_OK) return rc;
+            PN_MARK();
+            cur ^= 1;
+            continue;
+        }
+        rc = dw_launch(&S.dw, L.dw_w, L.dw_b, p->buf[cur ^ 1], st);
         if (rc != PN_OK) return rc;
         PN_MARK();
         EpiParams ep = {};
         ep.bias = L.pw_b;
-        ep.y = p->buf[0];
+        ep.y = p->buf[cur];
         const int m = d.n * S.h_out * S.w_out;
         if (d.dtype == PN_BF16)
             rc = gemm_tc_launch(&S.tc, ep, st);
         else
-            rc = launch_gemm_simt((const float *)p->buf[1], (const float *)L.pw_w, m, L.cin, L.cout, EPI_RELU6, ep, st);
+            rc = launch_gemm_simt((const float *)p->buf[cur ^ 1], (const float *)L.pw_w, m, L.cin, L.cout, EPI_RELU6, ep, st);
         if (rc != PN_OK) return rc;
         PN_MARK();
     }
@@ -246,7 +296,7 @@ static int plan_run(pn_plan *p, const void *input, float *heat, float *off, floa
     if (d.dtype == PN_BF16)
         rc = gemm_tc_launch(&p->head_tc, ep, st);
     else
-        rc = launch_gemm_simt((const float *)p->buf[0], (const float *)d.head_w, m, d.layers[d.num_layers - 1].cout, PN_HEAD_ROWS,
+        rc = launch_gemm_simt((const float *)p->buf[cur], (const float *)d.head_w, m, d.layers[d.num_layers - 1].cout, PN_HEAD_ROWS,
                               EPI_HEADS, ep, st);
     if (rc != PN_OK) return rc;
     PN_MARK();
@@ -277,6 +327,10 @@ int pn_plan_profile(pn_plan *p, const void *input, float *heat, float *off, floa
 }
 
 int pn_plan_num_launches(const pn_plan *plan) { return plan ? plan->launches : 0; }
+
+const char *pn_plan_launch_name(const pn_plan *plan, int i) {
+    return (plan && i >= 0 && i < plan->launches) ? plan->names[i] : "";
+}
 
 int pn_plan_destroy(pn_plan *plan) {
     delete plan;

@@ -128,4 +128,21 @@ struct GemmTc {
 int gemm_tc_prepare(GemmTc *g, const void *a, const void *w, void *y, int m, int k, int n, int epi);
 int gemm_tc_launch(const GemmTc *g, const EpiParams &ep, cudaStream_t s);
 
+// fused SeperableConv block (depthwise -> pointwise in one kernel, sepconv.cu); bf16 only
+struct SepOp {
+    alignas(64) unsigned char tmap_x[128];
+    alignas(64) unsigned char tmap_dww[128];
+    alignas(64) unsigned char tmap_dwb[128];
+    alignas(64) unsigned char tmap_w[128];
+    alignas(64) unsigned char tmap_y[128];
+    alignas(8) unsigned char geom[256];
+    int smem_bytes, cb, stride, dil, ho, wo, n, h, w, k, nc;
+};
+bool sep_supported(int k, int nc, int stride, int dil);
+int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int dil);
+int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, const void *pw_w, void *y, int n, int h,
+                int wd, int k, int nc, int stride, int dil);
+int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t s);
+void sep_describe(const SepOp *op, char *out, size_t cap);
+
 }  // namespace pn

@@ -1,0 +1,554 @@
+// B3 + B4 fused -- one whole SeperableConv block (posenet/models/mobilenet_v1.py:57-68 of the reference):
+//     y = relu6( pointwise1x1( relu6( depthwise3x3(x; stride, dilation) + b_dw ) ) + b_pw )
+// as ONE kernel: the depthwise result never travels to HBM.  It is produced by CUDA-core warps straight
+// into the 128B-swizzled shared-memory A tile that the tcgen05 tensor-core GEMM of the pointwise conv reads.
+//
+// Work item: an output tile of TH x TW (<= 128) pixels of one image x N_TILE (<= 256) output channels.
+// Per 64-channel k-block of the tile (persistent CTA, 1 per SM, warp-specialised):
+//   warp 0      TMA producer   input patch incl. halo as ONE cp.async.bulk.tensor.4d box per sub-tile (OOB zero fill
+//                              == the convolution's zero padding), the k-block's depthwise weights + bias ([9,K] /
+//                              [K] fp32 through 2-D maps, ragged K zero-filled), and the pointwise weight tile
+//                              [N_TILE x 64] (128B swizzle) -- three mbarrier rings (patch / W / A).
+//   warps 6-15  depthwise      each 8-lane group owns a strip of 4 (stride 1) or 2 (stride 2) adjacent output pixels x
+//                              64 channels (16 B per lane): fp32 math with packed fma.rn.f32x2 in the same tap order as
+//                              the stand-alone kernel (dwconv.cu), + bias, ReLU6, -> bf16 -> st.shared into row
+//                              r = ty*TW+tx of the A stage (16-byte chunk index XOR (r & 7) = SWIZZLE_128B K-major),
+//                              fence.proxy.async, mbarrier arrive.
+//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M = 128, N = N_TILE, K = 16, 4 (2 for CB = 32) per
+//                              k-block, accumulating in TMEM (double-buffered: 2 x N_TILE columns);
+//                              tcgen05.commit frees the A stage and the W stage.
+//   warps 2-5   epilogue       tcgen05.ld -> + bias, ReLU6 -> bf16 -> swizzled staging panel -> cp.async.bulk.tensor.4d
+//                              STORE of a [64 ch, TW, TH] box (the tensor map clips image edges and ragged N).
+// The strip -> thread assignment is fixed for the whole kernel (no integer division in the loop).
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace pn {
+
+constexpr int SEP_DW_WARPS = 10;
+constexpr int SEP_FIRST_DW_WARP = 6;
+constexpr int SEP_THREADS = (SEP_FIRST_DW_WARP + SEP_DW_WARPS) * 32;   // 512
+constexpr int SEP_DW_THREADS = SEP_DW_WARPS * 32;                      // 320
+constexpr int SEP_A_STAGES = 2;
+constexpr int SEP_A_BYTES = 128 * 128;                                 // 128 rows x 64 bf16
+constexpr int SEP_STG_BYTES = 128 * 128;                               // one 128 x 64 bf16 output panel
+constexpr int SEP_MAX_P = 6, SEP_MAX_W = 4;
+constexpr int SEP_WGT_BYTES = 9 * 64 * 4 + 64 * 4;                     // dw weights [9][64] + bias [64] fp32
+constexpr int SEP_SMEM_MAX = 232448;
+
+struct SepGeom {
+    int k, nc, ho, wo, pad;
+    int th, tw, subs, ths, thi, twi;      // output tile, sub-tiles (rows per sub), input box
+    int spr, strips_per_sub;              // strips per tile row / per sub-tile
+    int tiles_x, tiles_y, n_tiles, n_tile, panels, tmem_cols;
+    int kblocks;
+    int p_stages, w_stages, stg_bufs;
+    unsigned patch_stage_bytes, patch_box_bytes, wgt_off, w_stage_bytes;
+    unsigned off_a, off_stg, off_patch, off_bar;   // from the 1024-aligned base; W stages sit at 0
+    long long tiles;                      // m_tiles * n_tiles
+};
+
+struct SepBars {       // byte offsets of the mbarriers inside the barrier block
+    static constexpr int patch_full = 0, patch_empty = 8 * SEP_MAX_P, w_full = 16 * SEP_MAX_P,
+                         w_empty = 16 * SEP_MAX_P + 8 * SEP_MAX_W, a_full = 16 * SEP_MAX_P + 16 * SEP_MAX_W,
+                         a_empty = a_full + 8 * SEP_A_STAGES, tfull = a_empty + 8 * SEP_A_STAGES, tempty = tfull + 16,
+                         tmem_slot = tempty + 16, total = tmem_slot + 16;
+};
+
+__device__ __forceinline__ uint64_t sep_smem_desc(uint32_t saddr) {      // K-major SWIZZLE_128B (see gemm_tc.cu)
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint32_t sep_idesc(int n) {                   // D f32, A/B bf16, K-major, M = 128
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void sep_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+
+template <int CB, int S, int D>
+__global__ void __launch_bounds__(SEP_THREADS, 1)
+sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dww,
+               const __grid_constant__ CUtensorMap tmap_dwb, const __grid_constant__ CUtensorMap tmap_w,
+               const __grid_constant__ CUtensorMap tmap_y, const float *__restrict__ pw_bias, const SepGeom g) {
+    constexpr int LPP = CB / 8;                             // lanes per pixel (16 B = 8 bf16 channels per lane)
+    constexpr int NGROUPS = SEP_DW_THREADS / LPP;
+    constexpr int PXT = (S == 1) ? 4 : 2;                   // output pixels per strip
+    constexpr int NCOLS = (PXT - 1) * S + 2 * D + 1;        // input columns a strip touches
+    constexpr uint32_t PIXB = CB * 2;                       // bytes per pixel in the patch
+
+    extern __shared__ uint8_t sep_smem_raw[];
+    const uint32_t base = (smem_u32(sep_smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + g.off_bar;
+    auto bar = [&](int which, int s) { return bars + (uint32_t)which + 8u * (uint32_t)s; };
+    auto w_addr = [&](int s) { return base + (uint32_t)s * g.w_stage_bytes; };
+    auto a_addr = [&](int s) { return base + g.off_a + (uint32_t)s * SEP_A_BYTES; };
+    auto p_addr = [&](int s) { return base + g.off_patch + (uint32_t)s * g.patch_stage_bytes; };
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bar + SepBars::tmem_slot);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles_per_img = g.tiles_x * g.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_dww);
+        tma_prefetch_desc(&tmap_dwb);
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_y);
+        for (int s = 0; s < g.p_stages; ++s) {
+            mbar_init(bar(SepBars::patch_full, s), 1);
+            mbar_init(bar(SepBars::patch_empty, s), SEP_DW_THREADS);
+        }
+        for (int s = 0; s < g.w_stages; ++s) {
+            mbar_init(bar(SepBars::w_full, s), 1);
+            mbar_init(bar(SepBars::w_empty, s), 1);
+        }
+        for (int s = 0; s < SEP_A_STAGES; ++s) {
+            mbar_init(bar(SepBars::a_full, s), SEP_DW_THREADS);
+            mbar_init(bar(SepBars::a_empty, s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar(SepBars::tfull, s), 1);
+            mbar_init(bar(SepBars::tempty, s), 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + (uint32_t)SepBars::tmem_slot),
+                     "r"((uint32_t)g.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int ps = 0, ws = 0;
+            uint32_t pph = 0, wph = 0;
+            for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+                const int n_tile = (int)(tile % g.n_tiles);
+                const int m_tile = (int)(tile / g.n_tiles);
+                const int img = m_tile / m_tiles_per_img;
+                const int rem = m_tile - img * m_tiles_per_img;
+                const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+                for (int kb = 0; kb < g.kblocks; ++kb) {
+                    for (int sub = 0; sub < g.subs; ++sub) {
+                        mbar_wait(bar(SepBars::patch_empty, ps), pph ^ 1);
+                        const uint32_t full = bar(SepBars::patch_full, ps);
+                        mbar_expect_tx(full, g.patch_box_bytes + SEP_WGT_BYTES);
+                        tma_load_4d(p_addr(ps), &tmap_x, full, kb * CB, tx * g.tw * S - g.pad,
+                                    (ty * g.th + sub * g.ths) * S - g.pad, img);
+                        tma_load_2d(p_addr(ps) + g.wgt_off, &tmap_dww, full, kb * CB, 0);
+                        tma_load_2d(p_addr(ps) + g.wgt_off + 9 * 64 * 4, &tmap_dwb, full, kb * CB, 0);
+                        if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
+                    }
+                    mbar_wait(bar(SepBars::w_empty, ws), wph ^ 1);
+                    mbar_expect_tx(bar(SepBars::w_full, ws), g.w_stage_bytes);
+                    tma_load_2d(w_addr(ws), &tmap_w, bar(SepBars::w_full, ws), kb * CB, n_tile * g.n_tile);
+                    if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = sep_idesc(g.n_tile);
+            int as = 0, ws = 0, acc = 0;
+            uint32_t aph = 0, wph = 0, acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+                mbar_wait(bar(SepBars::tempty, acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.n_tile);
+                for (int kb = 0; kb < g.kblocks; ++kb) {
+                    mbar_wait(bar(SepBars::w_full, ws), wph);
+                    mbar_wait(bar(SepBars::a_full, as), aph);
+                    tc_fence_after();
+                    const uint32_t sa = a_addr(as), sb = w_addr(ws);
+#pragma unroll
+                    for (int k = 0; k < CB / 16; ++k)
+                        tc_mma_bf16(d_tmem, sep_smem_desc(sa + k * 32), sep_smem_desc(sb + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                    tc_commit(bar(SepBars::a_empty, as));
+                    tc_commit(bar(SepBars::w_empty, ws));
+                    if (++as == SEP_A_STAGES) { as = 0; aph ^= 1; }
+                    if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
+                }
+                tc_commit(bar(SepBars::tfull, acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp < SEP_FIRST_DW_WARP) {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                                          // TMEM lane quarter this warp may read
+        const int row_in_tile = q * 32 + lane;
+        const bool issuer = (threadIdx.x == 64);
+        const uint32_t staging = base + g.off_stg;
+        int acc = 0, buf = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+            const int n_tile = (int)(tile % g.n_tiles);
+            const int m_tile = (int)(tile / g.n_tiles);
+            const int img = m_tile / m_tiles_per_img;
+            const int rem = m_tile - img * m_tiles_per_img;
+            const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+            mbar_wait(bar(SepBars::tfull, acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * g.n_tile);
+#pragma unroll 1
+            for (int p = 0; p < g.panels; ++p) {
+                const int col0 = n_tile * g.n_tile + p * 64;
+                if (issuer) {                                            // the store that last read this buffer is done
+                    if (g.stg_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                }
+                sep_epi_bar();
+                const uint32_t srow = staging + (uint32_t)buf * SEP_STG_BYTES + (uint32_t)row_in_tile * 128u;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + (uint32_t)(p * 64 + hf * 32), v);
+                    tc_ld_wait();
+                    if (p == g.panels - 1 && hf == 1) {                  // accumulator fully in registers: hand it back
+                        tc_fence_before();
+                        mbar_arrive(bar(SepBars::tempty, acc));
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {                        // 8 columns -> one 16 B chunk, 128B-swizzled
+                        const int cc = col0 + hf * 32 + c * 8;
+                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                        if (cc < g.nc) {                                 // nc % 8 == 0
+                            b0 = __ldg(reinterpret_cast<const float4 *>(pw_bias + cc));
+                            b1 = __ldg(reinterpret_cast<const float4 *>(pw_bias + cc + 4));
+                        }
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 0]) + b0.x),
+                                                                        relu6f(__uint_as_float(v[8 * c + 1]) + b0.y));
+                        const __nv_bfloat162 h1 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 2]) + b0.z),
+                                                                        relu6f(__uint_as_float(v[8 * c + 3]) + b0.w));
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 4]) + b1.x),
+                                                                        relu6f(__uint_as_float(v[8 * c + 5]) + b1.y));
+                        const __nv_bfloat162 h3 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 6]) + b1.z),
+                                                                        relu6f(__uint_as_float(v[8 * c + 7]) + b1.w));
+                        st_shared_v4(srow + (uint32_t)(((hf * 4 + c) ^ (row_in_tile & 7)) << 4), *reinterpret_cast<const uint32_t *>(&h0),
+                                     *reinterpret_cast<const uint32_t *>(&h1), *reinterpret_cast<const uint32_t *>(&h2),
+                                     *reinterpret_cast<const uint32_t *>(&h3));
+                    }
+                }
+                fence_async_smem();                                      // generic writes -> visible to TMA
+                sep_epi_bar();
+                if (issuer) {
+                    tma_store_4d(&tmap_y, staging + (uint32_t)buf * SEP_STG_BYTES, col0, tx * g.tw, ty * g.th, img);
+                    bulk_commit();
+                }
+                if (g.stg_bufs == 2) buf ^= 1;
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (issuer) bulk_wait_all();                                     // smem must outlive the last bulk store
+    } else {
+        // ===================== depthwise producers of the A tile (warps 6..15) =====================
+        const int dwtid = threadIdx.x - SEP_FIRST_DW_WARP * 32;
+        const int cl = dwtid % LPP;                                       // which 16 B (8 channels) of the pixel
+        const int group = dwtid / LPP;
+        // fixed strip of this group inside every sub-tile: row-fastest so neighbouring groups sit on neighbouring rows
+        const bool has_strip = group < g.strips_per_sub;
+        const int srow_ = has_strip ? group % g.ths : 0;
+        const int sg = has_strip ? group / g.ths : 0;
+        const uint32_t rowb = (uint32_t)g.twi * PIXB;
+        const uint32_t strip_off = (uint32_t)(srow_ * S) * rowb + (uint32_t)(sg * PXT * S) * PIXB + (uint32_t)cl * 16u;
+        const uint32_t wgt_off = g.wgt_off + (uint32_t)cl * 32u;
+        const int col_first = sg * PXT;
+
+        int ps = 0, as = 0;
+        uint32_t pph = 0, aph = 0;
+        for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < g.kblocks; ++kb) {
+                mbar_wait(bar(SepBars::a_empty, as), aph ^ 1);            // the MMAs that read this A stage have retired
+                const uint32_t a_stage = a_addr(as);
+                for (int sub = 0; sub < g.subs; ++sub) {
+                    mbar_wait(bar(SepBars::patch_full, ps), pph);
+                    const int orow = sub * g.ths + srow_;                 // tile-local output row
+                    if (has_strip && orow < g.th) {
+                        const uint32_t stage = p_addr(ps);
+                        const uint32_t wsm = stage + wgt_off;
+                        float2 acc[PXT][4];
+                        {
+                            const float4 b0 = lds_f4(wsm + 9 * 64 * 4), b1 = lds_f4(wsm + 9 * 64 * 4 + 16);
+#pragma unroll
+                            for (int p = 0; p < PXT; ++p) {
+                                acc[p][0] = make_float2(b0.x, b0.y); acc[p][1] = make_float2(b0.z, b0.w);
+                                acc[p][2] = make_float2(b1.x, b1.y); acc[p][3] = make_float2(b1.z, b1.w);
+                            }
+                        }
+                        const uint32_t strip = stage + strip_off;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            float2 wv[3][4];
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float4 w0 = lds_f4(wsm + (uint32_t)((ky * 3 + kx) * 64 * 4)),
+                                             w1 = lds_f4(wsm + (uint32_t)((ky * 3 + kx) * 64 * 4 + 16));
+                                wv[kx][0] = make_float2(w0.x, w0.y); wv[kx][1] = make_float2(w0.z, w0.w);
+                                wv[kx][2] = make_float2(w1.x, w1.y); wv[kx][3] = make_float2(w1.z, w1.w);
+                            }
+                            const uint32_t rowp = strip + (uint32_t)(ky * D) * rowb;
+#pragma unroll
+                            for (int col = 0; col < NCOLS; ++col) {
+                                bool used = false;
+#pragma unroll
+                                for (int p = 0; p < PXT; ++p)
+#pragma unroll
+                                    for (int kx = 0; kx < 3; ++kx) used |= (p * S + kx * D == col);
+                                if (!used) continue;
+                                const uint4 r = ld_shared_v4(rowp + (uint32_t)col * PIXB);
+                                float2 v[4];                               // bf16 -> f32 is a 16-bit shift
+                                v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+                                v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+                                v[2] = make_float2(__uint_as_float(r.z << 16), __uint_as_float(r.z & 0xffff0000u));
+                                v[3] = make_float2(__uint_as_float(r.w << 16), __uint_as_float(r.w & 0xffff0000u));
+#pragma unroll
+                                for (int p = 0; p < PXT; ++p)
+#pragma unroll
+                                    for (int kx = 0; kx < 3; ++kx)
+                                        if (p * S + kx * D == col) {
+#pragma unroll
+                                            for (int j = 0; j < 4; ++j) acc[p][j] = ffma2(v[j], wv[kx][j], acc[p][j]);
+                                        }
+                            }
+                        }
+                        // + ReLU6 (round first, clamp after: 0 and 6 are exact in bf16 and rounding is monotone)
+                        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(0.f, 0.f), hi2 = __floats2bfloat162_rn(6.f, 6.f);
+#pragma unroll
+                        for (int p = 0; p < PXT; ++p) {
+                            const int col = col_first + p;
+                            if (col < g.tw) {
+                                uint32_t o[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    __nv_bfloat162 h = __hmin2(__hmax2(__floats2bfloat162_rn(acc[p][j].x, acc[p][j].y), lo2), hi2);
+                                    o[j] = *reinterpret_cast<uint32_t *>(&h);
+                                }
+                                const int r = orow * g.tw + col;          // A-tile row == TMEM lane == staging row
+                                st_shared_v4(a_stage + (uint32_t)r * 128u + (uint32_t)((cl ^ (r & 7)) << 4), o[0], o[1], o[2], o[3]);
+                            }
+                        }
+                    }
+                    mbar_arrive(bar(SepBars::patch_empty, ps));           // this thread no longer reads the patch
+                    if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
+                }
+                fence_async_smem();                                       // A-tile writes -> visible to the tensor core
+                mbar_arrive(bar(SepBars::a_full, as));
+                if (++as == SEP_A_STAGES) { as = 0; aph ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+static int next_pow2_cols(int c) {
+    int p = 32;
+    while (p < c) p <<= 1;
+    return p;
+}
+
+bool sep_supported(int k, int nc, int stride, int dil) {
+    return k % 8 == 0 && nc % 16 == 0 && k >= 8 && nc >= 16 &&
+           ((stride == 1 && (dil == 1 || dil == 2 || dil == 4)) || (stride == 2 && dil == 1));
+}
+
+// Tile shape, stage counts and the shared-memory carve-up for one block (pure host arithmetic, no CUDA calls).
+int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int dil) {
+    PN_CHECK_ARG(n > 0 && h > 0 && wd > 0, "pn_sepconv_block: bad shape");
+    PN_CHECK_ARG(sep_supported(k, nc, stride, dil), "pn_sepconv_block: unsupported block (cin %d cout %d stride %d dilation %d)", k,
+                 nc, stride, dil);
+    memset(op, 0, sizeof(*op));
+    SepGeom g;
+    memset(&g, 0, sizeof(g));
+    g.k = k; g.nc = nc;
+    g.pad = ((stride - 1) + dil * 2) / 2;
+    g.ho = (h + 2 * g.pad - 2 * dil - 1) / stride + 1;
+    g.wo = (wd + 2 * g.pad - 2 * dil - 1) / stride + 1;
+    PN_CHECK_ARG(g.ho > 0 && g.wo > 0, "pn_sepconv_block: empty output");
+    const int cb = (k <= 32 && stride == 1 && dil == 1) ? 32 : 64;   // 64 B pixels exist for the stride-1 first block only
+    const int lpp = cb / 8, ngroups = SEP_DW_THREADS / lpp, pxt = stride == 1 ? 4 : 2;
+    g.kblocks = ceil_div(k, cb);
+    g.n_tiles = ceil_div(nc, 256);
+    g.n_tile = nc / g.n_tiles;
+    PN_CHECK_ARG(g.n_tile * g.n_tiles == nc && g.n_tile % 16 == 0, "pn_sepconv_block: cout %d does not split into tiles", nc);
+    g.panels = ceil_div(g.n_tile, 64);
+    g.tmem_cols = next_pow2_cols(g.n_tile + g.panels * 64);
+    PN_CHECK_ARG(g.tmem_cols <= 512, "pn_sepconv_block: TMEM budget exceeded");
+    g.w_stage_bytes = (unsigned)g.n_tile * 128u;
+
+    // ---- tile search: fewest (tiles x per-tile cost); one strip per depthwise thread group per sub-tile
+    const int fixed = SEP_A_STAGES * SEP_A_BYTES + SEP_STG_BYTES + 2 * (int)g.w_stage_bytes + 1024 + 256;   // minimum non-patch smem
+    double best = 1e300;
+    for (int th = 1; th <= 64; ++th) {
+        for (int tw = 1; tw <= 64; ++tw) {
+            if (th * tw > 128) break;
+            if ((th - 1) >= g.ho + 7 || (tw - 1) >= g.wo + 7) continue;
+            for (int subs = 1; subs <= 4 && subs <= th; ++subs) {
+                const int ths = ceil_div(th, subs);
+                if ((subs - 1) * ths >= th) continue;                      // an empty last sub-tile
+                const int thi = (ths - 1) * stride + 2 * dil + 1;
+                int twi = (tw - 1) * stride + 2 * dil + 1;
+                if (cb == 32 && twi % 2 == 0) ++twi;                       // 64 B pixels: odd row pitch staggers the banks
+                if (thi > 256 || twi > 256) continue;
+                const long long box = (long long)thi * twi * cb * 2;
+                const long long stage = ((box + 127) & ~127ll) + SEP_WGT_BYTES;
+                const int spr = ceil_div(tw, pxt), sps = ths * spr;
+                if (sps > ngroups) continue;
+                const long long room = SEP_SMEM_MAX - fixed;
+                const int pst = (int)(room / stage);
+                if (pst < 2 || pst < subs + 1) continue;
+                const long long tiles = (long long)ceil_div(g.ho, th) * ceil_div(g.wo, tw);
+                // per k-block cycles: depthwise issue ~ 110 cycles per busy warp (+ hand-off per sub-tile), tensor pipe 2 cycles
+                // per output column, patch fill at ~40 B/clk
+                const double dwc = (double)subs * (ceil_div(sps * lpp, 32) * 110.0 + 120.0);
+                const double mma = (cb / 64.0) * 2.0 * g.n_tile;
+                const double fill = (double)subs * stage / 40.0;
+                double per_kb = dwc > mma ? dwc : mma;
+                if (fill > per_kb) per_kb = fill;
+                per_kb += 0.25 * fill;                                     // halo re-reads load the L2 -> SM path
+                if (pst < 3 * subs) per_kb *= 1.25;                        // shallow prefetch
+                // per tile: pipeline hand-off + an epilogue whose work is 128 rows x n_tile whatever the tile covers
+                const double cost = (double)tiles * (g.kblocks * per_kb + 400.0 + 200.0 * g.panels);
+                if (cost < best) {
+                    best = cost;
+                    g.th = th; g.tw = tw; g.subs = subs; g.ths = ths; g.thi = thi; g.twi = twi; g.spr = spr; g.strips_per_sub = sps;
+                    g.patch_box_bytes = (unsigned)box;
+                    g.wgt_off = (unsigned)((box + 127) & ~127ll);
+                    g.patch_stage_bytes = (unsigned)stage;
+                }
+            }
+        }
+    }
+    PN_CHECK_ARG(best < 1e300, "pn_sepconv_block: no tile shape fits (cin %d stride %d dilation %d)", k, stride, dil);
+    g.tiles_x = ceil_div(g.wo, g.tw);
+    g.tiles_y = ceil_div(g.ho, g.th);
+    g.tiles = (long long)n * g.tiles_x * g.tiles_y * g.n_tiles;
+    // ---- shared-memory carve-up: patches get what is left after W (2-3 stages), A, staging (1-2 panels)
+    int bestp = -1;
+    for (int stg = 2; stg >= 1; --stg)
+        for (int wst = 3; wst >= 2; --wst) {
+            const long long rest = SEP_SMEM_MAX - 1024 - 256 - SEP_A_STAGES * SEP_A_BYTES - (long long)stg * SEP_STG_BYTES - (long long)wst * g.w_stage_bytes;
+            if (rest <= 0) continue;
+            int pst = (int)(rest / g.patch_stage_bytes);
+            if (pst > SEP_MAX_P) pst = SEP_MAX_P;
+            const int want = 3 * g.subs > SEP_MAX_P ? SEP_MAX_P : 3 * g.subs;
+            const int score = (pst >= want ? 100 : pst * 10) + wst * 2 + stg;    // deep patch prefetch first
+            if (pst >= 2 && pst >= g.subs + 1 && score > bestp) {
+                bestp = score;
+                g.p_stages = pst; g.w_stages = wst; g.stg_bufs = stg;
+            }
+        }
+    PN_CHECK_ARG(bestp >= 0, "pn_sepconv_block: shared memory budget exceeded");
+    g.off_a = (unsigned)g.w_stages * g.w_stage_bytes;
+    g.off_stg = g.off_a + SEP_A_STAGES * SEP_A_BYTES;
+    g.off_patch = g.off_stg + (unsigned)g.stg_bufs * SEP_STG_BYTES;
+    g.off_bar = g.off_patch + (unsigned)g.p_stages * g.patch_stage_bytes;
+    op->smem_bytes = (int)(g.off_bar + SepBars::total + 1024);
+    PN_CHECK_ARG(op->smem_bytes <= SEP_SMEM_MAX, "pn_sepconv_block: internal smem accounting error (%d)", op->smem_bytes);
+    static_assert(sizeof(SepGeom) <= sizeof(op->geom), "SepOp::geom too small");
+    memcpy(op->geom, &g, sizeof(g));
+    op->cb = cb; op->stride = stride; op->dil = dil;
+    op->ho = g.ho; op->wo = g.wo;
+    op->n = n; op->h = h; op->w = wd; op->k = k; op->nc = nc;
+    return PN_OK;
+}
+
+int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, const void *pw_w, void *y, int n, int h,
+                int wd, int k, int nc, int stride, int dil) {
+    PN_CHECK_ARG(x && dw_w && dw_b && pw_w && y, "pn_sepconv_block: null pointer");
+    PN_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)pw_w & 15) == 0 && ((uintptr_t)dw_w & 15) == 0 &&
+                     ((uintptr_t)dw_b & 15) == 0,
+                 "pn_sepconv_block: pointers must be 16-byte aligned");
+    int rc = sep_geometry(op, n, h, wd, k, nc, stride, dil);
+    if (rc != PN_OK) return rc;
+    SepGeom g;
+    memcpy(&g, op->geom, sizeof(g));
+    const int cb = op->cb;
+    {   // input patches: (C, W, H, N) bf16, box [cb, twi, thi, 1], no swizzle, OOB -> 0
+        const uint64_t dims[4] = {(uint64_t)k, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
+        const uint64_t strides[3] = {(uint64_t)k * 2, (uint64_t)wd * k * 2, (uint64_t)h * wd * k * 2};
+        const uint32_t box[4] = {(uint32_t)cb, (uint32_t)g.twi, (uint32_t)g.thi, 1u};
+        if ((rc = encode_tmap(op->tmap_x, x, 2, 4, dims, strides, box, 0)) != PN_OK) return rc;
+    }
+    {   // depthwise weights [9, K] fp32, box [64, 9]; bias [1, K] fp32, box [64, 1]
+        const uint64_t dims[2] = {(uint64_t)k, 9};
+        const uint64_t strides[1] = {(uint64_t)k * 4};
+        const uint32_t box[2] = {64u, 9u};
+        if ((rc = encode_tmap(op->tmap_dww, dw_w, 4, 2, dims, strides, box, 0)) != PN_OK) return rc;
+        const uint64_t bdims[2] = {(uint64_t)k, 1};
+        const uint32_t bbox[2] = {64u, 1u};
+        if ((rc = encode_tmap(op->tmap_dwb, dw_b, 4, 2, bdims, strides, bbox, 0)) != PN_OK) return rc;
+    }
+    {   // pointwise weights [Nc, K] bf16, box [64, n_tile], 128B swizzle
+        const uint64_t dims[2] = {(uint64_t)k, (uint64_t)nc};
+        const uint64_t strides[1] = {(uint64_t)k * 2};
+        const uint32_t box[2] = {64u, (uint32_t)g.n_tile};
+        if ((rc = encode_tmap(op->tmap_w, pw_w, 2, 2, dims, strides, box, 3)) != PN_OK) return rc;
+    }
+    {   // output (C, W, H, N) bf16, box [64, tw, th, 1], 128B swizzle
+        const uint64_t dims[4] = {(uint64_t)nc, (uint64_t)g.wo, (uint64_t)g.ho, (uint64_t)n};
+        const uint64_t strides[3] = {(uint64_t)nc * 2, (uint64_t)g.wo * nc * 2, (uint64_t)g.ho * g.wo * nc * 2};
+        const uint32_t box[4] = {64u, (uint32_t)g.tw, (uint32_t)g.th, 1u};
+        if ((rc = encode_tmap(op->tmap_y, y, 2, 4, dims, strides, box, 3)) != PN_OK) return rc;
+    }
+    return PN_OK;
+}
+
+template <int CB, int S, int D>
+static int sep_launch_t(const SepOp *op, const SepGeom &g, const float *pw_bias, cudaStream_t st) {
+    static bool configured = false;
+    auto kern = sepconv_kernel<CB, S, D>;
+    if (!configured) {
+        PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SEP_SMEM_MAX));
+        configured = true;
+    }
+    const long long sms = num_sms();
+    const int grid = (int)(g.tiles < sms ? g.tiles : sms);
+    kern<<<grid, SEP_THREADS, op->smem_bytes, st>>>(
+        *reinterpret_cast<const CUtensorMap *>(op->tmap_x), *reinterpret_cast<const CUtensorMap *>(op->tmap_dww),
+        *reinterpret_cast<const CUtensorMap *>(op->tmap_dwb), *reinterpret_cast<const CUtensorMap *>(op->tmap_w),
+        *reinterpret_cast<const CUtensorMap *>(op->tmap_y), pw_bias, g);
+    PN_CHECK_LAUNCH();
+    return PN_OK;
+}
+
+int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t st) {
+    PN_CHECK_ARG(op && pw_bias, "pn_sepconv_block: null pointer");
+    SepGeom g;
+    memcpy(&g, op->geom, sizeof(g));
+    if (op->cb == 32) {
+        PN_CHECK_ARG(op->stride == 1 && op->dil == 1, "pn_sepconv_block: cin <= 32 is only built for stride 1, dilation 1");
+        return sep_launch_t<32, 1, 1>(op, g, pw_bias, st);
+    }
+    if (op->stride == 2) return sep_launch_t<64, 2, 1>(op, g, pw_bias, st);
+    if (op->dil == 1) return sep_launch_t<64, 1, 1>(op, g, pw_bias, st);
+    if (op->dil == 2) return sep_launch_t<64, 1, 2>(op, g, pw_bias, st);
+    return sep_launch_t<64, 1, 4>(op, g, pw_bias, st);
+}
+
+void sep_describe(const SepOp *op, char *out, size_t cap) {
+    SepGeom g;
+    memcpy(&g, op->geom, sizeof(g));
+    snprintf(out, cap, "tile %dx%d subs %d box %dx%d n_tile %d x%d kblocks %d stages p%d w%d stg%d smem %d tiles %lld", g.th, g.tw,
+             g.subs, g.thi, g.twi, g.n_tile, g.n_tiles, g.kblocks, g.p_stages, g.w_stages, g.stg_bufs, op->smem_bytes, g.tiles);
+}
+
+}  // namespace pn

@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get("POSENET_B200_LIB", os.path.join(_PKG_ROOT, "lib", "li
 PN_OK = 0
 PN_F32, PN_BF16 = 0, 1
 NUM_PARTS, NUM_EDGES, HEAD_CHANNELS, HEAD_ROWS = 17, 16, 115, 128
-ABI_VERSION = 1
+ABI_VERSION = 2
+PLAN_UNFUSED = 1
 
 
 class NativeError(RuntimeError):
@@ -38,7 +39,8 @@ class Layer(C.Structure):
 
 class NetDesc(C.Structure):
     _fields_ = [("dtype", C.c_int), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("input_u8", C.c_int),
-                ("num_layers", C.c_int), ("layers", Layer * 16), ("head_w", C.c_void_p), ("head_b", C.c_void_p)]
+                ("num_layers", C.c_int), ("layers", Layer * 16), ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+                ("flags", C.c_int)]
 
 
 _SIGNATURES = {
@@ -54,6 +56,9 @@ _SIGNATURES = {
                                C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pn_pwconv_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p]),
+    "pn_sepconv_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "pn_sepconv_describe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "pn_heads_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pn_candidates": (C.c_int, [C.POINTER(Map), C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p,
@@ -67,6 +72,7 @@ _SIGNATURES = {
     "pn_plan_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
                                   C.c_int, C.c_void_p]),
     "pn_plan_num_launches": (C.c_int, [C.c_void_p]),
+    "pn_plan_launch_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "pn_plan_destroy": (C.c_int, [C.c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)

@@ -91,7 +91,7 @@ class SeperableConv(nn.Module):
 class _Plan:
     """One compiled (batch, H, W, dtype, input kind) instance: arena + pn_plan handle."""
 
-    def __init__(self, model, n, h, w, dtype, input_u8):
+    def __init__(self, model, n, h, w, dtype, input_u8, fused=True):
         lib = nat.load()
         pk = model._packed(dtype)
         desc = nat.NetDesc()
@@ -106,6 +106,7 @@ class _Plan:
                 d.dw_w, d.dw_b = pk["dw_w"][i].data_ptr(), pk["dw_b"][i].data_ptr()
             d.pw_w, d.pw_b = pk["pw_w"][i].data_ptr(), pk["pw_b"][i].data_ptr()
         desc.head_w, desc.head_b = pk["head_w"].data_ptr(), pk["head_b"].data_ptr()
+        desc.flags = 0 if fused else nat.PLAN_UNFUSED
         arena_bytes, oh, ow = C.c_size_t(), C.c_int(), C.c_int()
         nat.check(lib.pn_plan_query(C.byref(desc), C.byref(arena_bytes), C.byref(oh), C.byref(ow)), "pn_plan_query")
         self.desc, self.packed = desc, pk                      # keep the weight tensors alive
@@ -127,8 +128,10 @@ class _Plan:
         ms = (C.c_float * self.launches)()
         nat.check(self._lib.pn_plan_profile(self.handle, C.c_void_p(x.data_ptr()), *[C.c_void_p(o.data_ptr()) for o in outs],
                                             ms, self.launches, nat.stream_ptr()), "pn_plan_profile")
-        names = ["stem"] + [k % i for i in range(1, self.desc.num_layers) for k in ("dw%d", "pw%d")] + ["heads"]
-        return list(zip(names, list(ms)))
+        return list(zip(self.launch_names(), list(ms)))
+
+    def launch_names(self):
+        return [self._lib.pn_plan_launch_name(self.handle, i).decode() for i in range(self.launches)]
 
     def __del__(self):
         try:
@@ -155,6 +158,7 @@ class MobileNetV1(nn.Module):
         for name, ch in _HEAD_CHANNELS.items():
             setattr(self, name, nn.Conv2d(last_depth, ch, 1, 1))
         self.compute_dtype = os.environ.get("POSENET_B200_DTYPE", "bf16")
+        self.fused_blocks = os.environ.get("POSENET_B200_UNFUSED", "0") != "1"
         self._pack_cache = {}
         self._plans = {}
         self.eval()
@@ -166,6 +170,11 @@ class MobileNetV1(nn.Module):
         """'bf16' (tcgen05 tensor cores, the default) or 'fp32' (FFMA parity mode)."""
         assert name in ("bf16", "fp32"), name
         self.compute_dtype = name
+        return self
+
+    def set_fused(self, fused=True):
+        """bf16 only: run each SeperableConv block as one fused kernel (default) or as depthwise + pointwise."""
+        self.fused_blocks = bool(fused)
         return self
 
     def _dtype_code(self):
@@ -227,12 +236,12 @@ class MobileNetV1(nn.Module):
         return pk
 
     def _plan(self, n, h, w, input_u8):
-        key = (n, h, w, self._dtype_code(), bool(input_u8), self._weights_version())
+        key = (n, h, w, self._dtype_code(), bool(input_u8), self.fused_blocks, self._weights_version())
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) >= 8:
                 self._plans.clear()
-            plan = self._plans[key] = _Plan(self, n, h, w, self._dtype_code(), input_u8)
+            plan = self._plans[key] = _Plan(self, n, h, w, self._dtype_code(), input_u8, self.fused_blocks)
         return plan
 
     # ------------------------------------------------------------------ execution

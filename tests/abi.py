@@ -51,6 +51,16 @@ def pwconv(a, w, b, dtype):
     return y
 
 
+def sepconv(x, w9, b_dw, w_pw, b_pw, stride, dil):
+    """Fused SeperableConv block (bf16): x NHWC bf16, w9 f32 [9,cin], w_pw bf16 [cout,cin]."""
+    n, h, wd, c = x.shape
+    cout = w_pw.shape[0]
+    y = torch.full((n, conv_out(h, stride, dil), conv_out(wd, stride, dil), cout), float("nan"), dtype=torch.bfloat16, device=x.device)
+    nat.check(nat.load().pn_sepconv_block(P(x), P(w9), P(b_dw), P(w_pw), P(b_pw), P(y), n, h, wd, c, cout, stride, dil,
+                                          nat.stream_ptr()), "pn_sepconv_block")
+    return y
+
+
 def heads(a, w128, b128, n_img, hw, dtype):
     k = a.shape[1]
     outs = [torch.full((n_img, ch, hw), float("nan"), dtype=torch.float32, device=a.device) for ch in (17, 34, 32, 32)]

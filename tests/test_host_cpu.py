@@ -22,13 +22,30 @@ def test_library_exports_every_declared_symbol():
     lib = nat.load()                                       # raises if missing / symbol absent / ABI mismatch
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.pn_abi_version() == 1
+    assert lib.pn_abi_version() == nat.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(nat.Map) == 40 and C.sizeof(nat.DecodeParams) == 24 and C.sizeof(nat.Layer) == 48
-    assert C.sizeof(nat.NetDesc) == 24 + 16 * 48 + 16
+    assert C.sizeof(nat.NetDesc) == 24 + 16 * 48 + 16 + 8          # + flags, padded to pointer alignment
+
+
+def test_sepconv_tile_geometry_is_host_computable():
+    """pn_sepconv_describe is pure host arithmetic: every block of every model/stride has a tile shape."""
+    import ctypes as C
+    lib, buf = nat.load(), C.create_string_buffer(256)
+    for mid, os_, hw in ((101, 16, 513), (101, 8, 257), (50, 8, 721), (75, 32, 257), (100, 32, 129)):
+        m = posenet.MobileNetV1(mid, output_stride=os_)
+        h = w = hw
+        for L in m._layers:
+            s, d = L["stride"], L["rate"]
+            if L["block_id"]:
+                assert lib.pn_sepconv_describe(2, h, w, L["inp"], L["outp"], s, d, buf, 256) == 0, lib.pn_last_error_string()
+                assert b"tile" in buf.value
+            pad = ((s - 1) + 2 * d) // 2
+            h = w = (h + 2 * pad - 2 * d - 1) // s + 1
+    assert lib.pn_sepconv_describe(2, 9, 9, 64, 64, 2, 2, buf, 256) != 0            # never produced by the tables
 
 
 @pytest.mark.parametrize("mid", [50, 75, 100, 101])
