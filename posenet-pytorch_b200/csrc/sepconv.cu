@@ -9,17 +9,19 @@
 //                              == the convolution's zero padding), the k-block's depthwise weights + bias ([9,K] /
 //                              [K] fp32 through 2-D maps, ragged K zero-filled), and the pointwise weight tile
 //                              [N_TILE x 64] (128B swizzle) -- three mbarrier rings (patch / W / A).
-//   warps 6-15  depthwise      each 8-lane group owns a strip of 4 (stride 1) or 2 (stride 2) adjacent output pixels x
-//                              64 channels (16 B per lane): fp32 math with packed fma.rn.f32x2 in the same tap order as
-//                              the stand-alone kernel (dwconv.cu), + bias, ReLU6, -> bf16 -> st.shared into row
-//                              r = ty*TW+tx of the A stage (16-byte chunk index XOR (r & 7) = SWIZZLE_128B K-major),
-//                              fence.proxy.async, mbarrier arrive.
-//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M = 128, N = N_TILE, K = 16, 4 (2 for CB = 32) per
-//                              k-block, accumulating in TMEM (double-buffered: 2 x N_TILE columns);
+//   warps 6-15  depthwise      a lane owns one channel pair (4 B of every pixel), a warp a column strip of 4 output pixels
+//                              that it walks down row by row with the 3x3 window's input rows held in registers, so
+//                              each patch element is read from shared memory once and the 9x2 weights stay in
+//                              registers (the kernel is shared-memory-bandwidth bound otherwise).  fp32 math with packed
+//                              fma.rn.f32x2 in the same tap order as the stand-alone kernel (dwconv.cu), + bias, ReLU6,
+//                              -> bf16 -> st.shared into row r = ty*TW+tx of the A stage (16-byte chunk index XOR
+//                              (r & 7) = SWIZZLE_128B K-major), fence.proxy.async, mbarrier arrive.
+//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M = 128, N = N_TILE, K = 16, up to 4 per k-block
+//                              (fewer on a ragged K tail), accumulating in TMEM (double-buffered: 2 x N_TILE columns);
 //                              tcgen05.commit frees the A stage and the W stage.
 //   warps 2-5   epilogue       tcgen05.ld -> + bias, ReLU6 -> bf16 -> swizzled staging panel -> cp.async.bulk.tensor.4d
 //                              STORE of a [64 ch, TW, TH] box (the tensor map clips image edges and ragged N).
-// The strip -> thread assignment is fixed for the whole kernel (no integer division in the loop).
+// The segment -> warp assignment is fixed for the whole kernel (no integer division in the loop).
 #include <cuda.h>
 #include <string.h>
 
@@ -42,8 +44,9 @@ constexpr int SEP_SMEM_MAX = 232448;
 struct SepGeom {
     int k, nc, ho, wo, pad;
     int th, tw, subs, ths, thi, twi;      // output tile, sub-tiles (rows per sub), input box
-    int spr, strips_per_sub;              // strips per tile row / per sub-tile
+    int spr, seg_rows, segs_per_sub;      // 4-pixel column strips per tile row; rows per segment; segments per sub-tile
     int tiles_x, tiles_y, n_tiles, n_tile, panels, tmem_cols;
+    int n_halves, n_half, acc_bufs;       // a tile's accumulator = n_halves UMMA column blocks of n_half (<= 256) columns
     int kblocks;
     int p_stages, w_stages, stg_bufs;
     unsigned patch_stage_bytes, patch_box_bytes, wgt_off, w_stage_bytes;
@@ -65,22 +68,37 @@ __device__ __forceinline__ uint32_t sep_idesc(int n) {                   // D f3
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void sep_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-    float4 r;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
     return r;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool on) {     // predicated, branch-free
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)on) : "memory");
+}
 
-template <int CB, int S, int D>
+// Register window of the depthwise stencil for a strip of 4 output pixels: output row t reads input rows
+// t*S + ky*D.  Sliding (D == 1): a ring of NR = 2D+1 rows, S new rows per step, PRE rows preloaded; otherwise the
+// three rows are loaded afresh each step.
+template <int S, int D> struct SepDwCfg {
+    static constexpr bool SLIDE = (D == 1);
+    static constexpr bool UNPACKED = (D == 1);       // window kept as fp32 pairs (18-27 pairs); wider windows stay packed
+    static constexpr int NR = SLIDE ? 2 * D + 1 : 3;
+    static constexpr int NCOLS = 3 * S + 2 * D + 1;
+    static constexpr int PRE = SLIDE ? 2 * D + 1 - S : 0;
+};
+
+template <int S, int D>
 __global__ void __launch_bounds__(SEP_THREADS, 1)
 sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dww,
                const __grid_constant__ CUtensorMap tmap_dwb, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_y, const float *__restrict__ pw_bias, const SepGeom g) {
-    constexpr int LPP = CB / 8;                             // lanes per pixel (16 B = 8 bf16 channels per lane)
-    constexpr int NGROUPS = SEP_DW_THREADS / LPP;
-    constexpr int PXT = (S == 1) ? 4 : 2;                   // output pixels per strip
-    constexpr int NCOLS = (PXT - 1) * S + 2 * D + 1;        // input columns a strip touches
-    constexpr uint32_t PIXB = CB * 2;                       // bytes per pixel in the patch
+    constexpr int CB = 64;                                  // channels per k-block (ragged K is zero-filled by TMA)
 
     extern __shared__ uint8_t sep_smem_raw[];
     const uint32_t base = (smem_u32(sep_smem_raw) + 1023u) & ~1023u;
@@ -103,14 +121,14 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         tma_prefetch_desc(&tmap_y);
         for (int s = 0; s < g.p_stages; ++s) {
             mbar_init(bar(SepBars::patch_full, s), 1);
-            mbar_init(bar(SepBars::patch_empty, s), SEP_DW_THREADS);
+            mbar_init(bar(SepBars::patch_empty, s), SEP_DW_WARPS);
         }
         for (int s = 0; s < g.w_stages; ++s) {
             mbar_init(bar(SepBars::w_full, s), 1);
             mbar_init(bar(SepBars::w_empty, s), 1);
         }
         for (int s = 0; s < SEP_A_STAGES; ++s) {
-            mbar_init(bar(SepBars::a_full, s), SEP_DW_THREADS);
+            mbar_init(bar(SepBars::a_full, s), SEP_DW_WARPS);
             mbar_init(bar(SepBars::a_empty, s), 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -152,17 +170,19 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         tma_load_2d(p_addr(ps) + g.wgt_off + 9 * 64 * 4, &tmap_dwb, full, kb * CB, 0);
                         if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
                     }
-                    mbar_wait(bar(SepBars::w_empty, ws), wph ^ 1);
-                    mbar_expect_tx(bar(SepBars::w_full, ws), g.w_stage_bytes);
-                    tma_load_2d(w_addr(ws), &tmap_w, bar(SepBars::w_full, ws), kb * CB, n_tile * g.n_tile);
-                    if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
+                    for (int hf = 0; hf < g.n_halves; ++hf) {
+                        mbar_wait(bar(SepBars::w_empty, ws), wph ^ 1);
+                        mbar_expect_tx(bar(SepBars::w_full, ws), g.w_stage_bytes);
+                        tma_load_2d(w_addr(ws), &tmap_w, bar(SepBars::w_full, ws), kb * CB, n_tile * g.n_tile + hf * g.n_half);
+                        if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = sep_idesc(g.n_tile);
+            const uint32_t idesc = sep_idesc(g.n_half);
             int as = 0, ws = 0, acc = 0;
             uint32_t aph = 0, wph = 0, acc_phase = 0;
             for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
@@ -170,20 +190,27 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.n_tile);
                 for (int kb = 0; kb < g.kblocks; ++kb) {
-                    mbar_wait(bar(SepBars::w_full, ws), wph);
                     mbar_wait(bar(SepBars::a_full, as), aph);
-                    tc_fence_after();
-                    const uint32_t sa = a_addr(as), sb = w_addr(ws);
+                    const uint32_t sa = a_addr(as);
+                    const int rem_k = g.k - kb * CB;                             // ragged K tail: only the k16 steps that hold channels
+                    const int ksteps = rem_k >= CB ? CB / 16 : (rem_k + 15) / 16;
+                    for (int hf = 0; hf < g.n_halves; ++hf) {
+                        mbar_wait(bar(SepBars::w_full, ws), wph);
+                        tc_fence_after();
+                        const uint32_t sb = w_addr(ws);
 #pragma unroll
-                    for (int k = 0; k < CB / 16; ++k)
-                        tc_mma_bf16(d_tmem, sep_smem_desc(sa + k * 32), sep_smem_desc(sb + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < CB / 16; ++k)
+                            if (k < ksteps)
+                                tc_mma_bf16(d_tmem + (uint32_t)(hf * g.n_half), sep_smem_desc(sa + k * 32), sep_smem_desc(sb + k * 32), idesc,
+                                            (uint32_t)((kb | k) != 0));
+                        tc_commit(bar(SepBars::w_empty, ws));
+                        if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
+                    }
                     tc_commit(bar(SepBars::a_empty, as));
-                    tc_commit(bar(SepBars::w_empty, ws));
                     if (++as == SEP_A_STAGES) { as = 0; aph ^= 1; }
-                    if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
                 }
                 tc_commit(bar(SepBars::tfull, acc));
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == g.acc_bufs) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp < SEP_FIRST_DW_WARP) {
@@ -249,22 +276,39 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 }
                 if (g.stg_bufs == 2) buf ^= 1;
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == g.acc_bufs) { acc = 0; acc_phase ^= 1; }
         }
         if (issuer) bulk_wait_all();                                     // smem must outlive the last bulk store
     } else {
         // ===================== depthwise producers of the A tile (warps 6..15) =====================
-        const int dwtid = threadIdx.x - SEP_FIRST_DW_WARP * 32;
-        const int cl = dwtid % LPP;                                       // which 16 B (8 channels) of the pixel
-        const int group = dwtid / LPP;
-        // fixed strip of this group inside every sub-tile: row-fastest so neighbouring groups sit on neighbouring rows
-        const bool has_strip = group < g.strips_per_sub;
-        const int srow_ = has_strip ? group % g.ths : 0;
-        const int sg = has_strip ? group / g.ths : 0;
-        const uint32_t rowb = (uint32_t)g.twi * PIXB;
-        const uint32_t strip_off = (uint32_t)(srow_ * S) * rowb + (uint32_t)(sg * PXT * S) * PIXB + (uint32_t)cl * 16u;
-        const uint32_t wgt_off = g.wgt_off + (uint32_t)cl * 32u;
-        const int col_first = sg * PXT;
+        // Lane l owns channels 2l, 2l+1 of the 64-channel k-block (4 B of every pixel), a warp owns a segment: a column
+        // strip of 4 output pixels x up to seg_rows rows.  It slides down the rows keeping the input-row window of the 3x3
+        // stencil in registers (fp32 pairs for dilation 1, bf16 pairs otherwise), so every patch element is read from
+        // shared memory once per segment, unpacked once, and the 9 x 2 weights + bias stay in registers for the whole
+        // k-block.  The rows entering the window at the next step are prefetched before the FMAs of the current one.
+        // One ld.shared.b32 / st.shared.b32 is one conflict-free 128 B wavefront per warp.
+        using Cfg = SepDwCfg<S, D>;
+        constexpr int NR = Cfg::NR, NCOLS = Cfg::NCOLS, PRE = Cfg::PRE;
+        constexpr bool SLIDE = Cfg::SLIDE, UNPACKED = Cfg::UNPACKED, PREFETCH = Cfg::UNPACKED;
+        constexpr int NNEW = SLIDE ? S : 3;                          // input rows loaded per step
+        const int dw_warp = warp - SEP_FIRST_DW_WARP;
+        const uint32_t rowb = (uint32_t)g.twi * 128u;
+        // this warp's (at most two) segments inside every sub-tile
+        int seg_col[2], seg_r0[2], seg_n[2];
+        uint32_t seg_off[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int seg = dw_warp + i * SEP_DW_WARPS;
+            const bool has = seg < g.segs_per_sub;
+            const int cs = has ? seg % g.spr : 0, rs = has ? seg / g.spr : 0;
+            seg_col[i] = cs * 4;
+            seg_r0[i] = rs * g.seg_rows;
+            seg_n[i] = has ? min(g.seg_rows, g.ths - seg_r0[i]) : 0;
+            seg_off[i] = (uint32_t)(seg_r0[i] * S) * rowb + (uint32_t)(seg_col[i] * S) * 128u + (uint32_t)lane * 4u;
+        }
+        const uint32_t a_lane = (uint32_t)(lane >> 2) << 4 | (uint32_t)(lane & 3) << 2;   // 16 B chunk | byte inside it
+        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(0.f, 0.f), hi2 = __floats2bfloat162_rn(6.f, 6.f);
+        auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
 
         int ps = 0, as = 0;
         uint32_t pph = 0, aph = 0;
@@ -274,81 +318,112 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 const uint32_t a_stage = a_addr(as);
                 for (int sub = 0; sub < g.subs; ++sub) {
                     mbar_wait(bar(SepBars::patch_full, ps), pph);
-                    const int orow = sub * g.ths + srow_;                 // tile-local output row
-                    if (has_strip && orow < g.th) {
-                        const uint32_t stage = p_addr(ps);
-                        const uint32_t wsm = stage + wgt_off;
-                        float2 acc[PXT][4];
-                        {
-                            const float4 b0 = lds_f4(wsm + 9 * 64 * 4), b1 = lds_f4(wsm + 9 * 64 * 4 + 16);
+                    const uint32_t stage = p_addr(ps);
+                    float2 wk[9], bias2;
+                    {
+                        const uint32_t wsm = stage + g.wgt_off + (uint32_t)lane * 8u;
 #pragma unroll
-                            for (int p = 0; p < PXT; ++p) {
-                                acc[p][0] = make_float2(b0.x, b0.y); acc[p][1] = make_float2(b0.z, b0.w);
-                                acc[p][2] = make_float2(b1.x, b1.y); acc[p][3] = make_float2(b1.z, b1.w);
-                            }
-                        }
-                        const uint32_t strip = stage + strip_off;
+                        for (int t = 0; t < 9; ++t) wk[t] = lds_f2(wsm + (uint32_t)t * 256u);
+                        bias2 = lds_f2(wsm + 9 * 256u);
+                    }
+#pragma unroll 1
+                    for (int i = 0; i < 2; ++i) {
+                        const int s_r0 = i ? seg_r0[1] : seg_r0[0], s_col = i ? seg_col[1] : seg_col[0];
+                        const int orow0 = sub * g.ths + s_r0;
+                        const int nrows = min(i ? seg_n[1] : seg_n[0], g.th - orow0);   // rows of this segment inside the tile
+                        if (nrows <= 0) continue;
+                        const uint32_t src = stage + (i ? seg_off[1] : seg_off[0]);
+                        const int ncol_ok = g.tw - s_col;                               // pixels p < ncol_ok exist
+                        int arow = orow0 * g.tw + s_col;                                // A-tile row == TMEM lane == staging row
+
+                        float2 ringf[UNPACKED ? NR : 1][NCOLS];                         // the window, unpacked (dilation 1)
+                        uint32_t ringp[UNPACKED ? 1 : NR][NCOLS];                       // ... or packed bf16 pairs
+                        uint32_t nxt[PREFETCH ? NNEW : 1][NCOLS];                       // rows entering the window next
+                        if (SLIDE) {
 #pragma unroll
-                        for (int ky = 0; ky < 3; ++ky) {
-                            float2 wv[3][4];
+                            for (int r = 0; r < PRE; ++r)
 #pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const float4 w0 = lds_f4(wsm + (uint32_t)((ky * 3 + kx) * 64 * 4)),
-                                             w1 = lds_f4(wsm + (uint32_t)((ky * 3 + kx) * 64 * 4 + 16));
-                                wv[kx][0] = make_float2(w0.x, w0.y); wv[kx][1] = make_float2(w0.z, w0.w);
-                                wv[kx][2] = make_float2(w1.x, w1.y); wv[kx][3] = make_float2(w1.z, w1.w);
-                            }
-                            const uint32_t rowp = strip + (uint32_t)(ky * D) * rowb;
-#pragma unroll
-                            for (int col = 0; col < NCOLS; ++col) {
-                                bool used = false;
-#pragma unroll
-                                for (int p = 0; p < PXT; ++p)
-#pragma unroll
-                                    for (int kx = 0; kx < 3; ++kx) used |= (p * S + kx * D == col);
-                                if (!used) continue;
-                                const uint4 r = ld_shared_v4(rowp + (uint32_t)col * PIXB);
-                                float2 v[4];                               // bf16 -> f32 is a 16-bit shift
-                                v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
-                                v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
-                                v[2] = make_float2(__uint_as_float(r.z << 16), __uint_as_float(r.z & 0xffff0000u));
-                                v[3] = make_float2(__uint_as_float(r.w << 16), __uint_as_float(r.w & 0xffff0000u));
-#pragma unroll
-                                for (int p = 0; p < PXT; ++p)
-#pragma unroll
-                                    for (int kx = 0; kx < 3; ++kx)
-                                        if (p * S + kx * D == col) {
-#pragma unroll
-                                            for (int j = 0; j < 4; ++j) acc[p][j] = ffma2(v[j], wv[kx][j], acc[p][j]);
-                                        }
-                            }
-                        }
-                        // + ReLU6 (round first, clamp after: 0 and 6 are exact in bf16 and rounding is monotone)
-                        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(0.f, 0.f), hi2 = __floats2bfloat162_rn(6.f, 6.f);
-#pragma unroll
-                        for (int p = 0; p < PXT; ++p) {
-                            const int col = col_first + p;
-                            if (col < g.tw) {
-                                uint32_t o[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    __nv_bfloat162 h = __hmin2(__hmax2(__floats2bfloat162_rn(acc[p][j].x, acc[p][j].y), lo2), hi2);
-                                    o[j] = *reinterpret_cast<uint32_t *>(&h);
+                                for (int c = 0; c < NCOLS; ++c) {
+                                    const uint32_t v = lds_u32(src + (uint32_t)r * rowb + (uint32_t)c * 128u);
+                                    if (UNPACKED) ringf[r][c] = unpack(v); else ringp[r][c] = v;
                                 }
-                                const int r = orow * g.tw + col;          // A-tile row == TMEM lane == staging row
-                                st_shared_v4(a_stage + (uint32_t)r * 128u + (uint32_t)((cl ^ (r & 7)) << 4), o[0], o[1], o[2], o[3]);
+                            if (PREFETCH) {
+#pragma unroll
+                                for (int n = 0; n < S; ++n)
+#pragma unroll
+                                    for (int c = 0; c < NCOLS; ++c) nxt[n][c] = lds_u32(src + (uint32_t)(PRE + n) * rowb + (uint32_t)c * 128u);
+                            }
+                        }
+#pragma unroll 1
+                        for (int t0 = 0; t0 < nrows; t0 += NR) {
+#pragma unroll
+                            for (int j = 0; j < NR; ++j) {
+                                const int t = t0 + j;
+                                if (t >= nrows) break;
+                                if (PREFETCH) {
+                                    // the prefetched rows enter the window ...
+#pragma unroll
+                                    for (int n = 0; n < NNEW; ++n)
+#pragma unroll
+                                        for (int c = 0; c < NCOLS; ++c) {
+                                            const int slot = (PRE + j * S + n) % NR;
+                                            if (UNPACKED) ringf[slot][c] = unpack(nxt[n][c]); else ringp[slot][c] = nxt[n][c];
+                                        }
+                                    // ... and the next step's rows are requested before this step's math
+                                    if (t + 1 < nrows) {
+#pragma unroll
+                                        for (int n = 0; n < NNEW; ++n) {
+                                            const uint32_t rp = src + (uint32_t)(PRE + (t + 1) * S + n) * rowb;
+#pragma unroll
+                                            for (int c = 0; c < NCOLS; ++c) nxt[n][c] = lds_u32(rp + (uint32_t)c * 128u);
+                                        }
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int n = 0; n < NNEW; ++n) {
+                                        const int slot = SLIDE ? (PRE + j * S + n) % NR : n;
+                                        const uint32_t rp = src + (uint32_t)(SLIDE ? PRE + t * S + n : t * S + n * D) * rowb;
+#pragma unroll
+                                        for (int c = 0; c < NCOLS; ++c) ringp[slot][c] = lds_u32(rp + (uint32_t)c * 128u);
+                                    }
+                                }
+                                float2 acc[4] = {bias2, bias2, bias2, bias2};
+#pragma unroll
+                                for (int ky = 0; ky < 3; ++ky) {
+                                    const int slot = SLIDE ? (j * S + ky * D) % NR : ky;
+#pragma unroll
+                                    for (int c = 0; c < NCOLS; ++c) {
+                                        const float2 v = UNPACKED ? ringf[slot][c] : unpack(ringp[slot][c]);
+#pragma unroll
+                                        for (int p = 0; p < 4; ++p)
+#pragma unroll
+                                            for (int kx = 0; kx < 3; ++kx)
+                                                if (p * S + kx * D == c) acc[p] = ffma2(v, wk[ky * 3 + kx], acc[p]);
+                                    }
+                                }
+#pragma unroll
+                                for (int p = 0; p < 4; ++p) {
+                                    // ReLU6: round first, clamp after (0 and 6 are exact in bf16, rounding is monotone)
+                                    __nv_bfloat162 h = __hmin2(__hmax2(__floats2bfloat162_rn(acc[p].x, acc[p].y), lo2), hi2);
+                                    const uint32_t r = (uint32_t)(arow + p);
+                                    sts_u32_if(a_stage + ((r << 7) | a_lane) ^ ((r & 7u) << 4), *reinterpret_cast<uint32_t *>(&h), p < ncol_ok);
+                                }
+                                arow += g.tw;
                             }
                         }
                     }
-                    mbar_arrive(bar(SepBars::patch_empty, ps));           // this thread no longer reads the patch
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(SepBars::patch_empty, ps));   // this warp no longer reads the patch
                     if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
                 }
                 fence_async_smem();                                       // A-tile writes -> visible to the tensor core
-                mbar_arrive(bar(SepBars::a_full, as));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(SepBars::a_full, as));
                 if (++as == SEP_A_STAGES) { as = 0; aph ^= 1; }
             }
         }
     }
+
 
     tc_fence_before();
     __syncthreads();
@@ -383,19 +458,28 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     g.ho = (h + 2 * g.pad - 2 * dil - 1) / stride + 1;
     g.wo = (wd + 2 * g.pad - 2 * dil - 1) / stride + 1;
     PN_CHECK_ARG(g.ho > 0 && g.wo > 0, "pn_sepconv_block: empty output");
-    const int cb = (k <= 32 && stride == 1 && dil == 1) ? 32 : 64;   // 64 B pixels exist for the stride-1 first block only
-    const int lpp = cb / 8, ngroups = SEP_DW_THREADS / lpp, pxt = stride == 1 ? 4 : 2;
+    const int cb = 64;
+    const bool slide = dil == 1;
+    const int ncols = 3 * stride + 2 * dil + 1, pre = slide ? 2 * dil + 1 - stride : 0;
     g.kblocks = ceil_div(k, cb);
-    g.n_tiles = ceil_div(nc, 256);
+    // Output columns per tile: up to 256 double-buffered in TMEM (the epilogue of tile i overlaps the main loop of tile
+    // i+1), or up to 512 as two UMMA column blocks single-buffered -- the depthwise work, which bounds the deep layers,
+    // is then done once per 512 output channels instead of once per 256.
+    g.n_tiles = ceil_div(nc, 512);
     g.n_tile = nc / g.n_tiles;
-    PN_CHECK_ARG(g.n_tile * g.n_tiles == nc && g.n_tile % 16 == 0, "pn_sepconv_block: cout %d does not split into tiles", nc);
+    g.n_halves = g.n_tile > 256 ? 2 : 1;
+    g.n_half = g.n_tile / g.n_halves;
+    PN_CHECK_ARG(g.n_tile * g.n_tiles == nc && g.n_half * g.n_halves == g.n_tile && g.n_half % 16 == 0,
+                 "pn_sepconv_block: cout %d does not split into tiles", nc);
     g.panels = ceil_div(g.n_tile, 64);
-    g.tmem_cols = next_pow2_cols(g.n_tile + g.panels * 64);
-    PN_CHECK_ARG(g.tmem_cols <= 512, "pn_sepconv_block: TMEM budget exceeded");
-    g.w_stage_bytes = (unsigned)g.n_tile * 128u;
+    g.acc_bufs = g.n_halves == 2 ? 1 : 2;
+    g.tmem_cols = g.n_halves == 2 ? 512 : next_pow2_cols(g.n_tile + g.panels * 64);
+    PN_CHECK_ARG(g.tmem_cols <= 512 && g.panels * 64 <= 512, "pn_sepconv_block: TMEM budget exceeded");
+    g.w_stage_bytes = (unsigned)g.n_half * 128u;
 
     // ---- tile search: fewest (tiles x per-tile cost); one strip per depthwise thread group per sub-tile
-    const int fixed = SEP_A_STAGES * SEP_A_BYTES + SEP_STG_BYTES + 2 * (int)g.w_stage_bytes + 1024 + 256;   // minimum non-patch smem
+    const int min_w = g.n_halves == 2 ? 3 : 2;                     // W ring entries (one per UMMA column block)
+    const int fixed = SEP_A_STAGES * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 256;   // minimum non-patch smem
     double best = 1e300;
     for (int th = 1; th <= 64; ++th) {
         for (int tw = 1; tw <= 64; ++tw) {
@@ -405,21 +489,35 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
                 const int ths = ceil_div(th, subs);
                 if ((subs - 1) * ths >= th) continue;                      // an empty last sub-tile
                 const int thi = (ths - 1) * stride + 2 * dil + 1;
-                int twi = (tw - 1) * stride + 2 * dil + 1;
-                if (cb == 32 && twi % 2 == 0) ++twi;                       // 64 B pixels: odd row pitch staggers the banks
+                const int twi = (tw - 1) * stride + 2 * dil + 1;
                 if (thi > 256 || twi > 256) continue;
                 const long long box = (long long)thi * twi * cb * 2;
                 const long long stage = ((box + 127) & ~127ll) + SEP_WGT_BYTES;
-                const int spr = ceil_div(tw, pxt), sps = ths * spr;
-                if (sps > ngroups) continue;
+                // segments: 4-pixel column strips x seg_rows rows, at most two per depthwise warp and sub-tile
+                const int spr = ceil_div(tw, 4);
+                int seg_rows = 1;
+                while (spr * ceil_div(ths, seg_rows) > SEP_DW_WARPS && seg_rows < ths) ++seg_rows;
+                int segs = spr * ceil_div(ths, seg_rows);
+                if (segs > SEP_DW_WARPS) {                                 // one pass impossible: allow two segments per warp
+                    seg_rows = 1;
+                    while (spr * ceil_div(ths, seg_rows) > 2 * SEP_DW_WARPS && seg_rows < ths) ++seg_rows;
+                    segs = spr * ceil_div(ths, seg_rows);
+                    if (segs > 2 * SEP_DW_WARPS) continue;
+                }
+                const int passes = ceil_div(segs, SEP_DW_WARPS);
                 const long long room = SEP_SMEM_MAX - fixed;
                 const int pst = (int)(room / stage);
                 if (pst < 2 || pst < subs + 1) continue;
                 const long long tiles = (long long)ceil_div(g.ho, th) * ceil_div(g.wo, tw);
-                // per k-block cycles: depthwise issue ~ 110 cycles per busy warp (+ hand-off per sub-tile), tensor pipe 2 cycles
-                // per output column, patch fill at ~40 B/clk
-                const double dwc = (double)subs * (ceil_div(sps * lpp, 32) * 110.0 + 120.0);
-                const double mma = (cb / 64.0) * 2.0 * g.n_tile;
+                // per k-block cycles.  A depthwise step (4 pixels x 64 channels, one warp) issues ~45 + 10 per window column
+                // instructions (+ ~1.3 per preloaded element); the warp that owns the longest segment chain sets the latency
+                // (~1.6 cycles per instruction when few warps share a scheduler), all warps together the issue time (4
+                // schedulers).  Tensor pipe: 2 cycles per output column.  Patch fill at ~40 B/clk.
+                const double step = 45.0 + 10.0 * ncols * (slide ? (stride + 2.0) / 3.0 : 1.0), prol = 1.3 * pre * ncols + 40.0;
+                const double lat = (double)subs * (passes * (seg_rows * step + prol) * 1.6 + 150.0);
+                const double issue = (double)subs * (spr * (ths * step + ceil_div(ths, seg_rows) * prol)) / 4.0;
+                const double dwc = lat > issue ? lat : issue;
+                const double mma = 2.0 * g.n_tile;                          // per k-block, all column blocks
                 const double fill = (double)subs * stage / 40.0;
                 double per_kb = dwc > mma ? dwc : mma;
                 if (fill > per_kb) per_kb = fill;
@@ -429,7 +527,8 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
                 const double cost = (double)tiles * (g.kblocks * per_kb + 400.0 + 200.0 * g.panels);
                 if (cost < best) {
                     best = cost;
-                    g.th = th; g.tw = tw; g.subs = subs; g.ths = ths; g.thi = thi; g.twi = twi; g.spr = spr; g.strips_per_sub = sps;
+                    g.th = th; g.tw = tw; g.subs = subs; g.ths = ths; g.thi = thi; g.twi = twi; g.spr = spr; g.seg_rows = seg_rows;
+                    g.segs_per_sub = segs;
                     g.patch_box_bytes = (unsigned)box;
                     g.wgt_off = (unsigned)((box + 127) & ~127ll);
                     g.patch_stage_bytes = (unsigned)stage;
@@ -444,13 +543,13 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     // ---- shared-memory carve-up: patches get what is left after W (2-3 stages), A, staging (1-2 panels)
     int bestp = -1;
     for (int stg = 2; stg >= 1; --stg)
-        for (int wst = 3; wst >= 2; --wst) {
+        for (int wst = SEP_MAX_W; wst >= min_w; --wst) {
             const long long rest = SEP_SMEM_MAX - 1024 - 256 - SEP_A_STAGES * SEP_A_BYTES - (long long)stg * SEP_STG_BYTES - (long long)wst * g.w_stage_bytes;
             if (rest <= 0) continue;
             int pst = (int)(rest / g.patch_stage_bytes);
             if (pst > SEP_MAX_P) pst = SEP_MAX_P;
             const int want = 3 * g.subs > SEP_MAX_P ? SEP_MAX_P : 3 * g.subs;
-            const int score = (pst >= want ? 100 : pst * 10) + wst * 2 + stg;    // deep patch prefetch first
+            const int score = (pst >= want ? 100 : pst * 10) + (wst > min_w + 1 ? min_w + 1 : wst) * 2 + stg;    // deep patch prefetch first
             if (pst >= 2 && pst >= g.subs + 1 && score > bestp) {
                 bestp = score;
                 g.p_stages = pst; g.w_stages = wst; g.stg_bufs = stg;
@@ -500,7 +599,7 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
     {   // pointwise weights [Nc, K] bf16, box [64, n_tile], 128B swizzle
         const uint64_t dims[2] = {(uint64_t)k, (uint64_t)nc};
         const uint64_t strides[1] = {(uint64_t)k * 2};
-        const uint32_t box[2] = {64u, (uint32_t)g.n_tile};
+        const uint32_t box[2] = {64u, (uint32_t)g.n_half};
         if ((rc = encode_tmap(op->tmap_w, pw_w, 2, 2, dims, strides, box, 3)) != PN_OK) return rc;
     }
     {   // output (C, W, H, N) bf16, box [64, tw, th, 1], 128B swizzle
@@ -512,10 +611,10 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
     return PN_OK;
 }
 
-template <int CB, int S, int D>
+template <int S, int D>
 static int sep_launch_t(const SepOp *op, const SepGeom &g, const float *pw_bias, cudaStream_t st) {
     static bool configured = false;
-    auto kern = sepconv_kernel<CB, S, D>;
+    auto kern = sepconv_kernel<S, D>;
     if (!configured) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SEP_SMEM_MAX));
         configured = true;
@@ -534,21 +633,18 @@ int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t st) {
     PN_CHECK_ARG(op && pw_bias, "pn_sepconv_block: null pointer");
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    if (op->cb == 32) {
-        PN_CHECK_ARG(op->stride == 1 && op->dil == 1, "pn_sepconv_block: cin <= 32 is only built for stride 1, dilation 1");
-        return sep_launch_t<32, 1, 1>(op, g, pw_bias, st);
-    }
-    if (op->stride == 2) return sep_launch_t<64, 2, 1>(op, g, pw_bias, st);
-    if (op->dil == 1) return sep_launch_t<64, 1, 1>(op, g, pw_bias, st);
-    if (op->dil == 2) return sep_launch_t<64, 1, 2>(op, g, pw_bias, st);
-    return sep_launch_t<64, 1, 4>(op, g, pw_bias, st);
+    if (op->stride == 2) return sep_launch_t<2, 1>(op, g, pw_bias, st);
+    if (op->dil == 1) return sep_launch_t<1, 1>(op, g, pw_bias, st);
+    if (op->dil == 2) return sep_launch_t<1, 2>(op, g, pw_bias, st);
+    return sep_launch_t<1, 4>(op, g, pw_bias, st);
 }
 
 void sep_describe(const SepOp *op, char *out, size_t cap) {
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    snprintf(out, cap, "tile %dx%d subs %d box %dx%d n_tile %d x%d kblocks %d stages p%d w%d stg%d smem %d tiles %lld", g.th, g.tw,
-             g.subs, g.thi, g.twi, g.n_tile, g.n_tiles, g.kblocks, g.p_stages, g.w_stages, g.stg_bufs, op->smem_bytes, g.tiles);
+    snprintf(out, cap, "tile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d stages p%d w%d stg%d smem %d tiles %lld",
+             g.th, g.tw, g.subs, g.thi, g.twi, g.segs_per_sub, g.seg_rows, g.n_tile, g.n_halves, g.n_half, g.n_tiles, g.kblocks, g.p_stages,
+             g.w_stages, g.stg_bufs, op->smem_bytes, g.tiles);
 }
 
 }  // namespace pn
