@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libposenet_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("PN_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _sources():

@@ -23,6 +23,7 @@
 //                              STORE of a [64 ch, TW, TH] box (the tensor map clips image edges and ragged N).
 // The segment -> warp assignment is fixed for the whole kernel (no integer division in the loop).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -34,7 +35,7 @@ constexpr int SEP_DW_WARPS = 10;
 constexpr int SEP_FIRST_DW_WARP = 6;
 constexpr int SEP_THREADS = (SEP_FIRST_DW_WARP + SEP_DW_WARPS) * 32;   // 512
 constexpr int SEP_DW_THREADS = SEP_DW_WARPS * 32;                      // 320
-constexpr int SEP_A_STAGES = 2;
+constexpr int SEP_MAX_A = 4;
 constexpr int SEP_A_BYTES = 128 * 128;                                 // 128 rows x 64 bf16
 constexpr int SEP_STG_BYTES = 128 * 128;                               // one 128 x 64 bf16 output panel
 constexpr int SEP_MAX_P = 6, SEP_MAX_W = 4;
@@ -48,16 +49,16 @@ struct SepGeom {
     int tiles_x, tiles_y, n_tiles, n_tile, panels, tmem_cols;
     int n_halves, n_half, acc_bufs;       // a tile's accumulator = n_halves UMMA column blocks of n_half (<= 256) columns
     int kblocks;
-    int p_stages, w_stages, stg_bufs;
+    int p_stages, w_stages, a_stages, stg_bufs;
     unsigned patch_stage_bytes, patch_box_bytes, wgt_off, w_stage_bytes;
-    unsigned off_a, off_stg, off_patch, off_bar;   // from the 1024-aligned base; W stages sit at 0
+    unsigned off_a, off_stg, off_patch, off_bias, off_bar;   // from the 1024-aligned base; W stages sit at 0
     long long tiles;                      // m_tiles * n_tiles
 };
 
 struct SepBars {       // byte offsets of the mbarriers inside the barrier block
     static constexpr int patch_full = 0, patch_empty = 8 * SEP_MAX_P, w_full = 16 * SEP_MAX_P,
                          w_empty = 16 * SEP_MAX_P + 8 * SEP_MAX_W, a_full = 16 * SEP_MAX_P + 16 * SEP_MAX_W,
-                         a_empty = a_full + 8 * SEP_A_STAGES, tfull = a_empty + 8 * SEP_A_STAGES, tempty = tfull + 16,
+                         a_empty = a_full + 8 * SEP_MAX_A, tfull = a_empty + 8 * SEP_MAX_A, tempty = tfull + 16,
                          tmem_slot = tempty + 16, total = tmem_slot + 16;
 };
 
@@ -68,6 +69,17 @@ __device__ __forceinline__ uint32_t sep_idesc(int n) {                   // D f3
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 __device__ __forceinline__ void sep_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {             // non-blocking phase test
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
     float2 r;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
@@ -92,6 +104,19 @@ template <int S, int D> struct SepDwCfg {
     static constexpr int NCOLS = 3 * S + 2 * D + 1;
     static constexpr int PRE = SLIDE ? 2 * D + 1 - S : 0;
 };
+
+// Optional timeline trace (compile with -DPN_SEP_TRACE, see tools/trace_sep.py): block 0 stamps clock64 per role.
+#ifdef PN_SEP_TRACE
+__device__ long long *g_sep_trace = nullptr;
+__device__ int g_sep_trace_cap = 0;
+#define SEP_TRACE(role, idx, what)                                                                               \
+    do {                                                                                                         \
+        if (blockIdx.x == 0 && g_sep_trace && (idx) < g_sep_trace_cap)                                           \
+            g_sep_trace[((role) * g_sep_trace_cap + (idx)) * 4 + (what)] = clock64();                            \
+    } while (0)
+#else
+#define SEP_TRACE(role, idx, what) do { } while (0)
+#endif
 
 template <int S, int D>
 __global__ void __launch_bounds__(SEP_THREADS, 1)
@@ -127,7 +152,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             mbar_init(bar(SepBars::w_full, s), 1);
             mbar_init(bar(SepBars::w_empty, s), 1);
         }
-        for (int s = 0; s < SEP_A_STAGES; ++s) {
+        for (int s = 0; s < g.a_stages; ++s) {
             mbar_init(bar(SepBars::a_full, s), SEP_DW_WARPS);
             mbar_init(bar(SepBars::a_empty, s), 1);
         }
@@ -143,6 +168,11 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    {   // pointwise bias -> shared memory once (the epilogue reads it per panel)
+        float *sbias = reinterpret_cast<float *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bias);
+        const int ncp = g.n_tiles * g.panels * 64;                // padded so that ragged panels read zeros
+        for (int i = threadIdx.x; i < ncp; i += SEP_THREADS) sbias[i] = i < g.nc ? __ldg(pw_bias + i) : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -150,32 +180,59 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer =====================
+        // One thread feeds two independent rings -- input patches (+ depthwise weights) and pointwise weight blocks --
+        // each with its own cursor over (tile, k-block, ...), polled without blocking so that a full W ring never holds
+        // back a patch load (the depthwise warps run ahead of the MMA by the depth of the A ring).
         if (lane == 0) {
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
-            for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
-                const int n_tile = (int)(tile % g.n_tiles);
-                const int m_tile = (int)(tile / g.n_tiles);
-                const int img = m_tile / m_tiles_per_img;
-                const int rem = m_tile - img * m_tiles_per_img;
-                const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
-                for (int kb = 0; kb < g.kblocks; ++kb) {
-                    for (int sub = 0; sub < g.subs; ++sub) {
-                        mbar_wait(bar(SepBars::patch_empty, ps), pph ^ 1);
+            long long p_tile = blockIdx.x, w_tile = blockIdx.x;
+            int p_kb = 0, p_sub = 0, w_kb = 0, w_hf = 0;
+            int p_img = 0, p_ty = 0, p_tx = 0, w_col = 0;
+            bool p_new = true, w_new = true;
+            const long long t0 = clock64();
+            while (p_tile < g.tiles || w_tile < g.tiles) {
+                bool progress = false;
+                if (p_tile < g.tiles) {
+                    if (p_new) {
+                        const int m_tile = (int)(p_tile / g.n_tiles);
+                        p_img = m_tile / m_tiles_per_img;
+                        const int rem = m_tile - p_img * m_tiles_per_img;
+                        p_ty = rem / g.tiles_x;
+                        p_tx = rem - p_ty * g.tiles_x;
+                        p_new = false;
+                    }
+                    if (mbar_test(bar(SepBars::patch_empty, ps), pph ^ 1)) {
                         const uint32_t full = bar(SepBars::patch_full, ps);
                         mbar_expect_tx(full, g.patch_box_bytes + SEP_WGT_BYTES);
-                        tma_load_4d(p_addr(ps), &tmap_x, full, kb * CB, tx * g.tw * S - g.pad,
-                                    (ty * g.th + sub * g.ths) * S - g.pad, img);
-                        tma_load_2d(p_addr(ps) + g.wgt_off, &tmap_dww, full, kb * CB, 0);
-                        tma_load_2d(p_addr(ps) + g.wgt_off + 9 * 64 * 4, &tmap_dwb, full, kb * CB, 0);
+                        tma_load_4d(p_addr(ps), &tmap_x, full, p_kb * CB, p_tx * g.tw * S - g.pad,
+                                    (p_ty * g.th + p_sub * g.ths) * S - g.pad, p_img);
+                        tma_load_2d(p_addr(ps) + g.wgt_off, &tmap_dww, full, p_kb * CB, 0);
+                        tma_load_2d(p_addr(ps) + g.wgt_off + 9 * 64 * 4, &tmap_dwb, full, p_kb * CB, 0);
                         if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
+                        if (++p_sub == g.subs) {
+                            p_sub = 0;
+                            if (++p_kb == g.kblocks) { p_kb = 0; p_tile += gridDim.x; p_new = true; }
+                        }
+                        progress = true;
                     }
-                    for (int hf = 0; hf < g.n_halves; ++hf) {
-                        mbar_wait(bar(SepBars::w_empty, ws), wph ^ 1);
+                }
+                if (w_tile < g.tiles) {
+                    if (w_new) { w_col = (int)(w_tile % g.n_tiles) * g.n_tile; w_new = false; }
+                    if (mbar_test(bar(SepBars::w_empty, ws), wph ^ 1)) {
                         mbar_expect_tx(bar(SepBars::w_full, ws), g.w_stage_bytes);
-                        tma_load_2d(w_addr(ws), &tmap_w, bar(SepBars::w_full, ws), kb * CB, n_tile * g.n_tile + hf * g.n_half);
+                        tma_load_2d(w_addr(ws), &tmap_w, bar(SepBars::w_full, ws), w_kb * CB, w_col + w_hf * g.n_half);
                         if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
+                        if (++w_hf == g.n_halves) {
+                            w_hf = 0;
+                            if (++w_kb == g.kblocks) { w_kb = 0; w_tile += gridDim.x; w_new = true; }
+                        }
+                        progress = true;
                     }
+                }
+                if (!progress && clock64() - t0 > 20000000000ll) {     // ~10 s: a protocol bug, never a slow kernel
+                    printf("posenet_b200: sepconv producer timeout (block %d)\n", blockIdx.x);
+                    __trap();
                 }
             }
         }
@@ -183,14 +240,17 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = sep_idesc(g.n_half);
-            int as = 0, ws = 0, acc = 0;
+            int as = 0, ws = 0, acc = 0, tr_i = 0;
             uint32_t aph = 0, wph = 0, acc_phase = 0;
+            (void)tr_i;
             for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
                 mbar_wait(bar(SepBars::tempty, acc), acc_phase ^ 1);
                 tc_fence_after();
+                SEP_TRACE(1, tr_i, 0);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.n_tile);
                 for (int kb = 0; kb < g.kblocks; ++kb) {
                     mbar_wait(bar(SepBars::a_full, as), aph);
+                    SEP_TRACE(1, tr_i, 1);
                     const uint32_t sa = a_addr(as);
                     const int rem_k = g.k - kb * CB;                             // ragged K tail: only the k16 steps that hold channels
                     const int ksteps = rem_k >= CB ? CB / 16 : (rem_k + 15) / 16;
@@ -207,7 +267,9 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
                     }
                     tc_commit(bar(SepBars::a_empty, as));
-                    if (++as == SEP_A_STAGES) { as = 0; aph ^= 1; }
+                    SEP_TRACE(1, tr_i, 2);
+                    ++tr_i;
+                    if (++as == g.a_stages) { as = 0; aph ^= 1; }
                 }
                 tc_commit(bar(SepBars::tfull, acc));
                 if (++acc == g.acc_bufs) { acc = 0; acc_phase ^= 1; }
@@ -219,8 +281,9 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const int row_in_tile = q * 32 + lane;
         const bool issuer = (threadIdx.x == 64);
         const uint32_t staging = base + g.off_stg;
-        int acc = 0, buf = 0;
+        int acc = 0, buf = 0, tr_e = 0;
         uint32_t acc_phase = 0;
+        (void)tr_e;
         for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
             const int n_tile = (int)(tile % g.n_tiles);
             const int m_tile = (int)(tile / g.n_tiles);
@@ -229,6 +292,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
             mbar_wait(bar(SepBars::tfull, acc), acc_phase);
             tc_fence_after();
+            if (issuer) SEP_TRACE(2, tr_e, 0);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * g.n_tile);
 #pragma unroll 1
             for (int p = 0; p < g.panels; ++p) {
@@ -249,12 +313,8 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {                        // 8 columns -> one 16 B chunk, 128B-swizzled
-                        const int cc = col0 + hf * 32 + c * 8;
-                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                        if (cc < g.nc) {                                 // nc % 8 == 0
-                            b0 = __ldg(reinterpret_cast<const float4 *>(pw_bias + cc));
-                            b1 = __ldg(reinterpret_cast<const float4 *>(pw_bias + cc + 4));
-                        }
+                        const uint32_t bsm = base + g.off_bias + (uint32_t)(col0 + hf * 32 + c * 8) * 4u;
+                        const float4 b0 = lds_f4(bsm), b1 = lds_f4(bsm + 16);
                         const __nv_bfloat162 h0 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 0]) + b0.x),
                                                                         relu6f(__uint_as_float(v[8 * c + 1]) + b0.y));
                         const __nv_bfloat162 h1 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 2]) + b0.z),
@@ -276,6 +336,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 }
                 if (g.stg_bufs == 2) buf ^= 1;
             }
+            if (issuer) { SEP_TRACE(2, tr_e, 1); ++tr_e; }
             if (++acc == g.acc_bufs) { acc = 0; acc_phase ^= 1; }
         }
         if (issuer) bulk_wait_all();                                     // smem must outlive the last bulk store
@@ -310,14 +371,18 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const __nv_bfloat162 lo2 = __floats2bfloat162_rn(0.f, 0.f), hi2 = __floats2bfloat162_rn(6.f, 6.f);
         auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
 
-        int ps = 0, as = 0;
+        int ps = 0, as = 0, tr_d = 0;
         uint32_t pph = 0, aph = 0;
+        (void)tr_d;
         for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
             for (int kb = 0; kb < g.kblocks; ++kb) {
+                if (dw_warp == 0 && lane == 0) SEP_TRACE(0, tr_d, 0);
                 mbar_wait(bar(SepBars::a_empty, as), aph ^ 1);            // the MMAs that read this A stage have retired
+                if (dw_warp == 0 && lane == 0) SEP_TRACE(0, tr_d, 1);
                 const uint32_t a_stage = a_addr(as);
                 for (int sub = 0; sub < g.subs; ++sub) {
                     mbar_wait(bar(SepBars::patch_full, ps), pph);
+                    if (dw_warp == 0 && lane == 0 && sub == 0) SEP_TRACE(0, tr_d, 2);
                     const uint32_t stage = p_addr(ps);
                     float2 wk[9], bias2;
                     {
@@ -418,8 +483,9 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 }
                 fence_async_smem();                                       // A-tile writes -> visible to the tensor core
                 __syncwarp();
+                if (dw_warp == 0 && lane == 0) { SEP_TRACE(0, tr_d, 3); ++tr_d; }
                 if (lane == 0) mbar_arrive(bar(SepBars::a_full, as));
-                if (++as == SEP_A_STAGES) { as = 0; aph ^= 1; }
+                if (++as == g.a_stages) { as = 0; aph ^= 1; }
             }
         }
     }
@@ -479,7 +545,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
 
     // ---- tile search: fewest (tiles x per-tile cost); one strip per depthwise thread group per sub-tile
     const int min_w = g.n_halves == 2 ? 3 : 2;                     // W ring entries (one per UMMA column block)
-    const int fixed = SEP_A_STAGES * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 256;   // minimum non-patch smem
+    const int fixed = 2 * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 256 + 4224;   // minimum non-patch smem
     double best = 1e300;
     for (int th = 1; th <= 64; ++th) {
         for (int tw = 1; tw <= 64; ++tw) {
@@ -540,26 +606,41 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     g.tiles_x = ceil_div(g.wo, g.tw);
     g.tiles_y = ceil_div(g.ho, g.th);
     g.tiles = (long long)n * g.tiles_x * g.tiles_y * g.n_tiles;
-    // ---- shared-memory carve-up: patches get what is left after W (2-3 stages), A, staging (1-2 panels)
+    // ---- shared-memory carve-up: W ring, A ring, output staging panels, patch ring, bias, barriers
+    const long long bias_bytes = ((long long)g.n_tiles * g.panels * 64 * 4 + 127) & ~127ll;
+    const long long avail = SEP_SMEM_MAX - 1024 - 256 - bias_bytes;
+    auto fits = [&](int pst, int wst, int ast, int stg) {
+        return (long long)wst * g.w_stage_bytes + (long long)ast * SEP_A_BYTES + (long long)stg * SEP_STG_BYTES +
+                   (long long)pst * g.patch_stage_bytes <= avail;
+    };
     int bestp = -1;
     for (int stg = 2; stg >= 1; --stg)
-        for (int wst = SEP_MAX_W; wst >= min_w; --wst) {
-            const long long rest = SEP_SMEM_MAX - 1024 - 256 - SEP_A_STAGES * SEP_A_BYTES - (long long)stg * SEP_STG_BYTES - (long long)wst * g.w_stage_bytes;
-            if (rest <= 0) continue;
-            int pst = (int)(rest / g.patch_stage_bytes);
-            if (pst > SEP_MAX_P) pst = SEP_MAX_P;
-            const int want = 3 * g.subs > SEP_MAX_P ? SEP_MAX_P : 3 * g.subs;
-            const int score = (pst >= want ? 100 : pst * 10) + (wst > min_w + 1 ? min_w + 1 : wst) * 2 + stg;    // deep patch prefetch first
-            if (pst >= 2 && pst >= g.subs + 1 && score > bestp) {
-                bestp = score;
-                g.p_stages = pst; g.w_stages = wst; g.stg_bufs = stg;
-            }
-        }
+        for (int ast = 3; ast >= 2; --ast)
+            for (int wst = SEP_MAX_W; wst >= min_w; --wst)
+                for (int pst = SEP_MAX_P; pst >= 2 && pst >= g.subs + 1; --pst) {
+                    if (!fits(pst, wst, ast, stg)) continue;
+                    const int want = 3 * g.subs > SEP_MAX_P ? SEP_MAX_P : 3 * g.subs;
+                    // deep patch prefetch first, then one spare W block, a third A stage, a second staging panel
+                    const int score = (pst >= want ? 1000 : pst * 100) + (wst > min_w + 1 ? min_w + 1 : wst) * 20 + ast * 8 + stg * 4 +
+                                      (pst > want ? 1 : 0);
+                    if (score > bestp) {
+                        bestp = score;
+                        g.p_stages = pst; g.w_stages = wst; g.a_stages = ast; g.stg_bufs = stg;
+                    }
+                }
     PN_CHECK_ARG(bestp >= 0, "pn_sepconv_block: shared memory budget exceeded");
+    if (const char *force = getenv("PN_SEP_STAGES")) {              // tuning aid: "p,w,a,stg"
+        int fp = 0, fw = 0, fa = 0, fs = 0;
+        if (sscanf(force, "%d,%d,%d,%d", &fp, &fw, &fa, &fs) == 4 && fp >= g.subs + 1 && fp <= SEP_MAX_P && fw >= min_w &&
+            fw <= SEP_MAX_W && fa >= 2 && fa <= SEP_MAX_A && fs >= 1 && fs <= 2 && fits(fp, fw, fa, fs)) {
+            g.p_stages = fp; g.w_stages = fw; g.a_stages = fa; g.stg_bufs = fs;
+        }
+    }
     g.off_a = (unsigned)g.w_stages * g.w_stage_bytes;
-    g.off_stg = g.off_a + SEP_A_STAGES * SEP_A_BYTES;
+    g.off_stg = g.off_a + (unsigned)g.a_stages * SEP_A_BYTES;
     g.off_patch = g.off_stg + (unsigned)g.stg_bufs * SEP_STG_BYTES;
-    g.off_bar = g.off_patch + (unsigned)g.p_stages * g.patch_stage_bytes;
+    g.off_bias = g.off_patch + (unsigned)g.p_stages * g.patch_stage_bytes;
+    g.off_bar = g.off_bias + (unsigned)bias_bytes;
     op->smem_bytes = (int)(g.off_bar + SepBars::total + 1024);
     PN_CHECK_ARG(op->smem_bytes <= SEP_SMEM_MAX, "pn_sepconv_block: internal smem accounting error (%d)", op->smem_bytes);
     static_assert(sizeof(SepGeom) <= sizeof(op->geom), "SepOp::geom too small");
@@ -642,9 +723,18 @@ int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t st) {
 void sep_describe(const SepOp *op, char *out, size_t cap) {
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    snprintf(out, cap, "tile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d stages p%d w%d stg%d smem %d tiles %lld",
+    snprintf(out, cap, "tile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d stages p%d w%d a%d stg%d smem %d tiles %lld",
              g.th, g.tw, g.subs, g.thi, g.twi, g.segs_per_sub, g.seg_rows, g.n_tile, g.n_halves, g.n_half, g.n_tiles, g.kblocks, g.p_stages,
-             g.w_stages, g.stg_bufs, op->smem_bytes, g.tiles);
+             g.w_stages, g.a_stages, g.stg_bufs, op->smem_bytes, g.tiles);
 }
 
 }  // namespace pn
+
+#ifdef PN_SEP_TRACE
+// debug only: trace buffer = 3 roles x cap events x 4 stamps (int64), zero-filled by the caller
+extern "C" int pn_debug_sep_trace(long long *buf, int cap) {
+    if (cudaMemcpyToSymbol(pn::g_sep_trace, &buf, sizeof(buf)) != cudaSuccess) return -2;
+    if (cudaMemcpyToSymbol(pn::g_sep_trace_cap, &cap, sizeof(cap)) != cudaSuccess) return -2;
+    return 0;
+}
+#endif

@@ -86,7 +86,7 @@ def test_sepconv_rejects_unsupported():
 
 @pytest.mark.parametrize("mid,os_,H,W,N", [(101, 16, 513, 513, 2), (50, 8, 193, 257, 1), (75, 32, 257, 257, 3), (101, 8, 129, 129, 1)])
 def test_fused_plan_matches_unfused_plan(mid, os_, H, W, N):
-    """Whole network: the fused plan (15 launches) against the two-kernel-per-block plan (28 launches)."""
+    """Whole network: the fused plan (15 launches + 1 per block wider than 512) against the two-kernel-per-block plan (28)."""
     sd = onet.init_params(mid, seed=3)
     m = posenet.MobileNetV1(mid, output_stride=os_)
     m.load_state_dict(sd)
@@ -96,7 +96,8 @@ def test_fused_plan_matches_unfused_plan(mid, os_, H, W, N):
     n_fused = m.num_launches(N, H, W)
     unfused = m.set_fused(False)(x.to(DEV))
     n_unfused = m.num_launches(N, H, W)
-    assert (n_fused, n_unfused) == (15, 28)
+    wide = sum(1 for L in m._layers[1:] if L["outp"] > 512)      # blocks wider than one 512-column tile stay two kernels
+    assert (n_fused, n_unfused) == (15 + wide, 28)
     for a, b in zip(fused, unfused):
         err = float((a - b).abs().max() / b.abs().max())
         assert err < 2e-3, err
