@@ -13,5 +13,6 @@ from posenet import sharding  # noqa: F401  (multi-GPU: shard images, gather pos
 from posenet.decode_multi import decode_multiple_poses, decode_multiple_poses_batch  # noqa: F401
 from posenet.models.model_factory import load_model, write_random_checkpoint  # noqa: F401
 from posenet.models import MobileNetV1, MOBILENET_V1_CHECKPOINTS  # noqa: F401
+from posenet.pipeline import BatchPipeline  # noqa: F401  (streaming batches: copies overlap the kernels)
 from posenet.utils import *  # noqa: F401,F403
 from posenet.utils import _process_input, process_input_gpu  # noqa: F401

@@ -29,14 +29,24 @@ def _as_maps(t, channels, device):
     return t.to(device) if t.device != device else t
 
 
+def split_pose_records(flat, n, P):
+    """Views of the packed record buffer ``flat`` (float64 [n*P*86], torch or numpy): pose_scores [n,P],
+    keypoint_scores [n,P,17], keypoint_coords [n,P,17,2], pose_offsets [n,P,17,2]."""
+    K = NUM_KEYPOINTS
+    o1, o2, o3 = n * P, n * P * (1 + K), n * P * (1 + K * 3)
+    return (flat[:o1].reshape(n, P), flat[o1:o2].reshape(n, P, K), flat[o2:o3].reshape(n, P, K, 2),
+            flat[o3:].reshape(n, P, K, 2))
+
+
 def decode_multiple_poses_batch(scores, offsets, displacements_fwd, displacements_bwd, output_stride,
                                 max_pose_detections=10, score_threshold=0.5, nms_radius=20, min_pose_score=0.5,
-                                workspace=None):
+                                workspace=None, out=None):
     """Decode N images at once, everything staying on the device (no synchronisation).
 
     Inputs are [N,17|34|32|32,h,w] fp32 CUDA tensors with any strides.  Returns
     ``(pose_scores [N,P], keypoint_scores [N,P,17], keypoint_coords [N,P,17,2], pose_offsets [N,P,17,2],
-    pose_counts [N] int32)`` as CUDA tensors (float64 like the reference's numpy outputs).
+    pose_counts [N] int32)`` as CUDA tensors (float64 like the reference's numpy outputs); the first four
+    are views of one packed buffer (``out``: optional preallocated float64 [N*P*86], zeroed here).
     """
     nat.require_device()
     lib = nat.load()
@@ -56,12 +66,12 @@ def decode_multiple_poses_batch(scores, offsets, displacements_fwd, displacement
     if ws is None:
         ws = workspace[key] = dict(keys=torch.empty((n, cap), dtype=torch.int64, device=dev),
                                    counts=torch.empty(n, dtype=torch.int32, device=dev))
-    out = torch.zeros(n * P * (1 + NUM_KEYPOINTS * 5), dtype=torch.float64, device=dev)
-    o1, o2, o3 = n * P, n * P * (1 + NUM_KEYPOINTS), n * P * (1 + NUM_KEYPOINTS * 3)
-    ps = out[:o1].view(n, P)
-    ks = out[o1:o2].view(n, P, NUM_KEYPOINTS)
-    kc = out[o2:o3].view(n, P, NUM_KEYPOINTS, 2)
-    ko = out[o3:].view(n, P, NUM_KEYPOINTS, 2)
+    if out is None:
+        out = torch.zeros(n * P * (1 + NUM_KEYPOINTS * 5), dtype=torch.float64, device=dev)
+    else:
+        assert out.dtype == torch.float64 and out.numel() == n * P * (1 + NUM_KEYPOINTS * 5) and out.is_contiguous()
+        out.zero_()
+    ps, ks, kc, ko = split_pose_records(out, n, P)
     pose_counts = torch.empty(n, dtype=torch.int32, device=dev)
     maps = [nat.make_map(t) for t in (heat, off, fwd, bwd)]
     prm = nat.DecodeParams(int(output_stride), P, float(nms_radius ** 2), float(min_pose_score))
