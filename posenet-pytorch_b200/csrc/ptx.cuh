@@ -59,6 +59,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *tmap, uint
         "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// 1-D bulk copy global -> shared (16-byte aligned addresses and size), completing on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
 __device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src),
                  "r"(c0), "r"(c1)

@@ -4,7 +4,10 @@
 // One thread per output pixel, all COUT channels in registers, weights broadcast from shared memory.
 // Input is either the reference's f32 NCHW tensor, or (fused P1, identity resize) the uint8 BGR
 // HWC image itself, normalised on the fly with the same two rounded fp32 ops as utils.py:23.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace pn {
 
@@ -67,6 +70,244 @@ __global__ void __launch_bounds__(128) stem_kernel(const void *__restrict__ xin,
     }
 }
 
+// ---- tensor-core stem for the production path (uint8 image in, bf16 NHWC out) ----------------------------------
+// The SIMT kernel above is bound by FFMA issue (27 x COUT FMAs per pixel, 6x the HBM time).  Here the layer is an
+// im2col GEMM on tcgen05: per tile of 128 output pixels, A[128, 32] holds the 27 taps (+5 zero columns) as bf16 and
+// W[32, 32] the weights; two UMMAs (K = 16) replace 864 FMAs per pixel.  Pixel bytes are exact in bf16, so the
+// normalisation x*(2/255)-1 of utils.py:23 is folded into the operands without losing the pixel value:
+//     x*(2/255) - 1 = (x - 128)*(2/255) + 1/255,   A = x - 128 (exact, in [-128, 127]),   W' = bf16(w * 2/255),
+//     bias' = b + sum_k w_k / 255,   and a padded tap holds -0.5, which normalises to exactly 0 (the reference's zero
+// padding of the normalised image).  Centring on 128 avoids the cancellation a raw-pixel formulation would have.
+// One CTA = 128 threads = 128 pixels; several CTAs per SM overlap each other's load / MMA / store phases.  The
+// tile's input bytes are one contiguous span of the image batch (whole rows), fetched with a bulk async copy.
+constexpr int STC_THREADS = 128;
+constexpr int STC_NBUF = 2;                          // span ring: the next tile's bytes load while this one is computed
+
+__device__ __forceinline__ uint64_t stc_smem_desc(uint32_t saddr) {      // K-major SWIZZLE_128B (see gemm_tc.cu)
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct StemTcArgs {
+    const uint8_t *img;
+    const float *w27, *bias;
+    __nv_bfloat16 *y;
+    int n, h, w, ho, wo, stride, cout;
+    long long total_px, total_bytes16;     // pixels; image bytes rounded up to 16
+    int span_cap;                          // bytes per span buffer (multiple of 16)
+};
+
+__global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a) {
+    extern __shared__ uint8_t stc_raw[];
+    const uint32_t base = (smem_u32(stc_raw) + 1023u) & ~1023u;
+    uint8_t *gen = stc_raw + (base - smem_u32(stc_raw));
+    const uint32_t sA = base;                         // 128 rows x 128 B (first 64 B of a row = K 0..31)
+    const uint32_t sW = base + 16384;                 // 32 rows x 128 B
+    const uint32_t sSpan = base + 16384 + 4096;       // STC_NBUF x span_cap
+    float *sBias = reinterpret_cast<float *>(gen + 16384 + 4096 + STC_NBUF * a.span_cap);
+    const uint32_t bars = base + 16384 + 4096 + STC_NBUF * (uint32_t)a.span_cap + 128;   // span_full[NBUF], mma_done, tmem slot
+    const uint32_t mma_bar = bars + 8u * STC_NBUF, tmem_slot_addr = mma_bar + 8u;
+    volatile uint32_t *tmem_slot =
+        reinterpret_cast<volatile uint32_t *>(gen + 16384 + 4096 + STC_NBUF * a.span_cap + 128 + 8 * STC_NBUF + 8);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long row_bytes = (long long)a.w * 3;
+    const long long num_tiles = (a.total_px + 127) / 128;
+
+    // span of tile t: the whole input rows its pixels read, as [lo16, lo16 + size)
+    // (all pixel indices fit 32 bits: the launcher checks total_px < 2^31)
+    auto span_of = [&](long long t, long long &lo16, uint32_t &size) {
+        const uint32_t m0 = (uint32_t)t * 128u, m1 = min(m0 + 127u, (uint32_t)a.total_px - 1u);
+        const uint32_t r0 = m0 / (uint32_t)a.wo, r1 = m1 / (uint32_t)a.wo;        // global output row = img * ho + oy
+        const int i0 = (int)(r0 / (uint32_t)a.ho), i1 = (int)(r1 / (uint32_t)a.ho);
+        const int oy0 = (int)(r0 - (uint32_t)i0 * (uint32_t)a.ho), oy1 = (int)(r1 - (uint32_t)i1 * (uint32_t)a.ho);
+        const int iy0 = max(oy0 * a.stride - 1, 0), iy1 = min(oy1 * a.stride + 1, a.h - 1);
+        const long long lo = ((long long)i0 * a.h + iy0) * row_bytes, hi = ((long long)i1 * a.h + iy1 + 1) * row_bytes;
+        lo16 = lo & ~15ll;
+        long long end = (hi + 15) & ~15ll;
+        if (end > a.total_bytes16) end = a.total_bytes16;
+        size = (uint32_t)(end - lo16);
+    };
+
+    if (tid == 0) {
+        for (int i = 0; i < STC_NBUF; ++i) mbar_init(bars + 8u * i, 1);
+        mbar_init(mma_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "r"(32u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // W'[n][k] = bf16(w[k][n] * 2/255) in the swizzled K-major layout; bias' = b + sum_k w_k / 255
+    for (int i = tid; i < 32 * 4; i += STC_THREADS) {               // (row n, 16-byte chunk c) -> 8 k values
+        const int nrow = i >> 2, c = i & 3;
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k0 = c * 8 + 2 * j;
+            const float w0 = (nrow < a.cout && k0 < 27) ? a.w27[k0 * a.cout + nrow] * (float)(2.0 / 255.0) : 0.f;
+            const float w1 = (nrow < a.cout && k0 + 1 < 27) ? a.w27[(k0 + 1) * a.cout + nrow] * (float)(2.0 / 255.0) : 0.f;
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(w0, w1);
+            pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
+        }
+        st_shared_v4(sW + (uint32_t)nrow * 128u + (uint32_t)((c ^ (nrow & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+    }
+    if (tid < 32) {
+        float sum = 0.f;
+        if (tid < a.cout)
+            for (int k = 0; k < 27; ++k) sum += a.w27[k * a.cout + tid];
+        sBias[tid] = tid < a.cout ? a.bias[tid] + sum * (float)(1.0 / 255.0) : 0.f;
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+    long long tile = blockIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < STC_NBUF - 1; ++i) {
+            const long long t = tile + (long long)i * gridDim.x;
+            if (t >= num_tiles) break;
+            long long lo16; uint32_t size;
+            span_of(t, lo16, size);
+            mbar_expect_tx(bars + 8u * i, size);
+            bulk_load_1d(sSpan + (uint32_t)i * (uint32_t)a.span_cap, a.img + lo16, size, bars + 8u * i);
+        }
+    }
+    uint32_t span_phase = 0, mma_phase = 0;             // bit b of span_phase = parity of ring slot b
+    int buf = 0;
+    for (; tile < num_tiles; tile += gridDim.x, buf = (buf + 1) % STC_NBUF) {
+        long long lo16; uint32_t size;
+        span_of(tile, lo16, size);
+        const long long m = tile * 128 + tid;
+        const bool live = m < a.total_px;
+        int img_i = 0, oy = 0, ox = 0;
+        if (live) {
+            const uint32_t r = (uint32_t)m / (uint32_t)a.wo;
+            ox = (int)((uint32_t)m - r * (uint32_t)a.wo);
+            img_i = (int)(r / (uint32_t)a.ho);
+            oy = (int)(r - (uint32_t)img_i * (uint32_t)a.ho);
+        }
+        mbar_wait(bars + 8u * buf, (span_phase >> buf) & 1u);
+        span_phase ^= 1u << buf;
+        // ---- im2col: this thread's pixel -> row `tid` of A
+        float f[32];
+#pragma unroll
+        for (int k = 27; k < 32; ++k) f[k] = 0.f;
+        const uint32_t sp = sSpan + (uint32_t)buf * (uint32_t)a.span_cap;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * a.stride - 1 + ky;
+            const bool row_ok = live && iy >= 0 && iy < a.h;
+            const long long rowoff = ((long long)img_i * a.h + iy) * row_bytes - lo16;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * a.stride - 1 + kx;
+                const bool ok = row_ok && ix >= 0 && ix < a.w;
+                const uint32_t addr = sp + (uint32_t)(ok ? rowoff + (long long)ix * 3 : 0);
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {                   // BGR bytes -> RGB taps; 2^23 + 128 + (x - 128) trick
+                    const uint32_t x = lds_u8(addr + (uint32_t)(2 - ci));
+                    f[(ky * 3 + kx) * 3 + ci] = ok ? __uint_as_float(0x4B000000u | x) - 8388736.0f : -0.5f;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[c * 8 + 2 * j], f[c * 8 + 2 * j + 1]);
+                pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
+            }
+            st_shared_v4(sA + (uint32_t)tid * 128u + (uint32_t)((c ^ (tid & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();                                         // A complete; the previous tile's TMEM reads are done
+        if (tid == 0) {
+            const long long next = tile + (long long)(STC_NBUF - 1) * gridDim.x;
+            if (next < num_tiles) {                              // refill the slot the previous tile has just released
+                const int nb = (buf + STC_NBUF - 1) % STC_NBUF;
+                long long nlo; uint32_t nsize;
+                span_of(next, nlo, nsize);
+                mbar_expect_tx(bars + 8u * nb, nsize);
+                bulk_load_1d(sSpan + (uint32_t)nb * (uint32_t)a.span_cap, a.img + nlo, nsize, bars + 8u * nb);
+            }
+            tc_fence_after();
+            tc_mma_bf16(tmem, stc_smem_desc(sA), stc_smem_desc(sW), IDESC, 0u);
+            tc_mma_bf16(tmem, stc_smem_desc(sA + 32), stc_smem_desc(sW + 32), IDESC, 1u);
+            tc_commit(mma_bar);
+        }
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        uint32_t v[32];
+        tc_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+        tc_ld_wait();
+        if (live) {
+            const __nv_bfloat162 lo2 = __floats2bfloat162_rn(0.f, 0.f), hi2 = __floats2bfloat162_rn(6.f, 6.f);
+            uint4 *dst = reinterpret_cast<uint4 *>(a.y + (size_t)m * a.cout);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c * 8 < a.cout) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = c * 8 + 2 * j;
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[col]) + sBias[col], __uint_as_float(v[col + 1]) + sBias[col + 1]);
+                        h2 = __hmin2(__hmax2(h2, lo2), hi2);
+                        o[j] = *reinterpret_cast<uint32_t *>(&h2);
+                    }
+                    dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
+    }
+}
+
+static bool stem_tc_usable(const void *x, const void *y, int cout, int h, int wd) {
+    return ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && cout % 8 == 0 && cout <= 32 && h >= 1 && wd >= 1 &&
+           getenv("PN_STEM_SIMT") == nullptr;
+}
+
+static int launch_stem_tc(const uint8_t *img, const float *w, const float *b, void *y, int n, int h, int wd, int ho, int wo,
+                          int stride, int cout, cudaStream_t st) {
+    StemTcArgs a;
+    a.img = img; a.w27 = w; a.bias = b; a.y = (__nv_bfloat16 *)y;
+    a.n = n; a.h = h; a.w = wd; a.ho = ho; a.wo = wo; a.stride = stride; a.cout = cout;
+    a.total_px = (long long)n * ho * wo;
+    if (a.total_px >= (1ll << 31) - 256) return 1;                // 32-bit pixel indexing inside the kernel
+    a.total_bytes16 = ((long long)n * h * wd * 3 + 15) & ~15ll;
+    // rows a 128-pixel tile can touch: its output rows (at most 128/wo + 2, across an image boundary too) x stride + 2
+    const long long rows_out = 128 / wo + 2;
+    long long span = (rows_out * stride + 2) * (long long)wd * 3 + 32;
+    span = (span + 127) & ~127ll;
+    const long long smem = 16384 + 4096 + STC_NBUF * span + 128 + 128 + 1024;
+    if (smem > 200 * 1024) return 1;                              // does not fit: caller falls back to the SIMT kernel
+    a.span_cap = (int)span;
+    static int configured = 0;
+    if (configured < smem) {
+        PN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = (int)smem;
+    }
+    const long long tiles = (a.total_px + 127) / 128;
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    const long long max_ctas = (long long)num_sms() * per_sm;
+    const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+    stem_tc_kernel<<<grid, STC_THREADS, (size_t)smem, st>>>(a);
+    PN_CHECK_LAUNCH();
+    return PN_OK;
+}
+
 template <int COUT, bool IN_U8>
 static int launch_t(const void *x, const float *w, const float *b, void *y, int n, int h, int wd, int ho, int wo,
                     int stride, int out_dtype, cudaStream_t st) {
@@ -86,6 +327,10 @@ int launch_stem(const void *x, bool x_is_u8, const float *w, const float *b, voi
     PN_CHECK_ARG(stride == 1 || stride == 2, "pn_stem_conv: stride must be 1 or 2 (got %d)", stride);
     PN_CHECK_ARG(out_dtype == PN_F32 || out_dtype == PN_BF16, "pn_stem_conv: bad dtype %d", out_dtype);
     const int ho = (h + 2 - 3) / stride + 1, wo = (wd + 2 - 3) / stride + 1;
+    if (x_is_u8 && out_dtype == PN_BF16 && stem_tc_usable(x, y, cout, h, wd)) {   // production path: tcgen05 im2col GEMM
+        const int rc = launch_stem_tc((const uint8_t *)x, w, b, y, n, h, wd, ho, wo, stride, cout, st);
+        if (rc <= 0) return rc;                                                  // rc > 0: span too large, use the SIMT kernel
+    }
 #define PN_STEM_CASE(C)                                                                                  \
     if (cout == C)                                                                                       \
         return x_is_u8 ? launch_t<C, true>(x, w, b, y, n, h, wd, ho, wo, stride, out_dtype, st)          \

@@ -60,10 +60,14 @@ def test_forward_full_size_config1(dtype):
     assert tuple(got[0].shape) == (2, 17, 33, 33)
     errs = head_err(got, ref)
     assert max(errs) < TOL[dtype], errs
-    # fused uint8 path == preprocess + forward, bit for bit
+    # fused uint8 path (normalisation inside the stem) vs preprocess + forward: bit for bit in fp32 mode; in bf16 mode
+    # the stem runs on the tensor cores with the normalisation folded into its operands -> same tolerance vs the oracle
     got_u8 = m.forward_u8(torch.from_numpy(np.stack(imgs)).to(DEV))
-    for a, b in zip(got, got_u8):
-        assert torch.equal(a, b)
+    if dtype == "fp32":
+        for a, b in zip(got, got_u8):
+            assert torch.equal(a, b)
+    else:
+        assert max(head_err(got_u8, ref)) < TOL[dtype], head_err(got_u8, ref)
 
 
 def test_chaotic_init_per_layer_parity_bf16():

@@ -75,6 +75,30 @@ def test_stem_u8_equals_preprocess_then_stem():
     assert torch.equal(y1, y2)
 
 
+@pytest.mark.parametrize("cout,n,h,w", [(32, 2, 513, 513), (16, 1, 721, 1281), (24, 3, 257, 257), (32, 5, 33, 47), (16, 2, 7, 5),
+                                        (32, 1, 1, 1), (24, 4, 2, 300), (32, 3, 129, 64), (16, 1, 64, 2049)])
+def test_stem_u8_tensor_core(cout, n, h, w):
+    """Production stem: uint8 BGR image -> bf16 NHWC through the tcgen05 im2col GEMM (normalisation folded into
+    the operands) against normalise-then-conv in fp32 (utils.py:23 + mobilenet_v1.py:47-54)."""
+    rng = np.random.default_rng(cout + h)
+    img = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    img[0, :, :1] = 255                                           # saturated borders: padding must contribute exactly 0
+    img[-1, -1:, :] = 0
+    torch.manual_seed(cout)
+    wt, b = torch.randn(cout, 3, 3, 3) * 0.25, torch.randn(cout) * 0.3
+    x = torch.from_numpy(img[..., ::-1].copy()).permute(0, 3, 1, 2).float() * (2.0 / 255.0) - 1.0
+    ref = F.relu6(F.conv2d(x, wt, b, stride=2, padding=1)).permute(0, 2, 3, 1)
+    w27 = wt.permute(2, 3, 1, 0).reshape(27, cout).contiguous().to(DEV)
+    y = abi.stem(torch.from_numpy(img).to(DEV), w27, b.to(DEV), 2, nat.PN_BF16, u8=True)
+    torch.cuda.synchronize()
+    y = y.float().cpu()
+    assert y.shape == ref.shape, (y.shape, ref.shape)
+    assert rel_err(y, ref) < 8e-3
+    assert float((y - ref).abs().mean()) < 3e-3 * float(ref.abs().mean() + 1e-3)
+    y2 = abi.stem(torch.from_numpy(img).to(DEV), w27, b.to(DEV), 2, nat.PN_BF16, u8=True).float().cpu()
+    assert torch.equal(y, y2)
+
+
 # ------------------------------------------------------------------------------------- B3
 @pytest.mark.parametrize("c,stride,dil,h,w", [(32, 1, 1, 33, 47), (64, 2, 1, 33, 47), (128, 2, 1, 32, 32), (256, 1, 2, 17, 23),
                                               (256, 1, 4, 19, 19), (24, 1, 1, 9, 9), (48, 2, 1, 65, 65), (512, 1, 1, 33, 33),
