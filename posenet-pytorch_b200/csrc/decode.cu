@@ -71,8 +71,19 @@ __global__ void __launch_bounds__(256) candidates_kernel(pn_map heat, int h, int
 }
 
 // ---------------------------------------------------------------------------------- D: greedy decode
+// The reference walks the sorted candidates one by one; per accepted pose it pays 16 dependent displacement hops
+// (2 dependent gathers each), which is pure latency.  decode_pose (decode.py:131-182) does not depend on the poses
+// accepted so far -- only the root NMS test and the instance score do -- so a block decodes in ROUNDS:
+//   (a) screen: all threads test the next candidates against the accepted poses and compact the survivors, in
+//       order, into up to DEC_BATCH slots (candidates suppressed now stay suppressed: poses are only ever added);
+//   (b) speculate: one thread per slot runs the full 32-step decode_pose, all slots in parallel;
+//   (c) commit: warp 0 replays the reference's greedy loop over the slots in order -- root NMS against every accepted
+//       pose (including those of this round), instance score, acceptance -- from shared memory only.
+// The sequence of accepted poses and every float64 operation is the reference's; only the latency is shared.
 constexpr int DEC_THREADS = 256;
-constexpr int DEC_KBUF = 4096;          // candidate keys sorted per round in shared memory (32 KB)
+constexpr int DEC_KBUF = 4096;          // candidate keys sorted per chunk in shared memory (32 KB)
+constexpr int DEC_BATCH = 128;          // slots decoded speculatively per round
+constexpr int DEC_ACC = 64;             // accepted poses whose coordinates are cached in shared memory
 
 struct DecodeArgs {
     pn_map heat, off, fwd, bwd;
@@ -87,15 +98,17 @@ struct DecodeArgs {
 
 struct DecodeShared {
     uint64_t keys[DEC_KBUF];
-    unsigned hist[256];
-    double ks[PN_NUM_PARTS];
-    double kc[PN_NUM_PARTS][2];
-    double ko[PN_NUM_PARTS][2];
+    // speculative pose records, [part][slot]: a warp's accesses to one part are conflict-free
+    double kc[PN_NUM_PARTS][2][DEC_BATCH];
+    float ks[PN_NUM_PARTS][DEC_BATCH];
+    float ko[PN_NUM_PARTS][2][DEC_BATCH];
+    uint32_t cand[DEC_BATCH];           // flat (part, y, x) index of each slot's root
+    double acc[DEC_ACC][PN_NUM_PARTS][2];   // keypoint coordinates of the accepted poses (the first DEC_ACC)
     double vals[PN_NUM_PARTS];
+    unsigned hist[256];
+    int warp_cnt[DEC_THREADS / 32];
     uint64_t pivot;
-    int cnt;
-    int npose;
-    int done;
+    int cnt, npose, done, next_ci;
 };
 
 // decode.py:15-16 / :50-51 -- np.clip(np.round(p / stride), 0, hi).astype(int32): f64 divide, half-even.
@@ -123,22 +136,22 @@ __device__ double np_sum(const double *a, int n) {
     return res;
 }
 
-// decode.py:9-63: one displacement hop source -> target along edge e (lane 0 of warp 0 only).
-__device__ __forceinline__ void hop(const DecodeArgs &a, DecodeShared &S, int img, const pn_map &disp, int e, int src,
+// decode.py:9-63: one displacement hop source -> target along edge e, on the pose record in slot `s`.
+__device__ __forceinline__ void hop(const DecodeArgs &a, DecodeShared &S, int s, int img, const pn_map &disp, int e, int src,
                                     int tgt) {
     const double stride = (double)a.prm.output_stride;
-    const double sy = S.kc[src][0], sx = S.kc[src][1];
+    const double sy = S.kc[src][0][s], sx = S.kc[src][1][s];
     const int iy = to_cell(sy, stride, a.h - 1), ix = to_cell(sx, stride, a.w - 1);
     const double py = __dadd_rn(sy, (double)map_at(disp, img, e, iy, ix));                    // decode.py:39-40
     const double px = __dadd_rn(sx, (double)map_at(disp, img, PN_NUM_EDGES + e, iy, ix));
     const int ty = to_cell(py, stride, a.h - 1), tx = to_cell(px, stride, a.w - 1);
     const float sc = map_at(a.heat, img, tgt, ty, tx);                                        // decode.py:53
     const float oy = map_at(a.off, img, tgt, ty, tx), ox = map_at(a.off, img, PN_NUM_PARTS + tgt, ty, tx);
-    S.ks[tgt] = (double)sc;
-    S.kc[tgt][0] = __dadd_rn((double)(ty * a.prm.output_stride), (double)oy);                 // decode.py:55-56
-    S.kc[tgt][1] = __dadd_rn((double)(tx * a.prm.output_stride), (double)ox);
-    S.ko[tgt][0] = (double)oy;
-    S.ko[tgt][1] = (double)ox;
+    S.ks[tgt][s] = sc;
+    S.kc[tgt][0][s] = __dadd_rn((double)(ty * a.prm.output_stride), (double)oy);              // decode.py:55-56
+    S.kc[tgt][1][s] = __dadd_rn((double)(tx * a.prm.output_stride), (double)ox);
+    S.ko[tgt][0][s] = oy;
+    S.ko[tgt][1][s] = ox;
 }
 
 __device__ __forceinline__ double sqdist(double ay, double ax, double by, double bx) {
@@ -146,14 +159,21 @@ __device__ __forceinline__ double sqdist(double ay, double ax, double by, double
     return __dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx));
 }
 
+// keypoint coordinate c of part `part` of accepted pose p (shared-memory cache, or the output array beyond it)
+__device__ __forceinline__ double acc_coord(const DecodeShared &S, const double *out_kc, int p, int part, int c) {
+    return p < DEC_ACC ? S.acc[p][part][c] : __ldcg(out_kc + ((size_t)p * PN_NUM_PARTS + part) * 2 + c);
+}
+
 __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
-    __shared__ DecodeShared S;
+    extern __shared__ __align__(16) unsigned char dec_smem_raw[];
+    DecodeShared &S = *reinterpret_cast<DecodeShared *>(dec_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.x;
     const int P = a.prm.max_pose_detections;
     const int n = min(a.counts[img], a.capacity);
     const uint64_t *keys = a.keys + (size_t)img * a.capacity;
     const int hw = a.h * a.w;
+    const int os = a.prm.output_stride;
     const double r2 = a.prm.squared_nms_radius;
     double *out_ps = a.pose_scores + (size_t)img * P;
     double *out_ks = a.kp_scores + (size_t)img * P * PN_NUM_PARTS;
@@ -235,86 +255,121 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
                 __syncthreads();
             }
         }
-        // ---- 3. greedy pass over this chunk (warp 0; the chain of dependent gathers is serial)
-        if (warp == 0) {
-            for (int ci = 0; ci < cnt && npose < P; ++ci) {
-                const uint32_t flat = (uint32_t)S.keys[ci];
+        // ---- 3. greedy pass over this chunk, in rounds of up to DEC_BATCH speculatively decoded candidates
+        int ci = 0;
+        while (ci < cnt && npose < P) {
+            // (a) screen candidates ci.. against the npose accepted poses; survivors -> slots, in order
+            int nb = 0, next = ci;
+            while (next < cnt && nb < DEC_BATCH) {
+                const int base = next, i = base + tid;
+                if (tid == 0) S.next_ci = 0x7fffffff;
+                bool keep = false;
+                uint32_t flat = 0;
+                if (i < cnt) {
+                    flat = (uint32_t)S.keys[i];
+                    const int part = flat / hw;
+                    const int rem = flat - part * hw;
+                    const int y = rem / a.w, x = rem - y * a.w;
+                    // decode_multi.py:106-109: int64 cell * stride + fp32 offset -> float64
+                    const double ry = __dadd_rn((double)(y * os), (double)map_at(a.off, img, part, y, x));
+                    const double rx = __dadd_rn((double)(x * os), (double)map_at(a.off, img, PN_NUM_PARTS + part, y, x));
+                    // decode_multi.py:8-11,111-113: same part of any accepted pose within the radius (<=)
+                    keep = true;
+                    for (int p = 0; p < npose; ++p)
+                        if (sqdist(acc_coord(S, out_kc, p, part, 0), acc_coord(S, out_kc, p, part, 1), ry, rx) <= r2) { keep = false; break; }
+                }
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+                if (lane == 0) S.warp_cnt[warp] = __popc(bal);
+                __syncthreads();
+                int pos = nb, total = nb;
+#pragma unroll
+                for (int wi = 0; wi < DEC_THREADS / 32; ++wi) {
+                    const int c = S.warp_cnt[wi];
+                    if (wi < warp) pos += c;
+                    total += c;
+                }
+                pos += __popc(bal & ((1u << lane) - 1));
+                if (keep) {
+                    if (pos < DEC_BATCH) S.cand[pos] = flat;
+                    else atomicMin(&S.next_ci, i);                  // first survivor that did not fit: resume there
+                }
+                __syncthreads();
+                next = total > DEC_BATCH ? S.next_ci : min(base + DEC_THREADS, cnt);
+                nb = min(total, DEC_BATCH);
+                __syncthreads();
+            }
+            // (b) one thread per slot: decode.py:131-182 on its own record
+            if (tid < nb) {
+                const int s = tid;
+                const uint32_t flat = S.cand[s];
                 const int part = flat / hw;
                 const int rem = flat - part * hw;
                 const int y = rem / a.w, x = rem - y * a.w;
-                const float rscore = map_at(a.heat, img, part, y, x);
-                // decode_multi.py:106-109: int64 cell * stride + fp32 offset -> float64
-                const double ry = __dadd_rn((double)(y * a.prm.output_stride), (double)map_at(a.off, img, part, y, x));
-                const double rx = __dadd_rn((double)(x * a.prm.output_stride),
-                                            (double)map_at(a.off, img, PN_NUM_PARTS + part, y, x));
-                // decode_multi.py:8-11,111-113: same part of any accepted pose within the radius (<=)
-                bool hit = false;
-                for (int p = lane; p < npose; p += 32) {
-                    const double cy = __ldcg(out_kc + ((size_t)p * PN_NUM_PARTS + part) * 2);
-                    const double cx = __ldcg(out_kc + ((size_t)p * PN_NUM_PARTS + part) * 2 + 1);
-                    if (sqdist(cy, cx, ry, rx) <= r2) hit = true;
+#pragma unroll
+                for (int k = 0; k < PN_NUM_PARTS; ++k) {
+                    S.ks[k][s] = 0.f;
+                    S.kc[k][0][s] = 0.0; S.kc[k][1][s] = 0.0;
+                    S.ko[k][0][s] = 0.f; S.ko[k][1][s] = 0.f;
                 }
-                if (__any_sync(0xFFFFFFFFu, hit)) continue;
-
-                // decode.py:131-182
-                if (lane < PN_NUM_PARTS) {
-                    S.ks[lane] = 0.0;
-                    S.kc[lane][0] = 0.0; S.kc[lane][1] = 0.0;
-                    S.ko[lane][0] = 0.0; S.ko[lane][1] = 0.0;
+                S.ks[part][s] = map_at(a.heat, img, part, y, x);
+                S.kc[part][0][s] = __dadd_rn((double)(y * os), (double)map_at(a.off, img, part, y, x));
+                S.kc[part][1][s] = __dadd_rn((double)(x * os), (double)map_at(a.off, img, PN_NUM_PARTS + part, y, x));
+                for (int e = PN_NUM_EDGES - 1; e >= 0; --e) {               // backward: child -> parent
+                    const int tgt = c_parent[e], src = c_child[e];
+                    if (S.ks[src][s] > 0.f && S.ks[tgt][s] == 0.f) hop(a, S, s, img, a.bwd, e, src, tgt);
                 }
-                __syncwarp();
-                if (lane == 0) {
-                    S.ks[part] = (double)rscore;
-                    S.kc[part][0] = ry;
-                    S.kc[part][1] = rx;
-                    for (int e = PN_NUM_EDGES - 1; e >= 0; --e) {           // backward: child -> parent
-                        const int tgt = c_parent[e], src = c_child[e];
-                        if (S.ks[src] > 0.0 && S.ks[tgt] == 0.0) hop(a, S, img, a.bwd, e, src, tgt);
-                    }
-                    for (int e = 0; e < PN_NUM_EDGES; ++e) {                // forward: parent -> child
-                        const int src = c_parent[e], tgt = c_child[e];
-                        if (S.ks[src] > 0.0 && S.ks[tgt] == 0.0) hop(a, S, img, a.fwd, e, src, tgt);
-                    }
+                for (int e = 0; e < PN_NUM_EDGES; ++e) {                    // forward: parent -> child
+                    const int src = c_parent[e], tgt = c_child[e];
+                    if (S.ks[src][s] > 0.f && S.ks[tgt][s] == 0.f) hop(a, S, s, img, a.fwd, e, src, tgt);
                 }
-                __syncwarp();
-
-                // decode_multi.py:14-24: keep the parts that are strictly farther than the radius from
-                // that part of EVERY accepted pose; sum in numpy's order; always divide by 17.
-                bool far = lane < PN_NUM_PARTS;
-                if (lane < PN_NUM_PARTS) {
-                    const double ky = S.kc[lane][0], kx = S.kc[lane][1];
-                    for (int p = 0; p < npose; ++p) {
-                        const double cy = __ldcg(out_kc + ((size_t)p * PN_NUM_PARTS + lane) * 2);
-                        const double cx = __ldcg(out_kc + ((size_t)p * PN_NUM_PARTS + lane) * 2 + 1);
-                        if (!(sqdist(cy, cx, ky, kx) > r2)) far = false;
-                    }
-                }
-                const unsigned fmask = __ballot_sync(0xFFFFFFFFu, far);
-                if (far) S.vals[__popc(fmask & ((1u << lane) - 1))] = S.ks[lane];
-                __syncwarp();
-                double score = 0.0;
-                if (lane == 0) score = __ddiv_rn(np_sum(S.vals, __popc(fmask)), (double)PN_NUM_PARTS);
-                score = __shfl_sync(0xFFFFFFFFu, score, 0);
-
-                if (a.prm.min_pose_score == 0.0 || score >= a.prm.min_pose_score) {    // decode_multi.py:128
-                    if (lane == 0) out_ps[npose] = score;
-                    if (lane < PN_NUM_PARTS) {
-                        const size_t o = (size_t)npose * PN_NUM_PARTS + lane;
-                        out_ks[o] = S.ks[lane];
-                        out_kc[o * 2] = S.kc[lane][0];
-                        out_kc[o * 2 + 1] = S.kc[lane][1];
-                        out_ko[o * 2] = S.ko[lane][0];
-                        out_ko[o * 2 + 1] = S.ko[lane][1];
-                    }
-                    ++npose;
-                    __threadfence_block();
-                }
-                __syncwarp();
             }
-            if (lane == 0) S.npose = npose;
+            __syncthreads();
+            // (c) warp 0: the reference's greedy loop over the slots, in candidate order
+            if (warp == 0) {
+                for (int s = 0; s < nb && npose < P; ++s) {
+                    const int part = S.cand[s] / hw;
+                    const double ry = S.kc[part][0][s], rx = S.kc[part][1][s];
+                    bool hit = false;
+                    for (int p = lane; p < npose; p += 32)
+                        if (sqdist(acc_coord(S, out_kc, p, part, 0), acc_coord(S, out_kc, p, part, 1), ry, rx) <= r2) hit = true;
+                    if (__any_sync(0xFFFFFFFFu, hit)) continue;
+                    // decode_multi.py:14-24: keep the parts that are strictly farther than the radius from
+                    // that part of EVERY accepted pose; sum in numpy's order; always divide by 17.
+                    bool far = lane < PN_NUM_PARTS;
+                    double ky = 0.0, kx = 0.0;
+                    if (lane < PN_NUM_PARTS) {
+                        ky = S.kc[lane][0][s]; kx = S.kc[lane][1][s];
+                        for (int p = 0; p < npose; ++p)
+                            if (!(sqdist(acc_coord(S, out_kc, p, lane, 0), acc_coord(S, out_kc, p, lane, 1), ky, kx) > r2)) far = false;
+                    }
+                    const unsigned fmask = __ballot_sync(0xFFFFFFFFu, far);
+                    if (far) S.vals[__popc(fmask & ((1u << lane) - 1))] = (double)S.ks[lane][s];
+                    __syncwarp();
+                    double score = 0.0;
+                    if (lane == 0) score = __ddiv_rn(np_sum(S.vals, __popc(fmask)), (double)PN_NUM_PARTS);
+                    score = __shfl_sync(0xFFFFFFFFu, score, 0);
+                    if (a.prm.min_pose_score == 0.0 || score >= a.prm.min_pose_score) {    // decode_multi.py:128
+                        if (lane == 0) out_ps[npose] = score;
+                        if (lane < PN_NUM_PARTS) {
+                            const size_t o = (size_t)npose * PN_NUM_PARTS + lane;
+                            out_ks[o] = (double)S.ks[lane][s];
+                            out_kc[o * 2] = ky;
+                            out_kc[o * 2 + 1] = kx;
+                            out_ko[o * 2] = (double)S.ko[lane][0][s];
+                            out_ko[o * 2 + 1] = (double)S.ko[lane][1][s];
+                            if (npose < DEC_ACC) { S.acc[npose][lane][0] = ky; S.acc[npose][lane][1] = kx; }
+                        }
+                        ++npose;
+                        __threadfence_block();
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) S.npose = npose;
+            }
+            __syncthreads();
+            npose = S.npose;
+            ci = next;
         }
-        __syncthreads();
-        npose = S.npose;
         lo = pivot;
         remaining -= cnt;
         __syncthreads();
@@ -355,7 +410,12 @@ extern "C" int pn_decode_greedy(const pn_map *heat, const pn_map *off, const pn_
     a.h = h; a.w = wd; a.keys = keys; a.capacity = capacity; a.counts = counts; a.prm = *params;
     a.pose_scores = pose_scores; a.kp_scores = kp_scores; a.kp_coords = kp_coords; a.kp_offsets = kp_offsets;
     a.pose_counts = pose_counts;
-    decode_kernel<<<n_img, DEC_THREADS, 0, as_stream(stream)>>>(a);
+    static bool configured = false;
+    if (!configured) {
+        PN_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared)));
+        configured = true;
+    }
+    decode_kernel<<<n_img, DEC_THREADS, sizeof(DecodeShared), as_stream(stream)>>>(a);
     PN_CHECK_LAUNCH();
     return PN_OK;
 }

@@ -50,13 +50,9 @@ template <> struct Vec16<__nv_bfloat16> {
     static __device__ __forceinline__ void store_relu6(__nv_bfloat16 *p, const float2 (&v)[4]) {
         // round first, clamp after: 0 and 6 are exact in bf16 and rounding is monotone, so this equals
         // clamp-then-round while the clamp runs on packed pairs
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(0.f, 0.f), hi = __floats2bfloat162_rn(6.f, 6.f);
         uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h = __hmin2(__hmax2(__floats2bfloat162_rn(v[j].x, v[j].y), lo), hi);
-            o[j] = *reinterpret_cast<uint32_t *>(&h);
-        }
+        for (int j = 0; j < 4; ++j) o[j] = relu6_bf16x2(v[j]);
         *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 };

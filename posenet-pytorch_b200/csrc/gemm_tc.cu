@@ -200,17 +200,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {                    // 8 columns -> one 16 B chunk, 128B-swizzled
                         const float4 b0 = __ldg(bp + 2 * c), b1 = __ldg(bp + 2 * c + 1);
-                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 0]) + b0.x),
-                                                                        relu6f(__uint_as_float(v[8 * c + 1]) + b0.y));
-                        const __nv_bfloat162 h1 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 2]) + b0.z),
-                                                                        relu6f(__uint_as_float(v[8 * c + 3]) + b0.w));
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 4]) + b1.x),
-                                                                        relu6f(__uint_as_float(v[8 * c + 5]) + b1.y));
-                        const __nv_bfloat162 h3 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 6]) + b1.z),
-                                                                        relu6f(__uint_as_float(v[8 * c + 7]) + b1.w));
-                        st_shared_v4(srow + (uint32_t)((c ^ (row_in_tile & 7)) << 4), *reinterpret_cast<const uint32_t *>(&h0),
-                                     *reinterpret_cast<const uint32_t *>(&h1), *reinterpret_cast<const uint32_t *>(&h2),
-                                     *reinterpret_cast<const uint32_t *>(&h3));
+                        const float2 s0 = fadd2(make_float2(__uint_as_float(v[8 * c + 0]), __uint_as_float(v[8 * c + 1])), make_float2(b0.x, b0.y));
+                        const float2 s1 = fadd2(make_float2(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])), make_float2(b0.z, b0.w));
+                        const float2 s2 = fadd2(make_float2(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])), make_float2(b1.x, b1.y));
+                        const float2 s3 = fadd2(make_float2(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])), make_float2(b1.z, b1.w));
+                        st_shared_v4(srow + (uint32_t)((c ^ (row_in_tile & 7)) << 4), relu6_bf16x2(s0), relu6_bf16x2(s1), relu6_bf16x2(s2),
+                                     relu6_bf16x2(s3));
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to TMA
                     epi_bar_sync();
@@ -234,12 +229,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float4 b = __ldg(bp + j);
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[4 * j + 0]) + b.x),
-                                                                          relu6f(__uint_as_float(v[4 * j + 1]) + b.y));
-                                __nv_bfloat162 h1 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[4 * j + 2]) + b.z),
-                                                                          relu6f(__uint_as_float(v[4 * j + 3]) + b.w));
-                                packed[2 * j] = *reinterpret_cast<uint32_t *>(&h0);
-                                packed[2 * j + 1] = *reinterpret_cast<uint32_t *>(&h1);
+                                packed[2 * j] = relu6_bf16x2(__uint_as_float(v[4 * j + 0]) + b.x, __uint_as_float(v[4 * j + 1]) + b.y);
+                                packed[2 * j + 1] = relu6_bf16x2(__uint_as_float(v[4 * j + 2]) + b.z, __uint_as_float(v[4 * j + 3]) + b.w);
                             }
                             uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(ep.y) + (size_t)row * N + col0);
                             dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);

@@ -141,6 +141,22 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2 *>(&ud);
 }
 
+// packed fp32 pair add (FADD2 on sm_100)
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ua = *reinterpret_cast<unsigned long long *>(&a), ub = *reinterpret_cast<unsigned long long *>(&b), ud;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    return *reinterpret_cast<float2 *>(&ud);
+}
+// ReLU6 of two fp32 values -> packed bf16x2 (lo in the low half) in two instructions: the max(x, 0) rides on the
+// conversion (cvt.rn.relu), the min(x, 6) runs on the packed pair.  Rounding is monotone and 0 / 6 are exact in bf16,
+// so this equals clamp-then-round.
+__device__ __forceinline__ uint32_t relu6_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("{\n\t.reg .b32 t;\n\tcvt.rn.relu.bf16x2.f32 t, %2, %1;\n\tmin.bf16x2 %0, t, %3;\n\t}" : "=r"(r) : "f"(lo), "f"(hi), "r"(0x40C040C0u));
+    return r;
+}
+__device__ __forceinline__ uint32_t relu6_bf16x2(float2 v) { return relu6_bf16x2(v.x, v.y); }
+
 // ---- host: tensor-map encoding (implemented in tmap.cu) ----------------------------------------------
 // rank <= 4; dims/box innermost first; strides_bytes[rank-1] are the byte strides of dims 1..rank-1.
 // esize 2 -> bf16, 4 -> fp32.  swizzle: 0 none, 1 32B, 2 64B, 3 128B.  OOB elements read as zero.

@@ -315,17 +315,12 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     for (int c = 0; c < 4; ++c) {                        // 8 columns -> one 16 B chunk, 128B-swizzled
                         const uint32_t bsm = base + g.off_bias + (uint32_t)(col0 + hf * 32 + c * 8) * 4u;
                         const float4 b0 = lds_f4(bsm), b1 = lds_f4(bsm + 16);
-                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 0]) + b0.x),
-                                                                        relu6f(__uint_as_float(v[8 * c + 1]) + b0.y));
-                        const __nv_bfloat162 h1 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 2]) + b0.z),
-                                                                        relu6f(__uint_as_float(v[8 * c + 3]) + b0.w));
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 4]) + b1.x),
-                                                                        relu6f(__uint_as_float(v[8 * c + 5]) + b1.y));
-                        const __nv_bfloat162 h3 = __floats2bfloat162_rn(relu6f(__uint_as_float(v[8 * c + 6]) + b1.z),
-                                                                        relu6f(__uint_as_float(v[8 * c + 7]) + b1.w));
-                        st_shared_v4(srow + (uint32_t)(((hf * 4 + c) ^ (row_in_tile & 7)) << 4), *reinterpret_cast<const uint32_t *>(&h0),
-                                     *reinterpret_cast<const uint32_t *>(&h1), *reinterpret_cast<const uint32_t *>(&h2),
-                                     *reinterpret_cast<const uint32_t *>(&h3));
+                        const float2 s0 = fadd2(make_float2(__uint_as_float(v[8 * c + 0]), __uint_as_float(v[8 * c + 1])), make_float2(b0.x, b0.y));
+                        const float2 s1 = fadd2(make_float2(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])), make_float2(b0.z, b0.w));
+                        const float2 s2 = fadd2(make_float2(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])), make_float2(b1.x, b1.y));
+                        const float2 s3 = fadd2(make_float2(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])), make_float2(b1.z, b1.w));
+                        st_shared_v4(srow + (uint32_t)(((hf * 4 + c) ^ (row_in_tile & 7)) << 4), relu6_bf16x2(s0), relu6_bf16x2(s1),
+                                     relu6_bf16x2(s2), relu6_bf16x2(s3));
                     }
                 }
                 fence_async_smem();                                      // generic writes -> visible to TMA
@@ -368,7 +363,6 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             seg_off[i] = (uint32_t)(seg_r0[i] * S) * rowb + (uint32_t)(seg_col[i] * S) * 128u + (uint32_t)lane * 4u;
         }
         const uint32_t a_lane = (uint32_t)(lane >> 2) << 4 | (uint32_t)(lane & 3) << 2;   // 16 B chunk | byte inside it
-        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(0.f, 0.f), hi2 = __floats2bfloat162_rn(6.f, 6.f);
         auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
 
         int ps = 0, as = 0, tr_d = 0;
@@ -468,10 +462,8 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                 }
 #pragma unroll
                                 for (int p = 0; p < 4; ++p) {
-                                    // ReLU6: round first, clamp after (0 and 6 are exact in bf16, rounding is monotone)
-                                    __nv_bfloat162 h = __hmin2(__hmax2(__floats2bfloat162_rn(acc[p].x, acc[p].y), lo2), hi2);
                                     const uint32_t r = (uint32_t)(arow + p);
-                                    sts_u32_if(a_stage + ((r << 7) | a_lane) ^ ((r & 7u) << 4), *reinterpret_cast<uint32_t *>(&h), p < ncol_ok);
+                                    sts_u32_if(a_stage + ((r << 7) | a_lane) ^ ((r & 7u) << 4), relu6_bf16x2(acc[p]), p < ncol_ok);
                                 }
                                 arow += g.tw;
                             }
