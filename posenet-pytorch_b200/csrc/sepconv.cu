@@ -10,6 +10,8 @@
 //                              [K] fp32 through 2-D maps, ragged K zero-filled), and the pointwise weight tile
 //                              [N_TILE x 64] (128B swizzle) -- three mbarrier rings (patch / W / A).
 //   warps 6-15  depthwise      a lane owns one channel pair (4 B of every pixel), a warp a column strip of 4 output pixels
+//                              (segments are handed out dynamically from a shared-memory counter, so the warps of the four
+//                              schedulers stay busy and run ahead into the next k-block while others finish the current one)
 //                              that it walks down row by row with the 3x3 window's input rows held in registers, so
 //                              each patch element is read from shared memory once and the 9x2 weights stay in
 //                              registers (the kernel is shared-memory-bandwidth bound otherwise).  fp32 math with packed
@@ -49,6 +51,7 @@ struct SepGeom {
     int tiles_x, tiles_y, n_tiles, n_tile, panels, tmem_cols;
     int n_halves, n_half, acc_bufs;       // a tile's accumulator = n_halves UMMA column blocks of n_half (<= 256) columns
     int kblocks;
+    int half, cbox;                       // K <= 32: two pixel columns per warp (16 lanes each), 32-channel patch box
     int p_stages, w_stages, a_stages, stg_bufs;
     unsigned patch_stage_bytes, patch_box_bytes, wgt_off, w_stage_bytes;
     unsigned off_a, off_stg, off_patch, off_bias, off_bar;   // from the 1024-aligned base; W stages sit at 0
@@ -59,7 +62,7 @@ struct SepBars {       // byte offsets of the mbarriers inside the barrier block
     static constexpr int patch_full = 0, patch_empty = 8 * SEP_MAX_P, w_full = 16 * SEP_MAX_P,
                          w_empty = 16 * SEP_MAX_P + 8 * SEP_MAX_W, a_full = 16 * SEP_MAX_P + 16 * SEP_MAX_W,
                          a_empty = a_full + 8 * SEP_MAX_A, tfull = a_empty + 8 * SEP_MAX_A, tempty = tfull + 16,
-                         tmem_slot = tempty + 16, total = tmem_slot + 16;
+                         tmem_slot = tempty + 16, seg_ctr = tmem_slot + 16, seg_tab = seg_ctr + 4 * 8, total = seg_tab + 4 * 64;
 };
 
 __device__ __forceinline__ uint64_t sep_smem_desc(uint32_t saddr) {      // K-major SWIZZLE_128B (see gemm_tc.cu)
@@ -97,13 +100,17 @@ __device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool on) {
 // Register window of the depthwise stencil for a strip of 4 output pixels: output row t reads input rows
 // t*S + ky*D.  Sliding (D == 1): a ring of NR = 2D+1 rows, S new rows per step, PRE rows preloaded; otherwise the
 // three rows are loaded afresh each step.
-template <int S, int D> struct SepDwCfg {
+// HALF (K <= 32 channels): lanes 0-15 own the even pixels of an 8-pixel strip, lanes 16-31 the odd ones, i.e. each lane
+// walks 4 pixels that are HS = 2 S input columns apart -- no lane idles on zero-filled channels.
+template <int S, int D, bool HALF> struct SepDwCfg {
     static constexpr bool SLIDE = (D == 1);
     static constexpr bool UNPACKED = (D == 1);       // window kept as fp32 pairs (18-27 pairs); wider windows stay packed
     static constexpr int NR = SLIDE ? 2 * D + 1 : 3;
-    static constexpr int NCOLS = 3 * S + 2 * D + 1;
+    static constexpr int HS = HALF ? 2 * S : S;      // input columns between a lane's consecutive output pixels
+    static constexpr int NCOLS = 3 * HS + 2 * D + 1;
     static constexpr int PRE = SLIDE ? 2 * D + 1 - S : 0;
 };
+
 
 // Optional timeline trace (compile with -DPN_SEP_TRACE, see tools/trace_sep.py): block 0 stamps clock64 per role.
 #ifdef PN_SEP_TRACE
@@ -118,7 +125,7 @@ __device__ int g_sep_trace_cap = 0;
 #define SEP_TRACE(role, idx, what) do { } while (0)
 #endif
 
-template <int S, int D>
+template <int S, int D, bool HALF>
 __global__ void __launch_bounds__(SEP_THREADS, 1)
 sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dww,
                const __grid_constant__ CUtensorMap tmap_dwb, const __grid_constant__ CUtensorMap tmap_w,
@@ -168,6 +175,15 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    {   // depthwise segment table (strip column | first row << 8 | rows << 16) and the hand-out counter
+        uint32_t *misc = reinterpret_cast<uint32_t *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bar);
+        if (threadIdx.x < 8) misc[SepBars::seg_ctr / 4 + threadIdx.x] = 0u;
+        if ((int)threadIdx.x < g.segs_per_sub) {
+            const int seg = threadIdx.x, cs = seg % g.spr, rs = seg / g.spr;
+            const int r0 = rs * g.seg_rows;
+            misc[SepBars::seg_tab / 4 + seg] = (uint32_t)(cs * (HALF ? 8 : 4)) | (uint32_t)r0 << 8 | (uint32_t)min(g.seg_rows, g.ths - r0) << 16;
+        }
+    }
     {   // pointwise bias -> shared memory once (the epilogue reads it per panel)
         float *sbias = reinterpret_cast<float *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bias);
         const int ncp = g.n_tiles * g.panels * 64;                // padded so that ragged panels read zeros
@@ -184,8 +200,9 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         // each with its own cursor over (tile, k-block, ...), polled without blocking so that a full W ring never holds
         // back a patch load (the depthwise warps run ahead of the MMA by the depth of the A ring).
         if (lane == 0) {
-            int ps = 0, ws = 0;
+            int ps = 0, ws = 0, tr_p = 0;
             uint32_t pph = 0, wph = 0;
+            (void)tr_p;
             long long p_tile = blockIdx.x, w_tile = blockIdx.x;
             int p_kb = 0, p_sub = 0, w_kb = 0, w_hf = 0;
             int p_img = 0, p_ty = 0, p_tx = 0, w_col = 0;
@@ -204,11 +221,14 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     }
                     if (mbar_test(bar(SepBars::patch_empty, ps), pph ^ 1)) {
                         const uint32_t full = bar(SepBars::patch_full, ps);
+                        SEP_TRACE(3, tr_p, 0);
                         mbar_expect_tx(full, g.patch_box_bytes + SEP_WGT_BYTES);
                         tma_load_4d(p_addr(ps), &tmap_x, full, p_kb * CB, p_tx * g.tw * S - g.pad,
                                     (p_ty * g.th + p_sub * g.ths) * S - g.pad, p_img);
                         tma_load_2d(p_addr(ps) + g.wgt_off, &tmap_dww, full, p_kb * CB, 0);
                         tma_load_2d(p_addr(ps) + g.wgt_off + 9 * 64 * 4, &tmap_dwb, full, p_kb * CB, 0);
+                        SEP_TRACE(3, tr_p, 1);
+                        ++tr_p;
                         if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
                         if (++p_sub == g.subs) {
                             p_sub = 0;
@@ -337,148 +357,157 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         if (issuer) bulk_wait_all();                                     // smem must outlive the last bulk store
     } else {
         // ===================== depthwise producers of the A tile (warps 6..15) =====================
-        // Lane l owns channels 2l, 2l+1 of the 64-channel k-block (4 B of every pixel), a warp owns a segment: a column
-        // strip of 4 output pixels x up to seg_rows rows.  It slides down the rows keeping the input-row window of the 3x3
-        // stencil in registers (fp32 pairs for dilation 1, bf16 pairs otherwise), so every patch element is read from
-        // shared memory once per segment, unpacked once, and the 9 x 2 weights + bias stay in registers for the whole
-        // k-block.  The rows entering the window at the next step are prefetched before the FMAs of the current one.
-        // One ld.shared.b32 / st.shared.b32 is one conflict-free 128 B wavefront per warp.
-        using Cfg = SepDwCfg<S, D>;
-        constexpr int NR = Cfg::NR, NCOLS = Cfg::NCOLS, PRE = Cfg::PRE;
+        // Lane l owns channels 2l, 2l+1 of the 64-channel k-block (4 B of every pixel).  A warp takes the next segment --
+        // a column strip of 4 output pixels (8 when HALF) x up to seg_rows rows of one (tile, k-block, sub-tile) item --
+        // from the CTA-wide counter, and slides down its rows keeping the input-row window of the 3x3 stencil in registers
+        // (fp32 pairs for dilation 1, bf16 pairs otherwise), so every patch element is read from shared memory once per
+        // segment, unpacked once, and the 9 x 2 weights + bias stay in registers for the segment.  The rows entering the
+        // window at the next step are prefetched before the FMAs of the current one.  One ld.shared.b32 / st.shared.b32
+        // is one conflict-free 128 B wavefront per warp.  Items are handed out in order, so a warp that finishes early
+        // simply starts on the next item's patch (if it has landed) while the others complete the current A stage.
+        using Cfg = SepDwCfg<S, D, HALF>;
+        constexpr int NR = Cfg::NR, NCOLS = Cfg::NCOLS, PRE = Cfg::PRE, HS = Cfg::HS;
         constexpr bool SLIDE = Cfg::SLIDE, UNPACKED = Cfg::UNPACKED, PREFETCH = Cfg::UNPACKED;
         constexpr int NNEW = SLIDE ? S : 3;                          // input rows loaded per step
-        const int dw_warp = warp - SEP_FIRST_DW_WARP;
-        const uint32_t rowb = (uint32_t)g.twi * 128u;
-        // this warp's (at most two) segments inside every sub-tile
-        int seg_col[2], seg_r0[2], seg_n[2];
-        uint32_t seg_off[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int seg = dw_warp + i * SEP_DW_WARPS;
-            const bool has = seg < g.segs_per_sub;
-            const int cs = has ? seg % g.spr : 0, rs = has ? seg / g.spr : 0;
-            seg_col[i] = cs * 4;
-            seg_r0[i] = rs * g.seg_rows;
-            seg_n[i] = has ? min(g.seg_rows, g.ths - seg_r0[i]) : 0;
-            seg_off[i] = (uint32_t)(seg_r0[i] * S) * rowb + (uint32_t)(seg_col[i] * S) * 128u + (uint32_t)lane * 4u;
-        }
-        const uint32_t a_lane = (uint32_t)(lane >> 2) << 4 | (uint32_t)(lane & 3) << 2;   // 16 B chunk | byte inside it
+        constexpr uint32_t PIX = HALF ? 64u : 128u;                  // bytes per patch pixel
+        const int hsel = HALF ? (lane >> 4) : 0, cp = HALF ? (lane & 15) : lane;
+        const uint32_t rowb = (uint32_t)g.twi * PIX;
+        const uint32_t lane_off = (uint32_t)(hsel * S) * PIX + (uint32_t)cp * 4u;
+        const uint32_t a_lane = (uint32_t)(cp >> 2) << 4 | (uint32_t)(cp & 3) << 2;       // 16 B chunk | byte inside it
         auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
+        int *seg_ctr = reinterpret_cast<int *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bar + SepBars::seg_ctr);
+        const uint32_t tab_addr = bars + (uint32_t)SepBars::seg_tab;
+        const int grabs_per_use = g.segs_per_sub + SEP_DW_WARPS;     // every warp ends an item with one empty-handed grab
 
-        int ps = 0, as = 0, tr_d = 0;
+        // Every warp walks all items -- (tile, k-block, sub-tile), one patch stage each -- in order, so its mbarrier parities
+        // never skip a phase; inside an item the segments are handed out by an atomic counter per patch stage (uses of a
+        // stage cannot interleave: the refill waits for all warps to have left the previous use).  A warp that finds the
+        // item exhausted moves straight on to the next one while the others finish.
+        int ps = 0, as = 0, puse = 0, tr_d = 0;
         uint32_t pph = 0, aph = 0;
         (void)tr_d;
+        const bool tracer = (warp == SEP_FIRST_DW_WARP && lane == 0);
+        (void)tracer;
         for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
-            for (int kb = 0; kb < g.kblocks; ++kb) {
-                if (dw_warp == 0 && lane == 0) SEP_TRACE(0, tr_d, 0);
-                mbar_wait(bar(SepBars::a_empty, as), aph ^ 1);            // the MMAs that read this A stage have retired
-                if (dw_warp == 0 && lane == 0) SEP_TRACE(0, tr_d, 1);
-                const uint32_t a_stage = a_addr(as);
-                for (int sub = 0; sub < g.subs; ++sub) {
-                    mbar_wait(bar(SepBars::patch_full, ps), pph);
-                    if (dw_warp == 0 && lane == 0 && sub == 0) SEP_TRACE(0, tr_d, 2);
-                    const uint32_t stage = p_addr(ps);
-                    float2 wk[9], bias2;
-                    {
-                        const uint32_t wsm = stage + g.wgt_off + (uint32_t)lane * 8u;
+          for (int kb = 0; kb < g.kblocks; ++kb) {
+            if (tracer) SEP_TRACE(0, tr_d, 0);
+            mbar_wait(bar(SepBars::a_empty, as), aph ^ 1);            // the MMAs that read this A stage have retired
+            if (tracer) SEP_TRACE(0, tr_d, 1);
+            const uint32_t a_stage = a_addr(as);
+            for (int sub = 0; sub < g.subs; ++sub) {
+              mbar_wait(bar(SepBars::patch_full, ps), pph);
+              if (tracer && sub == 0) SEP_TRACE(0, tr_d, 2);
+              const uint32_t stage = p_addr(ps);
+              const int grab_base = puse * grabs_per_use;
+              float2 wk[9], bias2;
+              bool have_w = false;
+              for (;;) {
+                int seg = 0;
+                if (lane == 0) seg = atomicAdd(seg_ctr + ps, 1) - grab_base;
+                seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
+                if (seg >= g.segs_per_sub) break;
+                if (!have_w) {
+                    const uint32_t wsm = stage + g.wgt_off + (uint32_t)cp * 8u;
 #pragma unroll
-                        for (int t = 0; t < 9; ++t) wk[t] = lds_f2(wsm + (uint32_t)t * 256u);
-                        bias2 = lds_f2(wsm + 9 * 256u);
-                    }
-#pragma unroll 1
-                    for (int i = 0; i < 2; ++i) {
-                        const int s_r0 = i ? seg_r0[1] : seg_r0[0], s_col = i ? seg_col[1] : seg_col[0];
-                        const int orow0 = sub * g.ths + s_r0;
-                        const int nrows = min(i ? seg_n[1] : seg_n[0], g.th - orow0);   // rows of this segment inside the tile
-                        if (nrows <= 0) continue;
-                        const uint32_t src = stage + (i ? seg_off[1] : seg_off[0]);
-                        const int ncol_ok = g.tw - s_col;                               // pixels p < ncol_ok exist
-                        int arow = orow0 * g.tw + s_col;                                // A-tile row == TMEM lane == staging row
-
-                        float2 ringf[UNPACKED ? NR : 1][NCOLS];                         // the window, unpacked (dilation 1)
-                        uint32_t ringp[UNPACKED ? 1 : NR][NCOLS];                       // ... or packed bf16 pairs
-                        uint32_t nxt[PREFETCH ? NNEW : 1][NCOLS];                       // rows entering the window next
-                        if (SLIDE) {
-#pragma unroll
-                            for (int r = 0; r < PRE; ++r)
-#pragma unroll
-                                for (int c = 0; c < NCOLS; ++c) {
-                                    const uint32_t v = lds_u32(src + (uint32_t)r * rowb + (uint32_t)c * 128u);
-                                    if (UNPACKED) ringf[r][c] = unpack(v); else ringp[r][c] = v;
-                                }
-                            if (PREFETCH) {
-#pragma unroll
-                                for (int n = 0; n < S; ++n)
-#pragma unroll
-                                    for (int c = 0; c < NCOLS; ++c) nxt[n][c] = lds_u32(src + (uint32_t)(PRE + n) * rowb + (uint32_t)c * 128u);
-                            }
-                        }
-#pragma unroll 1
-                        for (int t0 = 0; t0 < nrows; t0 += NR) {
-#pragma unroll
-                            for (int j = 0; j < NR; ++j) {
-                                const int t = t0 + j;
-                                if (t >= nrows) break;
-                                if (PREFETCH) {
-                                    // the prefetched rows enter the window ...
-#pragma unroll
-                                    for (int n = 0; n < NNEW; ++n)
-#pragma unroll
-                                        for (int c = 0; c < NCOLS; ++c) {
-                                            const int slot = (PRE + j * S + n) % NR;
-                                            if (UNPACKED) ringf[slot][c] = unpack(nxt[n][c]); else ringp[slot][c] = nxt[n][c];
-                                        }
-                                    // ... and the next step's rows are requested before this step's math
-                                    if (t + 1 < nrows) {
-#pragma unroll
-                                        for (int n = 0; n < NNEW; ++n) {
-                                            const uint32_t rp = src + (uint32_t)(PRE + (t + 1) * S + n) * rowb;
-#pragma unroll
-                                            for (int c = 0; c < NCOLS; ++c) nxt[n][c] = lds_u32(rp + (uint32_t)c * 128u);
-                                        }
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int n = 0; n < NNEW; ++n) {
-                                        const int slot = SLIDE ? (PRE + j * S + n) % NR : n;
-                                        const uint32_t rp = src + (uint32_t)(SLIDE ? PRE + t * S + n : t * S + n * D) * rowb;
-#pragma unroll
-                                        for (int c = 0; c < NCOLS; ++c) ringp[slot][c] = lds_u32(rp + (uint32_t)c * 128u);
-                                    }
-                                }
-                                float2 acc[4] = {bias2, bias2, bias2, bias2};
-#pragma unroll
-                                for (int ky = 0; ky < 3; ++ky) {
-                                    const int slot = SLIDE ? (j * S + ky * D) % NR : ky;
-#pragma unroll
-                                    for (int c = 0; c < NCOLS; ++c) {
-                                        const float2 v = UNPACKED ? ringf[slot][c] : unpack(ringp[slot][c]);
-#pragma unroll
-                                        for (int p = 0; p < 4; ++p)
-#pragma unroll
-                                            for (int kx = 0; kx < 3; ++kx)
-                                                if (p * S + kx * D == c) acc[p] = ffma2(v, wk[ky * 3 + kx], acc[p]);
-                                    }
-                                }
-#pragma unroll
-                                for (int p = 0; p < 4; ++p) {
-                                    const uint32_t r = (uint32_t)(arow + p);
-                                    sts_u32_if(a_stage + ((r << 7) | a_lane) ^ ((r & 7u) << 4), relu6_bf16x2(acc[p]), p < ncol_ok);
-                                }
-                                arow += g.tw;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(SepBars::patch_empty, ps));   // this warp no longer reads the patch
-                    if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
+                    for (int t = 0; t < 9; ++t) wk[t] = lds_f2(wsm + (uint32_t)t * 256u);
+                    bias2 = lds_f2(wsm + 9 * 256u);
+                    have_w = true;
                 }
-                fence_async_smem();                                       // A-tile writes -> visible to the tensor core
-                __syncwarp();
-                if (dw_warp == 0 && lane == 0) { SEP_TRACE(0, tr_d, 3); ++tr_d; }
-                if (lane == 0) mbar_arrive(bar(SepBars::a_full, as));
-                if (++as == g.a_stages) { as = 0; aph ^= 1; }
+                const uint32_t tab = lds_u32(tab_addr + (uint32_t)seg * 4u);
+                const int s_col = (int)(tab & 0xffu), s_r0 = (int)((tab >> 8) & 0xffu), s_n = (int)(tab >> 16);
+                const int orow0 = sub * g.ths + s_r0;
+                const int nrows = min(s_n, g.th - orow0);                       // rows of this segment inside the tile
+                if (nrows > 0) {
+                    const uint32_t src = stage + (uint32_t)(s_r0 * S) * rowb + (uint32_t)(s_col * S) * PIX + lane_off;
+                    const int ncol_ok = g.tw - s_col;                               // strip pixels px < ncol_ok exist
+                    int arow = orow0 * g.tw + s_col;                                // A-tile row == TMEM lane == staging row
+
+                    float2 ringf[UNPACKED ? NR : 1][NCOLS];                         // the window, unpacked (dilation 1)
+                    uint32_t ringp[UNPACKED ? 1 : NR][NCOLS];                       // ... or packed bf16 pairs
+                    uint32_t nxt[PREFETCH ? NNEW : 1][NCOLS];                       // rows entering the window next
+                    if (SLIDE) {
+    #pragma unroll
+                        for (int r = 0; r < PRE; ++r)
+    #pragma unroll
+                            for (int c = 0; c < NCOLS; ++c) {
+                                const uint32_t v = lds_u32(src + (uint32_t)r * rowb + (uint32_t)c * PIX);
+                                if (UNPACKED) ringf[r][c] = unpack(v); else ringp[r][c] = v;
+                            }
+                        if (PREFETCH) {
+    #pragma unroll
+                            for (int n = 0; n < S; ++n)
+    #pragma unroll
+                                for (int c = 0; c < NCOLS; ++c) nxt[n][c] = lds_u32(src + (uint32_t)(PRE + n) * rowb + (uint32_t)c * PIX);
+                        }
+                    }
+    #pragma unroll 1
+                    for (int t0 = 0; t0 < nrows; t0 += NR) {
+    #pragma unroll
+                        for (int j = 0; j < NR; ++j) {
+                            const int t = t0 + j;
+                            if (t >= nrows) break;
+                            if (PREFETCH) {
+                                // the prefetched rows enter the window ...
+    #pragma unroll
+                                for (int n = 0; n < NNEW; ++n)
+    #pragma unroll
+                                    for (int c = 0; c < NCOLS; ++c) {
+                                        const int slot = (PRE + j * S + n) % NR;
+                                        if (UNPACKED) ringf[slot][c] = unpack(nxt[n][c]); else ringp[slot][c] = nxt[n][c];
+                                    }
+                                // ... and the next step's rows are requested before this step's math
+                                if (t + 1 < nrows) {
+    #pragma unroll
+                                    for (int n = 0; n < NNEW; ++n) {
+                                        const uint32_t rp = src + (uint32_t)(PRE + (t + 1) * S + n) * rowb;
+    #pragma unroll
+                                        for (int c = 0; c < NCOLS; ++c) nxt[n][c] = lds_u32(rp + (uint32_t)c * PIX);
+                                    }
+                                }
+                            } else {
+    #pragma unroll
+                                for (int n = 0; n < NNEW; ++n) {
+                                    const int slot = SLIDE ? (PRE + j * S + n) % NR : n;
+                                    const uint32_t rp = src + (uint32_t)(SLIDE ? PRE + t * S + n : t * S + n * D) * rowb;
+    #pragma unroll
+                                    for (int c = 0; c < NCOLS; ++c) ringp[slot][c] = lds_u32(rp + (uint32_t)c * PIX);
+                                }
+                            }
+                            float2 acc[4] = {bias2, bias2, bias2, bias2};
+    #pragma unroll
+                            for (int ky = 0; ky < 3; ++ky) {
+                                const int slot = SLIDE ? (j * S + ky * D) % NR : ky;
+    #pragma unroll
+                                for (int c = 0; c < NCOLS; ++c) {
+                                    const float2 v = UNPACKED ? ringf[slot][c] : unpack(ringp[slot][c]);
+    #pragma unroll
+                                    for (int p = 0; p < 4; ++p)
+    #pragma unroll
+                                        for (int kx = 0; kx < 3; ++kx)
+                                            if (p * HS + kx * D == c) acc[p] = ffma2(v, wk[ky * 3 + kx], acc[p]);
+                                }
+                            }
+    #pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const int px = HALF ? 2 * p + hsel : p;                  // pixel inside the strip
+                                const uint32_t r = (uint32_t)(arow + px);
+                                sts_u32_if(a_stage + ((r << 7) | a_lane) ^ ((r & 7u) << 4), relu6_bf16x2(acc[p]), px < ncol_ok);
+                            }
+                            arow += g.tw;
+                        }
+                    }
+                }
+              }   // segments of this item
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(SepBars::patch_empty, ps));   // this warp no longer reads the patch
+              if (++ps == g.p_stages) { ps = 0; pph ^= 1; ++puse; }
             }
+            fence_async_smem();                                       // A-tile writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(SepBars::a_full, as));
+            if (tracer) { SEP_TRACE(0, tr_d, 3); ++tr_d; }
+            if (++as == g.a_stages) { as = 0; aph ^= 1; }
+          }
         }
     }
 
@@ -518,7 +547,11 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     PN_CHECK_ARG(g.ho > 0 && g.wo > 0, "pn_sepconv_block: empty output");
     const int cb = 64;
     const bool slide = dil == 1;
-    const int ncols = 3 * stride + 2 * dil + 1, pre = slide ? 2 * dil + 1 - stride : 0;
+    // K <= 32 (the first block of every model): half-warp per pixel column, 32-channel patch box (sepconv_kernel HALF)
+    g.half = (k <= 32 && stride == 1 && dil == 1) ? 1 : 0;
+    g.cbox = g.half ? 32 : cb;
+    const int sw = g.half ? 8 : 4;                                  // output pixels per strip step
+    const int ncols = 3 * stride * (g.half ? 2 : 1) + 2 * dil + 1, pre = slide ? 2 * dil + 1 - stride : 0;
     g.kblocks = ceil_div(k, cb);
     // Output columns per tile: up to 256 double-buffered in TMEM (the epilogue of tile i overlaps the main loop of tile
     // i+1), or up to 512 as two UMMA column blocks single-buffered -- the depthwise work, which bounds the deep layers,
@@ -537,43 +570,44 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
 
     // ---- tile search: fewest (tiles x per-tile cost); one strip per depthwise thread group per sub-tile
     const int min_w = g.n_halves == 2 ? 3 : 2;                     // W ring entries (one per UMMA column block)
-    const int fixed = 2 * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 256 + 4224;   // minimum non-patch smem
+    const int fixed = 2 * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 1024 + 4224;   // minimum non-patch smem
     double best = 1e300;
+    int f_th = 0, f_tw = 0, f_subs = 0;                            // tuning / debugging aid: PN_SEP_TILE="th,tw,subs"
+    if (const char *force = getenv("PN_SEP_TILE"))
+        if (sscanf(force, "%d,%d,%d", &f_th, &f_tw, &f_subs) != 3) f_th = f_tw = f_subs = 0;
     for (int th = 1; th <= 64; ++th) {
         for (int tw = 1; tw <= 64; ++tw) {
             if (th * tw > 128) break;
             if ((th - 1) >= g.ho + 7 || (tw - 1) >= g.wo + 7) continue;
             for (int subs = 1; subs <= 4 && subs <= th; ++subs) {
+                if (f_th && (th != f_th || tw != f_tw || subs != f_subs)) continue;
                 const int ths = ceil_div(th, subs);
                 if ((subs - 1) * ths >= th) continue;                      // an empty last sub-tile
                 const int thi = (ths - 1) * stride + 2 * dil + 1;
                 const int twi = (tw - 1) * stride + 2 * dil + 1;
                 if (thi > 256 || twi > 256) continue;
-                const long long box = (long long)thi * twi * cb * 2;
+                const long long box = (long long)thi * twi * g.cbox * 2;
                 const long long stage = ((box + 127) & ~127ll) + SEP_WGT_BYTES;
-                // segments: 4-pixel column strips x seg_rows rows, at most two per depthwise warp and sub-tile
-                const int spr = ceil_div(tw, 4);
-                int seg_rows = 1;
-                while (spr * ceil_div(ths, seg_rows) > SEP_DW_WARPS && seg_rows < ths) ++seg_rows;
-                int segs = spr * ceil_div(ths, seg_rows);
-                if (segs > SEP_DW_WARPS) {                                 // one pass impossible: allow two segments per warp
-                    seg_rows = 1;
-                    while (spr * ceil_div(ths, seg_rows) > 2 * SEP_DW_WARPS && seg_rows < ths) ++seg_rows;
-                    segs = spr * ceil_div(ths, seg_rows);
-                    if (segs > 2 * SEP_DW_WARPS) continue;
-                }
-                const int passes = ceil_div(segs, SEP_DW_WARPS);
+                // segments: 4-pixel (8 when half) column strips x seg_rows rows.  They are handed out dynamically across
+                // the items in flight (A stages x segments >= 16 keeps the 10 warps busy); ~4-5 rows amortise the window preload
+                const int spr = ceil_div(tw, sw);
+                int pieces = ceil_div(ths, 5);
+                if (pieces * spr * subs < 8) pieces = ceil_div(8, spr * subs);   // >= 16 segments in flight with 2 A stages
+                if (pieces > ths) pieces = ths;
+                const int seg_rows = ceil_div(ths, pieces);
+                const int segs = spr * ceil_div(ths, seg_rows);
+                if (segs > 64 || seg_rows > 255 || tw > 255) continue;
                 const long long room = SEP_SMEM_MAX - fixed;
                 const int pst = (int)(room / stage);
                 if (pst < 2 || pst < subs + 1) continue;
                 const long long tiles = (long long)ceil_div(g.ho, th) * ceil_div(g.wo, tw);
-                // per k-block cycles.  A depthwise step (4 pixels x 64 channels, one warp) issues ~45 + 10 per window column
-                // instructions (+ ~1.3 per preloaded element); the warp that owns the longest segment chain sets the latency
-                // (~1.6 cycles per instruction when few warps share a scheduler), all warps together the issue time (4
-                // schedulers).  Tensor pipe: 2 cycles per output column.  Patch fill at ~40 B/clk.
-                const double step = 45.0 + 10.0 * ncols * (slide ? (stride + 2.0) / 3.0 : 1.0), prol = 1.3 * pre * ncols + 40.0;
-                const double lat = (double)subs * (passes * (seg_rows * step + prol) * 1.6 + 150.0);
-                const double issue = (double)subs * (spr * (ths * step + ceil_div(ths, seg_rows) * prol)) / 4.0;
+                // per k-block cycles.  A depthwise step (one strip row, one warp) issues ~45 + 10 per window column
+                // instructions (+ ~1.3 per preloaded element and ~120 per segment hand-out); all warps together set the issue
+                // time (4 schedulers, 25 % imbalance), half a segment's latency (~1.6 cycles per instruction) is exposed.
+                // Tensor pipe: 2 cycles per output column.  Patch fill at ~40 B/clk.
+                const double step = 45.0 + 10.0 * ncols * (slide ? (stride + 2.0) / 3.0 : 1.0), prol = 1.3 * pre * ncols + 120.0;
+                const double lat = 0.5 * (seg_rows * step + prol) * 1.6;
+                const double issue = 1.25 * (double)subs * (spr * (ths * step + ceil_div(ths, seg_rows) * prol)) / 4.0;
                 const double dwc = lat > issue ? lat : issue;
                 const double mma = 2.0 * g.n_tile;                          // per k-block, all column blocks
                 const double fill = (double)subs * stage / 40.0;
@@ -600,7 +634,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     g.tiles = (long long)n * g.tiles_x * g.tiles_y * g.n_tiles;
     // ---- shared-memory carve-up: W ring, A ring, output staging panels, patch ring, bias, barriers
     const long long bias_bytes = ((long long)g.n_tiles * g.panels * 64 * 4 + 127) & ~127ll;
-    const long long avail = SEP_SMEM_MAX - 1024 - 256 - bias_bytes;
+    const long long avail = SEP_SMEM_MAX - 1024 - 1024 - bias_bytes;   // alignment slack, barrier block (SepBars::total)
     auto fits = [&](int pst, int wst, int ast, int stg) {
         return (long long)wst * g.w_stage_bytes + (long long)ast * SEP_A_BYTES + (long long)stg * SEP_STG_BYTES +
                    (long long)pst * g.patch_stage_bytes <= avail;
@@ -628,6 +662,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
             g.p_stages = fp; g.w_stages = fw; g.a_stages = fa; g.stg_bufs = fs;
         }
     }
+    static_assert(SepBars::total <= 1024, "barrier block exceeds its reserve");
     g.off_a = (unsigned)g.w_stages * g.w_stage_bytes;
     g.off_stg = g.off_a + (unsigned)g.a_stages * SEP_A_BYTES;
     g.off_patch = g.off_stg + (unsigned)g.stg_bufs * SEP_STG_BYTES;
@@ -657,7 +692,7 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
     {   // input patches: (C, W, H, N) bf16, box [cb, twi, thi, 1], no swizzle, OOB -> 0
         const uint64_t dims[4] = {(uint64_t)k, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
         const uint64_t strides[3] = {(uint64_t)k * 2, (uint64_t)wd * k * 2, (uint64_t)h * wd * k * 2};
-        const uint32_t box[4] = {(uint32_t)cb, (uint32_t)g.twi, (uint32_t)g.thi, 1u};
+        const uint32_t box[4] = {(uint32_t)g.cbox, (uint32_t)g.twi, (uint32_t)g.thi, 1u};
         if ((rc = encode_tmap(op->tmap_x, x, 2, 4, dims, strides, box, 0)) != PN_OK) return rc;
     }
     {   // depthwise weights [9, K] fp32, box [64, 9]; bias [1, K] fp32, box [64, 1]
@@ -684,10 +719,10 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
     return PN_OK;
 }
 
-template <int S, int D>
+template <int S, int D, bool HALF>
 static int sep_launch_t(const SepOp *op, const SepGeom &g, const float *pw_bias, cudaStream_t st) {
     static bool configured = false;
-    auto kern = sepconv_kernel<S, D>;
+    auto kern = sepconv_kernel<S, D, HALF>;
     if (!configured) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SEP_SMEM_MAX));
         configured = true;
@@ -706,24 +741,25 @@ int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t st) {
     PN_CHECK_ARG(op && pw_bias, "pn_sepconv_block: null pointer");
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    if (op->stride == 2) return sep_launch_t<2, 1>(op, g, pw_bias, st);
-    if (op->dil == 1) return sep_launch_t<1, 1>(op, g, pw_bias, st);
-    if (op->dil == 2) return sep_launch_t<1, 2>(op, g, pw_bias, st);
-    return sep_launch_t<1, 4>(op, g, pw_bias, st);
+    if (op->stride == 2) return sep_launch_t<2, 1, false>(op, g, pw_bias, st);
+    if (g.half) return sep_launch_t<1, 1, true>(op, g, pw_bias, st);
+    if (op->dil == 1) return sep_launch_t<1, 1, false>(op, g, pw_bias, st);
+    if (op->dil == 2) return sep_launch_t<1, 2, false>(op, g, pw_bias, st);
+    return sep_launch_t<1, 4, false>(op, g, pw_bias, st);
 }
 
 void sep_describe(const SepOp *op, char *out, size_t cap) {
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    snprintf(out, cap, "tile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d stages p%d w%d a%d stg%d smem %d tiles %lld",
-             g.th, g.tw, g.subs, g.thi, g.twi, g.segs_per_sub, g.seg_rows, g.n_tile, g.n_halves, g.n_half, g.n_tiles, g.kblocks, g.p_stages,
+    snprintf(out, cap, "%stile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d stages p%d w%d a%d stg%d smem %d tiles %lld",
+             g.half ? "half " : "", g.th, g.tw, g.subs, g.thi, g.twi, g.segs_per_sub, g.seg_rows, g.n_tile, g.n_halves, g.n_half, g.n_tiles, g.kblocks, g.p_stages,
              g.w_stages, g.a_stages, g.stg_bufs, op->smem_bytes, g.tiles);
 }
 
 }  // namespace pn
 
 #ifdef PN_SEP_TRACE
-// debug only: trace buffer = 3 roles x cap events x 4 stamps (int64), zero-filled by the caller
+// debug only: trace buffer = 4 roles x cap events x 4 stamps (int64), zero-filled by the caller
 extern "C" int pn_debug_sep_trace(long long *buf, int cap) {
     if (cudaMemcpyToSymbol(pn::g_sep_trace, &buf, sizeof(buf)) != cudaSuccess) return -2;
     if (cudaMemcpyToSymbol(pn::g_sep_trace_cap, &cap, sizeof(cap)) != cudaSuccess) return -2;

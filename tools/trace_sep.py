@@ -7,7 +7,7 @@ import torch
 import abi
 from posenet import _native as nat
 
-def run(n, h, w, cin, cout, stride, dil, cap=256):
+def run(n, h, w, cin, cout, stride, dil, cap=256, show=24):
     lib = nat.load()
     lib.pn_debug_sep_trace.argtypes = [C.c_void_p, C.c_int]
     g = torch.Generator().manual_seed(0)
@@ -19,27 +19,31 @@ def run(n, h, w, cin, cout, stride, dil, cap=256):
     for _ in range(2):
         abi.sepconv(x, w9, bd, wp, bp, stride, dil)
     torch.cuda.synchronize()
-    buf = torch.zeros((3, cap, 4), dtype=torch.int64, device="cuda")
+    buf = torch.zeros((4, cap, 4), dtype=torch.int64, device="cuda")
     assert lib.pn_debug_sep_trace(C.c_void_p(buf.data_ptr()), cap) == 0
     abi.sepconv(x, w9, bd, wp, bp, stride, dil)
     torch.cuda.synchronize()
     lib.pn_debug_sep_trace(None, 0)
     t = buf.cpu().numpy()
     t0 = t[t > 0].min()
-    dw, mma, epi = t[0], t[1], t[2]
+    dw, mma, epi, prod = t[0], t[1], t[2], t[3]
     desc = C.create_string_buffer(256)
     lib.pn_sepconv_describe(n, h, w, cin, cout, stride, dil, desc, 256)
     print("== %s: %s" % ((n, h, w, cin, cout, stride, dil), desc.value.decode()))
-    print("dw (warp 6): idx start  wait_A  wait_patch  compute | mma: a_full_seen  issued-after  | ")
-    for i in range(cap):
+    print("k-block item: dw warp6 start | wait_A wait_patch work || producer issue@ | mma a_full@ issued@ (tempty@)")
+    for i in range(show):
         if dw[i, 3] == 0: break
         m = mma[i]
-        print("%3d %8d  %6d %6d %6d | mma a_full@%8d commit@%8d tempty@%8d" % (
-            i, dw[i, 0] - t0, dw[i, 1] - dw[i, 0], dw[i, 2] - dw[i, 1], dw[i, 3] - dw[i, 2],
+        print("%3d %8d | %6d %6d %6d || prod@%8d | mma a_full@%8d commit@%8d tempty@%8d" % (
+            i, dw[i, 0] - t0, dw[i, 1] - dw[i, 0], dw[i, 2] - dw[i, 1], dw[i, 3] - dw[i, 2], prod[i, 0] - t0 if prod[i, 0] else -1,
             m[1] - t0 if m[1] else -1, m[2] - t0 if m[2] else -1, m[0] - t0 if m[0] else -1))
-    for i in range(cap):
+    for i in range(min(show, cap)):
         if epi[i, 1] == 0: break
         print("epilogue tile %d: start@%8d  dur %6d" % (i, epi[i, 0] - t0, epi[i, 1] - epi[i, 0]))
+    n_it = int((dw[:, 3] > 0).sum())
+    if n_it > 8:
+        print("steady state: %.0f cycles per k-block item over items 4..%d" % ((dw[n_it - 1, 0] - dw[4, 0]) / (n_it - 5), n_it - 1))
+
 
 if __name__ == "__main__":
     for shp in [(64, 33, 33, 512, 512, 1, 1), (64, 257, 257, 32, 64, 1, 1), (64, 129, 129, 128, 256, 2, 1), (64, 33, 33, 1024, 1024, 1, 2)]:
