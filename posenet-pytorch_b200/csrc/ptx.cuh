@@ -22,17 +22,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a pipeline protocol error traps instead of hanging the GPU.
+// Bounded wait: a pipeline protocol error traps instead of hanging the GPU.  The suspend-time hint lets the hardware park the
+// warp until the phase completes (or ~1 ms passes), so a waiting warp does not burn issue slots re-polling.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     for (;;) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(1000000u)
             : "memory");
         if (done) return;
         if (clock64() - t0 > 4000000000ll) {   // ~2 s: a protocol bug, never a slow tile

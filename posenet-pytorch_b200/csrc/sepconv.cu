@@ -538,6 +538,13 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     PN_CHECK_ARG(sep_supported(k, nc, stride, dil), "pn_sepconv_block: unsupported block (cin %d cout %d stride %d dilation %d)", k,
                  nc, stride, dil);
     memset(op, 0, sizeof(*op));
+    if (sepwarp_supported(k, nc, stride, dil)) {                    // narrow block: warp-autonomous kernel, no tile geometry
+        op->warp_kind = true;
+        op->stride = stride; op->dil = dil;
+        op->ho = h; op->wo = wd;
+        op->n = n; op->h = h; op->w = wd; op->k = k; op->nc = nc;
+        return PN_OK;
+    }
     SepGeom g;
     memset(&g, 0, sizeof(g));
     g.k = k; g.nc = nc;
@@ -686,6 +693,10 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
                  "pn_sepconv_block: pointers must be 16-byte aligned");
     int rc = sep_geometry(op, n, h, wd, k, nc, stride, dil);
     if (rc != PN_OK) return rc;
+    if (op->warp_kind) {
+        op->dw_w = dw_w; op->dw_b = dw_b; op->pw_w = pw_w; op->y = y;
+        return sepwarp_prepare(&op->warp, x, n, h, wd, k, nc);
+    }
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
     const int cb = op->cb;
@@ -739,6 +750,7 @@ static int sep_launch_t(const SepOp *op, const SepGeom &g, const float *pw_bias,
 
 int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t st) {
     PN_CHECK_ARG(op && pw_bias, "pn_sepconv_block: null pointer");
+    if (op->warp_kind) return sepwarp_launch(&op->warp, op->dw_w, op->dw_b, op->pw_w, pw_bias, op->y, st);
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
     if (op->stride == 2) return sep_launch_t<2, 1, false>(op, g, pw_bias, st);
@@ -749,6 +761,14 @@ int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t st) {
 }
 
 void sep_describe(const SepOp *op, char *out, size_t cap) {
+    if (op->warp_kind) {
+        SepWarpOp w;
+        if (sepwarp_prepare(&w, reinterpret_cast<const void *>(uintptr_t(1024)), op->n, op->h, op->w, op->k, op->nc) == PN_OK)
+            sepwarp_describe(&w, out, cap);
+        else
+            snprintf(out, cap, "warp-autonomous (geometry unavailable)");
+        return;
+    }
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
     snprintf(out, cap, "%stile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d stages p%d w%d a%d stg%d smem %d tiles %lld",

@@ -1,0 +1,274 @@
+// B3 + B4 fused for the NARROW blocks (cin <= 32, cout <= 64, stride 1, dilation 1 -- the first SeperableConv block of every
+// model, posenet/models/mobilenet_v1.py:57-68), as warp-autonomous pipelines.
+//
+// In these blocks a 128-pixel tile carries so little work (128 x 32 x 9 depthwise MACs, a 128 x 64 x 32 GEMM) that the
+// hand-offs of the CTA-wide pipeline in sepconv.cu (TMA -> depthwise warps -> tcgen05 -> epilogue warps, ~1.3k cycles of
+// barrier latency per tile) cost more than the math.  Here every warp owns a column strip of 8 output pixels and walks
+// down it on its own, with nothing shared between warps but the read-only weights:
+//   * its lane 0 streams the strip's input rows (8 rows x 10 pixels x 32 channels per chunk, halo columns included, OOB
+//     zero fill == the convolution's zero padding) into a private two-stage shared-memory ring with TMA;
+//   * lanes 0-15 own the even pixels of the strip, lanes 16-31 the odd ones, one channel pair each (as the HALF mode of
+//     sepconv.cu): the 3-row input window slides through registers as fp32 pairs, 36 packed FFMA2 per output row, same tap
+//     order, bias, ReLU6 and bf16 rounding as dwconv.cu;
+//   * two output rows (16 pixels) form one m16 tile: the depthwise result goes through a private 1.3 KB staging buffer
+//     into mma.sync.m16n8k16 fragments (ldmatrix), the pointwise weights come from shared memory the same way, and the
+//     fp32 accumulators get bias + ReLU6 and leave as 16-byte coalesced global stores (whole 128 B pixel rows).
+// The GEMM is 1 % of a tcgen05 tile, so the legacy warp-level tensor path is the right size for it; no TMEM, no CTA barrier.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace pn {
+
+constexpr int SWP_WARPS = 16;
+constexpr int SWP_THREADS = SWP_WARPS * 32;
+constexpr int SWP_ROWS = 8;                               // input rows per TMA chunk
+constexpr int SWP_COLS = 10;                              // 8 output pixels + 2 halo columns
+constexpr int SWP_PIX = 64;                               // bytes per patch pixel (32 channels bf16)
+constexpr int SWP_CHUNK = SWP_ROWS * SWP_COLS * SWP_PIX;  // 5120
+constexpr int SWP_A_STRIDE = 80;                          // A staging: 16 pixel rows x (32 ch bf16 + 16 B pad), ldmatrix conflict-free
+constexpr int SWP_O_STRIDE = 144;                         // output staging: 16 pixel rows x (64 ch bf16 + 16 B pad)
+constexpr int SWP_W_STRIDE = 80;                          // pointwise weights [cout][32 + pad]
+constexpr int SWP_WARP_SMEM = (2 * SWP_CHUNK + 16 * SWP_A_STRIDE + 16 * SWP_O_STRIDE + 16 + 127) / 128 * 128;   // 13952: TMA wants 128 B
+constexpr int SWP_SHARED = 64 * SWP_W_STRIDE + 64 * 4;    // weights + bias
+constexpr int SWP_SMEM = SWP_WARPS * SWP_WARP_SMEM + SWP_SHARED + 1024;
+
+struct SwpGeom {
+    int n, h, w, k, nc;
+    int strips, nq, rb;            // 8-pixel column strips per image row, row blocks per strip, output rows per block
+    int ks, nt;                    // k16 slices (1 or 2), n8 tiles (cout / 8)
+    long long items;               // n * strips * nq
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t swp_lds_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void swp_sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(SWP_THREADS, 1)
+sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restrict__ dw_w, const float *__restrict__ dw_b,
+               const __nv_bfloat16 *__restrict__ pw_w, const float *__restrict__ pw_b, __nv_bfloat16 *__restrict__ y, const SwpGeom g) {
+    extern __shared__ uint8_t swp_raw[];
+    const uint32_t base = (smem_u32(swp_raw) + 1023u) & ~1023u;
+    uint8_t *gen = swp_raw + (base - smem_u32(swp_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sW = base + SWP_WARPS * SWP_WARP_SMEM, sBias = sW + 64 * SWP_W_STRIDE;
+    const uint32_t mine = base + (uint32_t)warp * SWP_WARP_SMEM;
+    const uint32_t sRing = mine, sA = mine + 2 * SWP_CHUNK, sO = sA + 16 * SWP_A_STRIDE, bars = sO + 16 * SWP_O_STRIDE;
+
+    // ---- CTA-wide, once: pointwise weights [cout][k] -> padded rows, bias; per warp: its two ring barriers
+    for (int i = threadIdx.x; i < 64 * 4; i += SWP_THREADS) {            // (row n, 16-byte chunk c) = 8 input channels
+        const int nrow = i >> 2, c = i & 3;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (nrow < g.nc && c * 8 < g.k) v = *reinterpret_cast<const uint4 *>(pw_w + (size_t)nrow * g.k + c * 8);
+        *reinterpret_cast<uint4 *>(gen + SWP_WARPS * SWP_WARP_SMEM + nrow * SWP_W_STRIDE + c * 16) = v;
+    }
+    if (threadIdx.x < 64) reinterpret_cast<float *>(gen + SWP_WARPS * SWP_WARP_SMEM + 64 * SWP_W_STRIDE)[threadIdx.x] =
+        (int)threadIdx.x < g.nc ? pw_b[threadIdx.x] : 0.f;
+    if (lane == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 8, 1);
+        mbar_fence_init();
+        if (warp == 0) tma_prefetch_desc(&tmap_x);
+    }
+    __syncthreads();
+
+    // ---- per lane: pixel parity, channel pair, the 9 x 2 depthwise weights + bias in registers for the whole kernel
+    const int hsel = lane >> 4, cp = lane & 15;
+    float2 wk[9], bias2;
+    {
+        const bool ok = 2 * cp < g.k;                                    // k is a multiple of 8: the pair is in or out as a whole
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wk[t] = ok ? *reinterpret_cast<const float2 *>(dw_w + (size_t)t * g.k + 2 * cp) : make_float2(0.f, 0.f);
+        bias2 = ok ? *reinterpret_cast<const float2 *>(dw_b + 2 * cp) : make_float2(0.f, 0.f);
+    }
+    auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
+    const uint32_t lane_off = (uint32_t)hsel * SWP_PIX + (uint32_t)cp * 4u;
+    const uint32_t a_lane_addr = sA + (uint32_t)hsel * SWP_A_STRIDE + (uint32_t)cp * 4u;                 // + (half * 8 + 2 p) rows
+    const uint32_t a_ld_addr = sA + (uint32_t)(lane & 15) * SWP_A_STRIDE + (uint32_t)(lane >> 4) * 16u;    // ldmatrix row / k-chunk
+    const uint32_t w_ld_addr = sW + (uint32_t)(lane & 7) * SWP_W_STRIDE + (uint32_t)(lane >> 3) * 16u;     // + nt * 8 rows
+    const int gq = lane >> 2, qq = lane & 3;                              // accumulator fragment: rows gq / gq + 8, columns 2 qq (+1)
+
+    uint32_t phase_bits = 0;                                              // bit s = parity of ring stage s
+    uint32_t chunk_ctr = 0;                                               // chunks this warp has consumed so far (stage = ctr & 1)
+    const long long total_warps = (long long)gridDim.x * SWP_WARPS;
+
+    for (long long item = (long long)blockIdx.x * SWP_WARPS + warp; item < g.items; item += total_warps) {
+        // item -> (image, row block, strip); consecutive warps take neighbouring strips (they share halo columns in L2)
+        const int xs = (int)(item % g.strips);
+        const long long rest = item / g.strips;
+        const int q = (int)(rest % g.nq), img = (int)(rest / g.nq);
+        const int x0 = xs * 8, y0 = q * g.rb;
+        const int rows_out = min(g.rb, g.h - y0);
+        if (rows_out <= 0) continue;
+        const int rows_in = rows_out + 2, nchunks = (rows_in + SWP_ROWS - 1) / SWP_ROWS;
+        const int ncol_ok = g.w - x0;                                     // strip pixels px < ncol_ok exist
+        auto issue = [&](int ci) {                                        // lane 0: chunk ci of this item -> its ring stage
+            const uint32_t s = (chunk_ctr + (uint32_t)ci) & 1u;
+            mbar_expect_tx(bars + 8u * s, SWP_CHUNK);
+            tma_load_4d(sRing + s * SWP_CHUNK, &tmap_x, bars + 8u * s, 0, x0 - 1, y0 - 1 + ci * SWP_ROWS, img);
+        };
+        if (lane == 0) {
+            issue(0);
+            if (nchunks > 1) issue(1);
+        }
+        float2 ring[3][9];
+        uint32_t stage_addr = 0;
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows_in; r0 += 3) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int r = r0 + j;
+                if (r >= rows_in) break;
+                const int ci = r >> 3, rr = r & 7;
+                if (rr == 0) {                                            // entering a new chunk: wait for its bytes
+                    const uint32_t s = (chunk_ctr + (uint32_t)ci) & 1u;
+                    mbar_wait(bars + 8u * s, (phase_bits >> s) & 1u);
+                    phase_bits ^= 1u << s;
+                    stage_addr = sRing + s * SWP_CHUNK + lane_off;
+                }
+                {   // input row r enters the window
+                    const uint32_t rp = stage_addr + (uint32_t)rr * (SWP_COLS * SWP_PIX);
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) ring[j][c] = unpack(swp_lds_u32(rp + (uint32_t)c * SWP_PIX));
+                }
+                // the chunk's last row is in registers once this row's output is computed: then its stage is refilled
+                const bool refill = (rr == SWP_ROWS - 1 || r == rows_in - 1);
+                if (r < 2) continue;                                      // (rows_in >= 3: no refill point among rows 0, 1)
+                const int t = r - 2;                                      // output row of the block: window rows r-2, r-1, r
+                float2 acc[4] = {bias2, bias2, bias2, bias2};
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int slot = (j + 1 + ky) % 3;                    // rows r-2, r-1, r live in slots (j+1)%3, (j+2)%3, j
+#pragma unroll
+                    for (int c = 0; c < 9; ++c)
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx)
+                                if (2 * p + kx == c) acc[p] = ffma2(ring[slot][c], wk[ky * 3 + kx], acc[p]);
+                }
+                const uint32_t arow = a_lane_addr + (uint32_t)((t & 1) * 8) * SWP_A_STRIDE;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) swp_sts_u32(arow + (uint32_t)(2 * p) * SWP_A_STRIDE, relu6_bf16x2(acc[p]));
+                if ((t & 1) || t == rows_out - 1) {
+                // ---- two output rows (or the last single one) are staged: 16 pixels x cin -> pointwise GEMM on mma.sync
+                __syncwarp();
+                uint32_t a0[4], a1[4] = {0u, 0u, 0u, 0u};
+                ldmatrix_x4(a_ld_addr, a0);
+                if (g.ks > 1) ldmatrix_x4(a_ld_addr + 32u, a1);
+#pragma unroll 1
+                for (int nt = 0; nt < g.nt; ++nt) {
+                    uint32_t b[4];
+                    ldmatrix_x4(w_ld_addr + (uint32_t)(nt * 8) * SWP_W_STRIDE, b);
+                    float d[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_bf16_16816(d, a0, b[0], b[1]);
+                    if (g.ks > 1) mma_bf16_16816(d, a1, b[2], b[3]);
+                    float2 bv;
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bv.x), "=f"(bv.y) : "r"(sBias + (uint32_t)(nt * 8 + 2 * qq) * 4u));
+                    const uint32_t o = sO + (uint32_t)gq * SWP_O_STRIDE + (uint32_t)(nt * 16 + qq * 4);
+                    swp_sts_u32(o, relu6_bf16x2(d[0] + bv.x, d[1] + bv.y));
+                    swp_sts_u32(o + 8u * SWP_O_STRIDE, relu6_bf16x2(d[2] + bv.x, d[3] + bv.y));
+                }
+                __syncwarp();
+                // 16-byte coalesced stores: 8 lanes cover one pixel's channels, 4 pixels per instruction
+                const int t_first = (t & 1) ? t - 1 : t;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = i * 4 + (lane >> 3), ch = lane & 7;   // staging row = (output row parity) * 8 + pixel
+                    const int tt = t_first + (row >> 3), px = row & 7;
+                    if (ch < g.nt && tt <= t && px < ncol_ok) {
+                        const uint4 v = ld_shared_v4(sO + (uint32_t)row * SWP_O_STRIDE + (uint32_t)ch * 16u);
+                        *reinterpret_cast<uint4 *>(y + ((((size_t)img * g.h + (y0 + tt)) * g.w + (x0 + px)) * g.nc + ch * 8)) = v;
+                    }
+                }
+                __syncwarp();                                             // staging buffers are rewritten by the next rows
+                }
+                if (refill) {                                             // every lane has consumed the chunk (its FMAs are issued)
+                    __syncwarp();
+                    if (lane == 0 && ci + 2 < nchunks) issue(ci + 2);
+                }
+            }
+        }
+        chunk_ctr += (uint32_t)nchunks;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+bool sepwarp_supported(int k, int nc, int stride, int dil) {
+    return stride == 1 && dil == 1 && k >= 8 && k <= 32 && k % 8 == 0 && nc >= 8 && nc <= 64 && nc % 8 == 0 &&
+           getenv("PN_NO_SEPWARP") == nullptr;
+}
+
+int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, int nc) {
+    PN_CHECK_ARG(n > 0 && h > 0 && wd > 0 && sepwarp_supported(k, nc, 1, 1), "pn_sepconv_block: bad narrow-block shape");
+    memset(op, 0, sizeof(*op));
+    SwpGeom g;
+    memset(&g, 0, sizeof(g));
+    g.n = n; g.h = h; g.w = wd; g.k = k; g.nc = nc;
+    g.strips = ceil_div(wd, 8);
+    g.ks = ceil_div(k, 16);
+    g.nt = nc / 8;
+    // row blocks: about six items per warp of a full grid, at least 8 output rows each
+    const long long warps = (long long)num_sms() * SWP_WARPS;
+    long long nq = (6 * warps + (long long)n * g.strips - 1) / ((long long)n * g.strips);
+    const int max_nq = ceil_div(h, 8);
+    if (nq > max_nq) nq = max_nq;
+    if (nq < 1) nq = 1;
+    g.rb = ceil_div(h, (int)nq);
+    g.nq = ceil_div(h, g.rb);
+    g.items = (long long)n * g.strips * g.nq;
+    const uint64_t dims[4] = {(uint64_t)k, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)k * 2, (uint64_t)wd * k * 2, (uint64_t)h * wd * k * 2};
+    const uint32_t box[4] = {32u, (uint32_t)SWP_COLS, (uint32_t)SWP_ROWS, 1u};
+    int rc = encode_tmap(op->tmap_x, x, 2, 4, dims, strides, box, 0);
+    if (rc != PN_OK) return rc;
+    static_assert(sizeof(SwpGeom) <= sizeof(op->geom), "SepWarpOp::geom too small");
+    memcpy(op->geom, &g, sizeof(g));
+    return PN_OK;
+}
+
+int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, const void *pw_w, const float *pw_b, void *y,
+                   cudaStream_t st) {
+    PN_CHECK_ARG(op && dw_w && dw_b && pw_w && pw_b && y, "pn_sepconv_block: null pointer");
+    PN_CHECK_ARG(((uintptr_t)y & 15) == 0 && ((uintptr_t)pw_w & 15) == 0 && ((uintptr_t)dw_w & 7) == 0 && ((uintptr_t)dw_b & 7) == 0,
+                 "pn_sepconv_block: misaligned pointer");
+    SwpGeom g;
+    memcpy(&g, op->geom, sizeof(g));
+    static bool configured = false;
+    if (!configured) {
+        PN_CHECK_CUDA(cudaFuncSetAttribute(sepwarp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWP_SMEM));
+        configured = true;
+    }
+    const long long ctas = (g.items + SWP_WARPS - 1) / SWP_WARPS;
+    const int grid = (int)(ctas < num_sms() ? ctas : num_sms());
+    sepwarp_kernel<<<grid, SWP_THREADS, SWP_SMEM, st>>>(*reinterpret_cast<const CUtensorMap *>(op->tmap_x), dw_w, dw_b,
+                                                         (const __nv_bfloat16 *)pw_w, pw_b, (__nv_bfloat16 *)y, g);
+    PN_CHECK_LAUNCH();
+    return PN_OK;
+}
+
+void sepwarp_describe(const SepWarpOp *op, char *out, size_t cap) {
+    SwpGeom g;
+    memcpy(&g, op->geom, sizeof(g));
+    snprintf(out, cap, "warp-autonomous strips %d x %d row blocks of %d rows, k16 slices %d, n8 tiles %d, items %lld, smem %d", g.strips,
+             g.nq, g.rb, g.ks, g.nt, g.items, SWP_SMEM);
+}
+
+}  // namespace pn
