@@ -87,6 +87,12 @@ __device__ __forceinline__ uint64_t stc_smem_desc(uint32_t saddr) {      // K-ma
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+__device__ __forceinline__ uint32_t lds_u32s(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+
 struct StemTcArgs {
     const uint8_t *img;
     const float *w27, *bias;
@@ -195,20 +201,35 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
 #pragma unroll
         for (int k = 27; k < 32; ++k) f[k] = 0.f;
         const uint32_t sp = sSpan + (uint32_t)buf * (uint32_t)a.span_cap;
+        // The 9 bytes of a window row (3 pixels x BGR) are contiguous: three aligned 32-bit loads + funnel shifts bring them
+        // to byte 0 (one pixel later when the window starts left of the image), then one PRMT per tap builds 2^23 + x.
+        const int ix0 = ox * a.stride - 1;
+        const int lead = ix0 < 0 ? 1 : 0;                                  // window column 0 is padding (pad = 1)
+        bool okx[3];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) okx[kx] = live && ix0 + kx >= 0 && ix0 + kx < a.w;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = oy * a.stride - 1 + ky;
             const bool row_ok = live && iy >= 0 && iy < a.h;
             const long long rowoff = ((long long)img_i * a.h + iy) * row_bytes - lo16;
+            const uint32_t b0 = row_ok ? (uint32_t)(rowoff + (long long)(ix0 + lead) * 3) : 0u;
+            const uint32_t a0 = sp + (b0 & ~3u), sh = (b0 & 3u) * 8u;
+            const uint32_t w0 = lds_u32s(a0), w1 = lds_u32s(a0 + 4), w2 = lds_u32s(a0 + 8);
+            uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = w2 >> sh;
+            const uint32_t ls = (uint32_t)lead * 24u;                      // shift the 9 bytes up by one pixel
+            v2 = __funnelshift_l(v1, v2, ls);
+            v1 = __funnelshift_l(v0, v1, ls);
+            v0 = v0 << ls;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ox * a.stride - 1 + kx;
-                const bool ok = row_ok && ix >= 0 && ix < a.w;
-                const uint32_t addr = sp + (uint32_t)(ok ? rowoff + (long long)ix * 3 : 0);
+                const bool ok = row_ok && okx[kx];
 #pragma unroll
-                for (int ci = 0; ci < 3; ++ci) {                   // BGR bytes -> RGB taps; 2^23 + 128 + (x - 128) trick
-                    const uint32_t x = lds_u8(addr + (uint32_t)(2 - ci));
-                    f[(ky * 3 + kx) * 3 + ci] = ok ? __uint_as_float(0x4B000000u | x) - 8388736.0f : -0.5f;
+                for (int ci = 0; ci < 3; ++ci) {                           // BGR bytes -> RGB taps; 2^23 + 128 + (x - 128) trick
+                    const int i = kx * 3 + (2 - ci);                       // byte index inside the 9-byte window row
+                    const uint32_t src = i < 4 ? v0 : i < 8 ? v1 : v2;
+                    const uint32_t bits = __byte_perm(src, 0x4B000000u, 0x7540u + (uint32_t)(i & 3));
+                    f[(ky * 3 + kx) * 3 + ci] = ok ? __uint_as_float(bits) - 8388736.0f : -0.5f;
                 }
             }
         }
