@@ -112,8 +112,10 @@ struct DecodeShared {
 };
 
 // decode.py:15-16 / :50-51 -- np.clip(np.round(p / stride), 0, hi).astype(int32): f64 divide, half-even.
-__device__ __forceinline__ int to_cell(double p, double stride, int hi) {
-    double r = rint(__ddiv_rn(p, stride));
+// inv > 0: the stride is a power of two and p * (1 / stride) is the same double as p / stride (an exact scaling), which
+// saves the ~30-instruction division sequence four times per hop; otherwise (inv == 0) the division is done as written.
+__device__ __forceinline__ int to_cell(double p, double stride, double inv, int hi) {
+    double r = rint(inv > 0.0 ? __dmul_rn(p, inv) : __ddiv_rn(p, stride));
     r = fmin(fmax(r, 0.0), (double)hi);
     return (int)r;
 }
@@ -139,12 +141,13 @@ __device__ double np_sum(const double *a, int n) {
 // decode.py:9-63: one displacement hop source -> target along edge e, on the pose record in slot `s`.
 __device__ __forceinline__ void hop(const DecodeArgs &a, DecodeShared &S, int s, int img, const pn_map &disp, int e, int src,
                                     int tgt) {
-    const double stride = (double)a.prm.output_stride;
+    const int os = a.prm.output_stride;
+    const double stride = (double)os, inv = (os & (os - 1)) == 0 ? 1.0 / stride : 0.0;
     const double sy = S.kc[src][0][s], sx = S.kc[src][1][s];
-    const int iy = to_cell(sy, stride, a.h - 1), ix = to_cell(sx, stride, a.w - 1);
+    const int iy = to_cell(sy, stride, inv, a.h - 1), ix = to_cell(sx, stride, inv, a.w - 1);
     const double py = __dadd_rn(sy, (double)map_at(disp, img, e, iy, ix));                    // decode.py:39-40
     const double px = __dadd_rn(sx, (double)map_at(disp, img, PN_NUM_EDGES + e, iy, ix));
-    const int ty = to_cell(py, stride, a.h - 1), tx = to_cell(px, stride, a.w - 1);
+    const int ty = to_cell(py, stride, inv, a.h - 1), tx = to_cell(px, stride, inv, a.w - 1);
     const float sc = map_at(a.heat, img, tgt, ty, tx);                                        // decode.py:53
     const float oy = map_at(a.off, img, tgt, ty, tx), ox = map_at(a.off, img, PN_NUM_PARTS + tgt, ty, tx);
     S.ks[tgt][s] = sc;

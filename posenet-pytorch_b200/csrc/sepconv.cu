@@ -577,7 +577,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
 
     // ---- tile search: fewest (tiles x per-tile cost); one strip per depthwise thread group per sub-tile
     const int min_w = g.n_halves == 2 ? 3 : 2;                     // W ring entries (one per UMMA column block)
-    const int fixed = 2 * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 1024 + 4224;   // minimum non-patch smem
+    const int fixed = 2 * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 640 + 4224;   // minimum non-patch smem
     double best = 1e300;
     int f_th = 0, f_tw = 0, f_subs = 0;                            // tuning / debugging aid: PN_SEP_TILE="th,tw,subs"
     if (const char *force = getenv("PN_SEP_TILE"))
@@ -641,7 +641,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     g.tiles = (long long)n * g.tiles_x * g.tiles_y * g.n_tiles;
     // ---- shared-memory carve-up: W ring, A ring, output staging panels, patch ring, bias, barriers
     const long long bias_bytes = ((long long)g.n_tiles * g.panels * 64 * 4 + 127) & ~127ll;
-    const long long avail = SEP_SMEM_MAX - 1024 - 1024 - bias_bytes;   // alignment slack, barrier block (SepBars::total)
+    const long long avail = SEP_SMEM_MAX - 1024 - 640 - bias_bytes;   // alignment slack, barrier block (SepBars::total)
     auto fits = [&](int pst, int wst, int ast, int stg) {
         return (long long)wst * g.w_stage_bytes + (long long)ast * SEP_A_BYTES + (long long)stg * SEP_STG_BYTES +
                    (long long)pst * g.patch_stage_bytes <= avail;
@@ -662,6 +662,10 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
                     }
                 }
     PN_CHECK_ARG(bestp >= 0, "pn_sepconv_block: shared memory budget exceeded");
+    // 512-column tiles have a single accumulator: the epilogue cannot overlap the next tile's MMAs, so what pays is a
+    // short epilogue (two staging panels keep the TMA stores in flight) and a third A stage for the depthwise warps to
+    // run ahead into -- worth more than a third patch stage (measured: 84 -> 77 us on the 512 -> 512 blocks)
+    if (g.n_halves == 2 && g.subs == 1 && fits(2, min_w, 3, 2)) { g.p_stages = 2; g.w_stages = min_w; g.a_stages = 3; g.stg_bufs = 2; }
     if (const char *force = getenv("PN_SEP_STAGES")) {              // tuning aid: "p,w,a,stg"
         int fp = 0, fw = 0, fa = 0, fs = 0;
         if (sscanf(force, "%d,%d,%d,%d", &fp, &fw, &fa, &fs) == 4 && fp >= g.subs + 1 && fp <= SEP_MAX_P && fw >= min_w &&
@@ -669,7 +673,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
             g.p_stages = fp; g.w_stages = fw; g.a_stages = fa; g.stg_bufs = fs;
         }
     }
-    static_assert(SepBars::total <= 1024, "barrier block exceeds its reserve");
+    static_assert(SepBars::total <= 640, "barrier block exceeds its reserve");
     g.off_a = (unsigned)g.w_stages * g.w_stage_bytes;
     g.off_stg = g.off_a + (unsigned)g.a_stages * SEP_A_BYTES;
     g.off_patch = g.off_stg + (unsigned)g.stg_bufs * SEP_STG_BYTES;
