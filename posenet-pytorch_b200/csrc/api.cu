@@ -214,10 +214,10 @@ int pn_plan_create(const pn_net_desc *desc, void *arena, size_t arena_bytes, pn_
             snprintf(p->names[p->launches++], sizeof(p->names[0]), "stem");
             continue;
         }
-        // Fuse a block when its whole output width fits one accumulator tile (<= 512 channels): wider blocks would
-        // redo the depthwise work once per 512 outputs and are faster as two kernels (PN_SEP_ALL=1 fuses them too).
+        // Fuse a block when the depthwise work is done once per tile (sep_fuse_recommended; PN_SEP_ALL=1 fuses every
+        // supported block)
         S.fused = desc->dtype == PN_BF16 && !(desc->flags & PN_PLAN_UNFUSED) && sep_supported(L.cin, L.cout, L.stride, L.dilation) &&
-                  (L.cout <= 512 || getenv("PN_SEP_ALL") != nullptr);
+                  (sep_fuse_recommended(L.cin, L.cout, L.stride, L.dilation) || getenv("PN_SEP_ALL") != nullptr);
         if (S.fused) {
             rc = sep_prepare(&S.sep, p->buf[cur], L.dw_w, L.dw_b, L.pw_w, p->buf[cur ^ 1], desc->n, S.h_in, S.w_in, L.cin, L.cout,
                              L.stride, L.dilation);

@@ -134,6 +134,7 @@ struct SepWarpOp {
     alignas(8) unsigned char geom[64];
 };
 bool sepwarp_supported(int k, int nc, int stride, int dil);
+int sepwarp_geometry(SepWarpOp *op, int n, int h, int wd, int k, int nc);
 int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, int nc);
 int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, const void *pw_w, const float *pw_b, void *y,
                    cudaStream_t s);
@@ -156,6 +157,7 @@ struct SepOp {
     void *y;
 };
 bool sep_supported(int k, int nc, int stride, int dil);
+bool sep_fuse_recommended(int k, int nc, int stride, int dil);
 int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int dil);
 int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, const void *pw_w, void *y, int n, int h,
                 int wd, int k, int nc, int stride, int dil);

@@ -37,7 +37,7 @@ constexpr int SEP_DW_WARPS = 10;
 constexpr int SEP_FIRST_DW_WARP = 6;
 constexpr int SEP_THREADS = (SEP_FIRST_DW_WARP + SEP_DW_WARPS) * 32;   // 512
 constexpr int SEP_DW_THREADS = SEP_DW_WARPS * 32;                      // 320
-constexpr int SEP_MAX_A = 4;
+constexpr int SEP_MAX_A = 6;
 constexpr int SEP_A_BYTES = 128 * 128;                                 // 128 rows x 64 bf16
 constexpr int SEP_STG_BYTES = 128 * 128;                               // one 128 x 64 bf16 output panel
 constexpr int SEP_MAX_P = 6, SEP_MAX_W = 4;
@@ -52,6 +52,7 @@ struct SepGeom {
     int n_halves, n_half, acc_bufs;       // a tile's accumulator = n_halves UMMA column blocks of n_half (<= 256) columns
     int kblocks;
     int half, cbox;                       // K <= 32: two pixel columns per warp (16 lanes each), 32-channel patch box
+    int cl;                               // CTAs per cluster (1, 2, 4): each owns 256 output channels and 1 / cl of the k-blocks
     int p_stages, w_stages, a_stages, stg_bufs;
     unsigned patch_stage_bytes, patch_box_bytes, wgt_off, w_stage_bytes;
     unsigned off_a, off_stg, off_patch, off_bias, off_bar;   // from the 1024-aligned base; W stages sit at 0
@@ -93,6 +94,34 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
     return r;
 }
+// ---- cluster helpers (N-split blocks, see the kernel header) ------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {           // shared::cta -> shared::cluster of `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void remote_expect_tx(uint32_t cluster_bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t cluster_dst, uint32_t src, uint32_t bytes, uint32_t cluster_bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cluster_dst),
+                 "r"(src), "r"(bytes), "r"(cluster_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {      // arrives on `bar` of every CTA in the mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
 __device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool on) {     // predicated, branch-free
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)on) : "memory");
 }
@@ -125,12 +154,20 @@ __device__ int g_sep_trace_cap = 0;
 #define SEP_TRACE(role, idx, what) do { } while (0)
 #endif
 
-template <int S, int D, bool HALF>
+template <int S, int D, bool HALF, int CL>
 __global__ void __launch_bounds__(SEP_THREADS, 1)
 sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dww,
                const __grid_constant__ CUtensorMap tmap_dwb, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_y, const float *__restrict__ pw_bias, const SepGeom g) {
     constexpr int CB = 64;                                  // channels per k-block (ragged K is zero-filled by TMA)
+    // CL > 1: a cluster of CL CTAs shares every 128-pixel tile.  CTA `rank` owns output channels [rank * 256, +256) --
+    // its own pointwise weights, accumulators (double-buffered) and epilogue -- and computes the depthwise result of the
+    // k-blocks kb % CL == rank only; the finished A stage is pushed into the peers' shared memory with one DSMEM bulk copy
+    // each (completing on their a_full barrier), so the depthwise work, which bounds these blocks, is done once per tile.
+    constexpr bool CLUSTER = CL > 1;
+    const int rank = CLUSTER ? (int)cluster_rank() : 0;
+    const long long tile_first = CLUSTER ? blockIdx.x / CL : blockIdx.x, tile_step = CLUSTER ? gridDim.x / CL : gridDim.x;
+    const int col_base = CLUSTER ? rank * g.n_tile : 0;      // first output channel of this CTA
 
     extern __shared__ uint8_t sep_smem_raw[];
     const uint32_t base = (smem_u32(sep_smem_raw) + 1023u) & ~1023u;
@@ -160,8 +197,9 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             mbar_init(bar(SepBars::w_empty, s), 1);
         }
         for (int s = 0; s < g.a_stages; ++s) {
-            mbar_init(bar(SepBars::a_full, s), SEP_DW_WARPS);
-            mbar_init(bar(SepBars::a_empty, s), 1);
+            // a stage produced by a peer is filled by its bulk copy (one expect_tx arrival + the bytes)
+            mbar_init(bar(SepBars::a_full, s), (!CLUSTER || s % CL == rank) ? SEP_DW_WARPS : 1);
+            mbar_init(bar(SepBars::a_empty, s), CL);            // every CTA's MMAs have read the stage (multicast commits)
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar(SepBars::tfull, s), 1);
@@ -187,10 +225,11 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     {   // pointwise bias -> shared memory once (the epilogue reads it per panel)
         float *sbias = reinterpret_cast<float *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bias);
         const int ncp = g.n_tiles * g.panels * 64;                // padded so that ragged panels read zeros
-        for (int i = threadIdx.x; i < ncp; i += SEP_THREADS) sbias[i] = i < g.nc ? __ldg(pw_bias + i) : 0.f;
+        for (int i = threadIdx.x; i < ncp; i += SEP_THREADS) sbias[i] = col_base + i < g.nc ? __ldg(pw_bias + col_base + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER) cluster_sync_all();                          // the peers' barriers exist before anything remote targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -203,13 +242,33 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             int ps = 0, ws = 0, tr_p = 0;
             uint32_t pph = 0, wph = 0;
             (void)tr_p;
-            long long p_tile = blockIdx.x, w_tile = blockIdx.x;
-            int p_kb = 0, p_sub = 0, w_kb = 0, w_hf = 0;
+            long long p_tile = tile_first, w_tile = tile_first;
+            int p_kb = rank, p_sub = 0, w_kb = 0, w_hf = 0;       // patches: this CTA's k-blocks only
             int p_img = 0, p_ty = 0, p_tx = 0, w_col = 0;
             bool p_new = true, w_new = true;
+            // cluster: this thread also pushes every finished A stage of this CTA to the peers the moment its last depthwise
+            // warp has arrived (NOT from the MMA loop: that one runs in k-block order and would make the two CTAs ping-pong)
+            int s_as = rank;
+            uint32_t s_aph = 0;
+            long long s_left = 0;
+            if (CLUSTER && tile_first < g.tiles) s_left = ((g.tiles - tile_first + tile_step - 1) / tile_step) * (g.kblocks / CL);
             const long long t0 = clock64();
-            while (p_tile < g.tiles || w_tile < g.tiles) {
+            while (p_tile < g.tiles || w_tile < g.tiles || s_left > 0) {
                 bool progress = false;
+                if (CLUSTER && s_left > 0 && mbar_test(bar(SepBars::a_full, s_as), s_aph)) {
+                    const uint32_t sa = a_addr(s_as);
+#pragma unroll
+                    for (int pr = 0; pr < CL; ++pr)
+                        if (pr != rank) {
+                            const uint32_t rbar = map_to_cta(bar(SepBars::a_full, s_as), (uint32_t)pr);
+                            remote_expect_tx(rbar, SEP_A_BYTES);
+                            dsmem_bulk_copy(map_to_cta(sa, (uint32_t)pr), sa, SEP_A_BYTES, rbar);
+                        }
+                    s_as += CL;
+                    if (s_as >= g.a_stages) { s_as -= g.a_stages; s_aph ^= 1; }
+                    --s_left;
+                    progress = true;
+                }
                 if (p_tile < g.tiles) {
                     if (p_new) {
                         const int m_tile = (int)(p_tile / g.n_tiles);
@@ -232,20 +291,21 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
                         if (++p_sub == g.subs) {
                             p_sub = 0;
-                            if (++p_kb == g.kblocks) { p_kb = 0; p_tile += gridDim.x; p_new = true; }
+                            p_kb += CL;
+                            if (p_kb >= g.kblocks) { p_kb = rank; p_tile += tile_step; p_new = true; }
                         }
                         progress = true;
                     }
                 }
                 if (w_tile < g.tiles) {
-                    if (w_new) { w_col = (int)(w_tile % g.n_tiles) * g.n_tile; w_new = false; }
+                    if (w_new) { w_col = col_base + (int)(w_tile % g.n_tiles) * g.n_tile; w_new = false; }
                     if (mbar_test(bar(SepBars::w_empty, ws), wph ^ 1)) {
                         mbar_expect_tx(bar(SepBars::w_full, ws), g.w_stage_bytes);
                         tma_load_2d(w_addr(ws), &tmap_w, bar(SepBars::w_full, ws), w_kb * CB, w_col + w_hf * g.n_half);
                         if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
                         if (++w_hf == g.n_halves) {
                             w_hf = 0;
-                            if (++w_kb == g.kblocks) { w_kb = 0; w_tile += gridDim.x; w_new = true; }
+                            if (++w_kb == g.kblocks) { w_kb = 0; w_tile += tile_step; w_new = true; }
                         }
                         progress = true;
                     }
@@ -263,7 +323,8 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             int as = 0, ws = 0, acc = 0, tr_i = 0;
             uint32_t aph = 0, wph = 0, acc_phase = 0;
             (void)tr_i;
-            for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+            long long kb_total = 0;                                   // k-blocks consumed (A-stage uses), for the drain below
+            for (long long tile = tile_first; tile < g.tiles; tile += tile_step) {
                 mbar_wait(bar(SepBars::tempty, acc), acc_phase ^ 1);
                 tc_fence_after();
                 SEP_TRACE(1, tr_i, 0);
@@ -286,13 +347,24 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         tc_commit(bar(SepBars::w_empty, ws));
                         if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
                     }
-                    tc_commit(bar(SepBars::a_empty, as));
+                    if (CLUSTER) tc_commit_multicast(bar(SepBars::a_empty, as), (uint16_t)((1u << CL) - 1u));
+                    else tc_commit(bar(SepBars::a_empty, as));
+                    ++kb_total;
                     SEP_TRACE(1, tr_i, 2);
                     ++tr_i;
                     if (++as == g.a_stages) { as = 0; aph ^= 1; }
                 }
                 tc_commit(bar(SepBars::tfull, acc));
                 if (++acc == g.acc_bufs) { acc = 0; acc_phase ^= 1; }
+            }
+            if (CLUSTER) {
+                // Drain: the peers' multicast commits arrive on this CTA's a_empty barriers asynchronously; every stage's
+                // last use must have collected all CL arrivals before this CTA may leave (its shared memory dies with it).
+                for (int s2 = 0; s2 < g.a_stages; ++s2) {
+                    if (kb_total <= s2) continue;
+                    const long long uses = (kb_total - s2 + g.a_stages - 1) / g.a_stages;
+                    mbar_wait(bar(SepBars::a_empty, s2), (uint32_t)((uses - 1) & 1));
+                }
             }
         }
     } else if (warp < SEP_FIRST_DW_WARP) {
@@ -304,7 +376,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         int acc = 0, buf = 0, tr_e = 0;
         uint32_t acc_phase = 0;
         (void)tr_e;
-        for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+        for (long long tile = tile_first; tile < g.tiles; tile += tile_step) {
             const int n_tile = (int)(tile % g.n_tiles);
             const int m_tile = (int)(tile / g.n_tiles);
             const int img = m_tile / m_tiles_per_img;
@@ -346,7 +418,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 fence_async_smem();                                      // generic writes -> visible to TMA
                 sep_epi_bar();
                 if (issuer) {
-                    tma_store_4d(&tmap_y, staging + (uint32_t)buf * SEP_STG_BYTES, col0, tx * g.tw, ty * g.th, img);
+                    tma_store_4d(&tmap_y, staging + (uint32_t)buf * SEP_STG_BYTES, col_base + col0, tx * g.tw, ty * g.th, img);
                     bulk_commit();
                 }
                 if (g.stg_bufs == 2) buf ^= 1;
@@ -383,13 +455,13 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         // never skip a phase; inside an item the segments are handed out by an atomic counter per patch stage (uses of a
         // stage cannot interleave: the refill waits for all warps to have left the previous use).  A warp that finds the
         // item exhausted moves straight on to the next one while the others finish.
-        int ps = 0, as = 0, puse = 0, tr_d = 0;
+        int ps = 0, as = rank, puse = 0, tr_d = 0;                       // cluster: this CTA fills the A stages s % CL == rank
         uint32_t pph = 0, aph = 0;
         (void)tr_d;
         const bool tracer = (warp == SEP_FIRST_DW_WARP && lane == 0);
         (void)tracer;
-        for (long long tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
-          for (int kb = 0; kb < g.kblocks; ++kb) {
+        for (long long tile = tile_first; tile < g.tiles; tile += tile_step) {
+          for (int kb = rank; kb < g.kblocks; kb += CL) {
             if (tracer) SEP_TRACE(0, tr_d, 0);
             mbar_wait(bar(SepBars::a_empty, as), aph ^ 1);            // the MMAs that read this A stage have retired
             if (tracer) SEP_TRACE(0, tr_d, 1);
@@ -506,7 +578,8 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(SepBars::a_full, as));
             if (tracer) { SEP_TRACE(0, tr_d, 3); ++tr_d; }
-            if (++as == g.a_stages) { as = 0; aph ^= 1; }
+            as += CL;
+            if (as >= g.a_stages) { as -= g.a_stages; aph ^= 1; }
           }
         }
     }
@@ -514,6 +587,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER) cluster_sync_all();                          // no peer still copies into / arrives on this CTA's shared memory
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
@@ -530,6 +604,14 @@ static int next_pow2_cols(int c) {
 bool sep_supported(int k, int nc, int stride, int dil) {
     return k % 8 == 0 && nc % 16 == 0 && k >= 8 && nc >= 16 &&
            ((stride == 1 && (dil == 1 || dil == 2 || dil == 4)) || (stride == 2 && dil == 1));
+}
+
+// Blocks worth running fused: whole output width in one accumulator tile (<= 512 channels), or 1024 channels shared by a
+// 4-CTA cluster; anything else would redo the depthwise work once per 512 outputs and is faster as two kernels.
+bool sep_fuse_recommended(int k, int nc, int stride, int dil) {
+    if (!sep_supported(k, nc, stride, dil)) return false;
+    if (nc <= 512) return true;
+    return nc == 1024 && k % 64 == 0 && (k / 64) % 4 == 0 && getenv("PN_SEP_CLUSTER") != nullptr;
 }
 
 // Tile shape, stage counts and the shared-memory carve-up for one block (pure host arithmetic, no CUDA calls).
@@ -565,9 +647,20 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     // is then done once per 512 output channels instead of once per 256.
     g.n_tiles = ceil_div(nc, 512);
     g.n_tile = nc / g.n_tiles;
+    // ... or, for 512 / 1024 output channels, a cluster of 2 / 4 CTAs shares the tile: 256 double-buffered columns each,
+    // the depthwise result of a k-block computed by one CTA and copied to the others (see the kernel).  Measured on the
+    // 512 -> 512 blocks of C2: 82 us against 72 us for the single-CTA tile (the A-stage turnaround across two SMs costs
+    // more than the overlapped epilogue wins), 4-CTA clusters are latency-bound outright -- so this path is opt-in
+    // (PN_SEP_CLUSTER=1) and exercised by the tests only.
+    g.cl = 1;
+    if ((nc == 512 || nc == 1024) && k % cb == 0 && (k / cb) % (nc / 256) == 0 && getenv("PN_SEP_CLUSTER") != nullptr) {
+        g.cl = nc / 256;
+        g.n_tiles = 1;
+        g.n_tile = 256;
+    }
     g.n_halves = g.n_tile > 256 ? 2 : 1;
     g.n_half = g.n_tile / g.n_halves;
-    PN_CHECK_ARG(g.n_tile * g.n_tiles == nc && g.n_half * g.n_halves == g.n_tile && g.n_half % 16 == 0,
+    PN_CHECK_ARG(g.n_tile * g.n_tiles * g.cl == nc && g.n_half * g.n_halves == g.n_tile && g.n_half % 16 == 0,
                  "pn_sepconv_block: cout %d does not split into tiles", nc);
     g.panels = ceil_div(g.n_tile, 64);
     g.acc_bufs = g.n_halves == 2 ? 1 : 2;
@@ -577,7 +670,8 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
 
     // ---- tile search: fewest (tiles x per-tile cost); one strip per depthwise thread group per sub-tile
     const int min_w = g.n_halves == 2 ? 3 : 2;                     // W ring entries (one per UMMA column block)
-    const int fixed = 2 * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 640 + 4224;   // minimum non-patch smem
+    const int min_a = g.cl > 2 ? g.cl : 2;                         // cluster: the A ring is a multiple of the cluster size
+    const int fixed = min_a * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 640 + 4224;   // minimum non-patch smem
     double best = 1e300;
     int f_th = 0, f_tw = 0, f_subs = 0;                            // tuning / debugging aid: PN_SEP_TILE="th,tw,subs"
     if (const char *force = getenv("PN_SEP_TILE"))
@@ -638,7 +732,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     PN_CHECK_ARG(best < 1e300, "pn_sepconv_block: no tile shape fits (cin %d stride %d dilation %d)", k, stride, dil);
     g.tiles_x = ceil_div(g.wo, g.tw);
     g.tiles_y = ceil_div(g.ho, g.th);
-    g.tiles = (long long)n * g.tiles_x * g.tiles_y * g.n_tiles;
+    g.tiles = (long long)n * g.tiles_x * g.tiles_y * g.n_tiles;       // cluster: m tiles (one cluster covers all columns)
     // ---- shared-memory carve-up: W ring, A ring, output staging panels, patch ring, bias, barriers
     const long long bias_bytes = ((long long)g.n_tiles * g.panels * 64 * 4 + 127) & ~127ll;
     const long long avail = SEP_SMEM_MAX - 1024 - 640 - bias_bytes;   // alignment slack, barrier block (SepBars::total)
@@ -648,19 +742,23 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     };
     int bestp = -1;
     for (int stg = 2; stg >= 1; --stg)
-        for (int ast = 3; ast >= 2; --ast)
+        for (int ast = SEP_MAX_A; ast >= 2; --ast) {
+            if (g.cl == 1 && ast > 3) continue;
+            if (g.cl > 1 && ast % g.cl != 0) continue;
             for (int wst = SEP_MAX_W; wst >= min_w; --wst)
                 for (int pst = SEP_MAX_P; pst >= 2 && pst >= g.subs + 1; --pst) {
                     if (!fits(pst, wst, ast, stg)) continue;
-                    const int want = 3 * g.subs > SEP_MAX_P ? SEP_MAX_P : 3 * g.subs;
+                    // (a cluster CTA consumes patches for 1 / cl of the k-blocks only: two stages cover it, A stages matter more)
+                    const int want = g.cl > 1 ? (g.subs + 1 > 2 ? g.subs + 1 : 2) : 3 * g.subs > SEP_MAX_P ? SEP_MAX_P : 3 * g.subs;
                     // deep patch prefetch first, then one spare W block, a third A stage, a second staging panel
-                    const int score = (pst >= want ? 1000 : pst * 100) + (wst > min_w + 1 ? min_w + 1 : wst) * 20 + ast * 8 + stg * 4 +
+                    const int score = (pst >= want ? 1000 : pst * 100) + (wst > min_w + 1 ? min_w + 1 : wst) * 20 + (g.cl > 1 ? (ast > 4 ? 4 : ast) * 16 : ast * 8) + stg * 4 +
                                       (pst > want ? 1 : 0);
                     if (score > bestp) {
                         bestp = score;
                         g.p_stages = pst; g.w_stages = wst; g.a_stages = ast; g.stg_bufs = stg;
                     }
                 }
+        }
     PN_CHECK_ARG(bestp >= 0, "pn_sepconv_block: shared memory budget exceeded");
     // 512-column tiles have a single accumulator: the epilogue cannot overlap the next tile's MMAs, so what pays is a
     // short epilogue (two staging panels keep the TMA stores in flight) and a third A stage for the depthwise warps to
@@ -669,7 +767,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     if (const char *force = getenv("PN_SEP_STAGES")) {              // tuning aid: "p,w,a,stg"
         int fp = 0, fw = 0, fa = 0, fs = 0;
         if (sscanf(force, "%d,%d,%d,%d", &fp, &fw, &fa, &fs) == 4 && fp >= g.subs + 1 && fp <= SEP_MAX_P && fw >= min_w &&
-            fw <= SEP_MAX_W && fa >= 2 && fa <= SEP_MAX_A && fs >= 1 && fs <= 2 && fits(fp, fw, fa, fs)) {
+            fw <= SEP_MAX_W && fa >= 2 && fa <= SEP_MAX_A && fa % g.cl == 0 && fs >= 1 && fs <= 2 && fits(fp, fw, fa, fs)) {
             g.p_stages = fp; g.w_stages = fw; g.a_stages = fa; g.stg_bufs = fs;
         }
     }
@@ -734,22 +832,47 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
     return PN_OK;
 }
 
-template <int S, int D, bool HALF>
+template <int S, int D, bool HALF, int CL>
 static int sep_launch_t(const SepOp *op, const SepGeom &g, const float *pw_bias, cudaStream_t st) {
     static bool configured = false;
-    auto kern = sepconv_kernel<S, D, HALF>;
+    static int max_clusters = 0;
+    auto kern = sepconv_kernel<S, D, HALF, CL>;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(SEP_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)op->smem_bytes;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
     if (!configured) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SEP_SMEM_MAX));
+        if (CL > 1) {                                             // how many clusters fit at once (GPC boundaries cost a few SMs)
+            cfg.gridDim = dim3((unsigned)(num_sms() / CL * CL), 1, 1);
+            cfg.dynamicSmemBytes = SEP_SMEM_MAX;
+            PN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+            PN_CHECK_ARG(max_clusters > 0, "pn_sepconv_block: no %d-CTA cluster fits on this device", CL);
+            cfg.dynamicSmemBytes = (size_t)op->smem_bytes;
+        }
         configured = true;
     }
-    const long long sms = num_sms();
-    const int grid = (int)(g.tiles < sms ? g.tiles : sms);
-    kern<<<grid, SEP_THREADS, op->smem_bytes, st>>>(
-        *reinterpret_cast<const CUtensorMap *>(op->tmap_x), *reinterpret_cast<const CUtensorMap *>(op->tmap_dww),
-        *reinterpret_cast<const CUtensorMap *>(op->tmap_dwb), *reinterpret_cast<const CUtensorMap *>(op->tmap_w),
-        *reinterpret_cast<const CUtensorMap *>(op->tmap_y), pw_bias, g);
-    PN_CHECK_LAUNCH();
+    const long long units = CL > 1 ? max_clusters : num_sms();     // persistent: one CTA (cluster) per SM (SM group)
+    const int grid = (int)(g.tiles < units ? g.tiles : units) * CL;
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    PN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *reinterpret_cast<const CUtensorMap *>(op->tmap_x),
+                                     *reinterpret_cast<const CUtensorMap *>(op->tmap_dww), *reinterpret_cast<const CUtensorMap *>(op->tmap_dwb),
+                                     *reinterpret_cast<const CUtensorMap *>(op->tmap_w), *reinterpret_cast<const CUtensorMap *>(op->tmap_y),
+                                     pw_bias, g));
     return PN_OK;
+}
+
+template <int S, int D>
+static int sep_launch_cl(const SepOp *op, const SepGeom &g, const float *pw_bias, cudaStream_t st) {
+    if (g.cl == 2) return sep_launch_t<S, D, false, 2>(op, g, pw_bias, st);
+    if (g.cl == 4) return sep_launch_t<S, D, false, 4>(op, g, pw_bias, st);
+    return sep_launch_t<S, D, false, 1>(op, g, pw_bias, st);
 }
 
 int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t st) {
@@ -757,26 +880,24 @@ int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t st) {
     if (op->warp_kind) return sepwarp_launch(&op->warp, op->dw_w, op->dw_b, op->pw_w, pw_bias, op->y, st);
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    if (op->stride == 2) return sep_launch_t<2, 1, false>(op, g, pw_bias, st);
-    if (g.half) return sep_launch_t<1, 1, true>(op, g, pw_bias, st);
-    if (op->dil == 1) return sep_launch_t<1, 1, false>(op, g, pw_bias, st);
-    if (op->dil == 2) return sep_launch_t<1, 2, false>(op, g, pw_bias, st);
-    return sep_launch_t<1, 4, false>(op, g, pw_bias, st);
+    if (op->stride == 2) return sep_launch_cl<2, 1>(op, g, pw_bias, st);
+    if (g.half) return sep_launch_t<1, 1, true, 1>(op, g, pw_bias, st);
+    if (op->dil == 1) return sep_launch_cl<1, 1>(op, g, pw_bias, st);
+    if (op->dil == 2) return sep_launch_cl<1, 2>(op, g, pw_bias, st);
+    return sep_launch_cl<1, 4>(op, g, pw_bias, st);
 }
 
 void sep_describe(const SepOp *op, char *out, size_t cap) {
     if (op->warp_kind) {
         SepWarpOp w;
-        if (sepwarp_prepare(&w, reinterpret_cast<const void *>(uintptr_t(1024)), op->n, op->h, op->w, op->k, op->nc) == PN_OK)
-            sepwarp_describe(&w, out, cap);
-        else
-            snprintf(out, cap, "warp-autonomous (geometry unavailable)");
+        if (sepwarp_geometry(&w, op->n, op->h, op->w, op->k, op->nc) == PN_OK) sepwarp_describe(&w, out, cap);
+        else snprintf(out, cap, "warp-autonomous (geometry unavailable)");
         return;
     }
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    snprintf(out, cap, "%stile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d stages p%d w%d a%d stg%d smem %d tiles %lld",
-             g.half ? "half " : "", g.th, g.tw, g.subs, g.thi, g.twi, g.segs_per_sub, g.seg_rows, g.n_tile, g.n_halves, g.n_half, g.n_tiles, g.kblocks, g.p_stages,
+    snprintf(out, cap, "%s%stile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d stages p%d w%d a%d stg%d smem %d tiles %lld",
+             g.half ? "half " : "", g.cl == 2 ? "cluster2 " : g.cl == 4 ? "cluster4 " : "", g.th, g.tw, g.subs, g.thi, g.twi, g.segs_per_sub, g.seg_rows, g.n_tile, g.n_halves, g.n_half, g.n_tiles, g.kblocks, g.p_stages,
              g.w_stages, g.a_stages, g.stg_bufs, op->smem_bytes, g.tiles);
 }
 

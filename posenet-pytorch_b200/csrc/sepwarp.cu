@@ -216,7 +216,8 @@ bool sepwarp_supported(int k, int nc, int stride, int dil) {
            getenv("PN_NO_SEPWARP") == nullptr;
 }
 
-int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, int nc) {
+// strips / row blocks / item count: pure host arithmetic (no CUDA calls beyond the cached SM count)
+int sepwarp_geometry(SepWarpOp *op, int n, int h, int wd, int k, int nc) {
     PN_CHECK_ARG(n > 0 && h > 0 && wd > 0 && sepwarp_supported(k, nc, 1, 1), "pn_sepconv_block: bad narrow-block shape");
     memset(op, 0, sizeof(*op));
     SwpGeom g;
@@ -234,14 +235,18 @@ int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, i
     g.rb = ceil_div(h, (int)nq);
     g.nq = ceil_div(h, g.rb);
     g.items = (long long)n * g.strips * g.nq;
-    const uint64_t dims[4] = {(uint64_t)k, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
-    const uint64_t strides[3] = {(uint64_t)k * 2, (uint64_t)wd * k * 2, (uint64_t)h * wd * k * 2};
-    const uint32_t box[4] = {32u, (uint32_t)SWP_COLS, (uint32_t)SWP_ROWS, 1u};
-    int rc = encode_tmap(op->tmap_x, x, 2, 4, dims, strides, box, 0);
-    if (rc != PN_OK) return rc;
     static_assert(sizeof(SwpGeom) <= sizeof(op->geom), "SepWarpOp::geom too small");
     memcpy(op->geom, &g, sizeof(g));
     return PN_OK;
+}
+
+int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, int nc) {
+    int rc = sepwarp_geometry(op, n, h, wd, k, nc);
+    if (rc != PN_OK) return rc;
+    const uint64_t dims[4] = {(uint64_t)k, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)k * 2, (uint64_t)wd * k * 2, (uint64_t)h * wd * k * 2};
+    const uint32_t box[4] = {32u, (uint32_t)SWP_COLS, (uint32_t)SWP_ROWS, 1u};
+    return encode_tmap(op->tmap_x, x, 2, 4, dims, strides, box, 0);
 }
 
 int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, const void *pw_w, const float *pw_b, void *y,

@@ -101,3 +101,20 @@ def test_fused_plan_matches_unfused_plan(mid, os_, H, W, N):
     for a, b in zip(fused, unfused):
         err = float((a - b).abs().max() / b.abs().max())
         assert err < 2e-3, err
+
+
+def test_cluster_variant_opt_in():
+    """PN_SEP_CLUSTER=1: 512 / 1024-output blocks shared by a 2 / 4-CTA cluster (N split, depthwise result pushed to the peers
+    over DSMEM).  Not the default (slower than the single-CTA tile, see sepconv.cu) but kept correct: same checks, own process."""
+    import os, subprocess, sys
+    code = (
+        "import sys, torch; sys.path[:0] = [%r, %r, %r]\n"
+        "import test_gpu_sepconv as t\n"
+        "for shp in [(3, 33, 33, 512, 512, 1, 1), (2, 65, 65, 256, 512, 2, 1), (2, 33, 33, 512, 1024, 1, 1), (2, 33, 33, 1024, 1024, 1, 2)]:\n"
+        "    t.test_sepconv_block(shp)\n"
+        "print('cluster ok')\n"
+    ) % (os.path.dirname(os.path.abspath(__file__)), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "posenet-pytorch_b200"),
+         os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, PN_SEP_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "cluster ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
