@@ -116,6 +116,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (EPI == EPI_HEADS && threadIdx.x < 128) {                             // head bias (128 padded entries) -> the staging area
+        reinterpret_cast<float *>(smem_gen + STAGES * STAGE_BYTES)[threadIdx.x] = threadIdx.x < (unsigned)N ? __ldg(ep.bias + threadIdx.x) : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -215,6 +218,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     buf ^= 1;
                 }
+            } else if constexpr (EPI == EPI_HEADS) {
+                // Scatter to four fp32 NCHW tensors.  Fully unrolled over the 115 columns, so the column -> (tensor, channel)
+                // mapping, the bias offsets and the sigmoid split are compile-time; per element: one shared-memory bias read
+                // (4 per LDS.128), one add, one pointer add, one 4-byte store that the warp's 32 pixels coalesce into a
+                // 128 B line.  The accumulator is handed back as soon as its last column is in registers.
+                static_assert(BLOCK_N == 128, "heads epilogue expects one 128-column tile (115 head channels + padding)");
+                const bool valid = row < M;
+                const int img = valid ? row / ep.hw : 0, pix = valid ? row - img * ep.hw : 0;
+                const size_t hw = (size_t)ep.hw;
+                float *ph = ep.heat + (size_t)img * 17 * hw + pix, *po = ep.off + (size_t)img * 34 * hw + pix;
+                float *pf = ep.fwd + (size_t)img * 32 * hw + pix, *pb = ep.bwd + (size_t)img * 32 * hw + pix;
+#pragma unroll
+                for (int c = 0; c < BLOCK_N; c += 16) {
+                    uint32_t v[16];
+                    tc_ld16(taddr + (uint32_t)c, v);
+                    tc_ld_wait();
+                    if (c + 16 == BLOCK_N) {
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+                    float bs[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const uint4 b4 = ld_shared_v4(staging + (uint32_t)(c + j) * 4u);
+                        bs[j] = __uint_as_float(b4.x); bs[j + 1] = __uint_as_float(b4.y);
+                        bs[j + 2] = __uint_as_float(b4.z); bs[j + 3] = __uint_as_float(b4.w);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int col = c + j;                       // compile-time
+                            const float x = __uint_as_float(v[j]) + bs[j];
+                            if (col < 17) ph[(size_t)col * hw] = 1.f / (1.f + expf(-x));          // mobilenet_v1.py:158
+                            else if (col < 51) po[(size_t)(col - 17) * hw] = x;
+                            else if (col < 83) pf[(size_t)(col - 51) * hw] = x;
+                            else if (col < 115) pb[(size_t)(col - 83) * hw] = x;
+                        }
+                    }
+                }
             } else {
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N; c += 16) {
@@ -223,23 +265,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     tc_ld_wait();
                     const int col0 = n_tile * BLOCK_N + c;
                     if (row < M) {
-                        if (EPI == EPI_RELU6) {
-                            const float4 *bp = reinterpret_cast<const float4 *>(ep.bias + col0);
-                            uint32_t packed[8];
+                        const float4 *bp = reinterpret_cast<const float4 *>(ep.bias + col0);
+                        uint32_t packed[8];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 b = __ldg(bp + j);
-                                packed[2 * j] = relu6_bf16x2(__uint_as_float(v[4 * j + 0]) + b.x, __uint_as_float(v[4 * j + 1]) + b.y);
-                                packed[2 * j + 1] = relu6_bf16x2(__uint_as_float(v[4 * j + 2]) + b.z, __uint_as_float(v[4 * j + 3]) + b.w);
-                            }
-                            uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(ep.y) + (size_t)row * N + col0);
-                            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                store_head(ep, row, col0 + j, __uint_as_float(v[j]) + __ldg(ep.bias + col0 + j));
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b = __ldg(bp + j);
+                            packed[2 * j] = relu6_bf16x2(__uint_as_float(v[4 * j + 0]) + b.x, __uint_as_float(v[4 * j + 1]) + b.y);
+                            packed[2 * j + 1] = relu6_bf16x2(__uint_as_float(v[4 * j + 2]) + b.z, __uint_as_float(v[4 * j + 3]) + b.w);
                         }
+                        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(ep.y) + (size_t)row * N + col0);
+                        dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
                     }
                 }
                 tc_fence_before();
@@ -315,9 +351,12 @@ static int launch_tc(const GemmTc *g, const EpiParams &ep, cudaStream_t st) {
 }
 
 int gemm_tc_launch(const GemmTc *g, const EpiParams &ep, cudaStream_t st) {
+    if (g->epi == EPI_HEADS) {                                               // the heads are one 128-column tile (115 + padding)
+        PN_CHECK_ARG(g->block_n == 128 && g->n == 128, "pn_heads_gemm: expected %d packed head rows", PN_HEAD_ROWS);
+        return launch_tc<128, EPI_HEADS>(g, ep, st);
+    }
 #define PN_TC_CASE(BN)                                                       \
-    if (g->block_n == BN)                                                    \
-        return g->epi == EPI_RELU6 ? launch_tc<BN, EPI_RELU6>(g, ep, st) : launch_tc<BN, EPI_HEADS>(g, ep, st);
+    if (g->block_n == BN) return launch_tc<BN, EPI_RELU6>(g, ep, st);
     PN_TC_CASE(256)
     PN_TC_CASE(192)
     PN_TC_CASE(128)
