@@ -183,6 +183,14 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
     double *out_kc = a.kp_coords + (size_t)img * P * PN_NUM_PARTS * 2;
     double *out_ko = a.kp_offsets + (size_t)img * P * PN_NUM_PARTS * 2;
 
+#ifdef PN_DEC_TRACE
+    long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tr_t = clock64();
+    int tr_rounds = 0, tr_slots = 0;
+#define DEC_STAMP(i) do { const long long now_ = clock64(); tr[i] += now_ - tr_t; tr_t = now_; } while (0)
+#else
+#define DEC_STAMP(i) do { } while (0)
+#endif
     uint64_t lo = 0;            // every key consumed so far is <= lo (real keys are never 0)
     int remaining = n;
     int npose = 0;
@@ -232,6 +240,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
                 bits += 8;
             }
         }
+        DEC_STAMP(0);
         // ---- 2. gather (lo, pivot] into shared memory and sort ascending (bitonic)
         if (tid == 0) S.cnt = 0;
         __syncthreads();
@@ -241,23 +250,41 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
         }
         __syncthreads();
         const int cnt = S.cnt;
-        int m = 2;
-        while (m < cnt) m <<= 1;
-        for (int i = cnt + tid; i < m; i += DEC_THREADS) S.keys[i] = ~0ull;
-        __syncthreads();
-        for (int k = 2; k <= m; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < m; i += DEC_THREADS) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const uint64_t x = S.keys[i], y = S.keys[ixj];
-                        const bool up = ((i & k) == 0);
-                        if ((x > y) == up) { S.keys[i] = y; S.keys[ixj] = x; }
+        DEC_STAMP(1);
+        if (cnt <= DEC_KBUF / 2 && cnt <= 1024) {
+            // Small chunk (the usual case: a few hundred candidates): rank sort.  Keys are unique, so the number of smaller
+            // keys IS the sorted position; every thread reads the same key at a time (a shared-memory broadcast), and the
+            // whole sort is two barriers instead of ~50 bitonic passes.
+            uint64_t *scratch = S.keys + DEC_KBUF / 2;
+            for (int i = tid; i < cnt; i += DEC_THREADS) {
+                const uint64_t k = S.keys[i];
+                int rank = 0;
+                for (int j = 0; j < cnt; ++j) rank += (S.keys[j] < k) ? 1 : 0;
+                scratch[rank] = k;
+            }
+            __syncthreads();
+            for (int i = tid; i < cnt; i += DEC_THREADS) S.keys[i] = scratch[i];
+            __syncthreads();
+        } else {
+            int m = 2;
+            while (m < cnt) m <<= 1;
+            for (int i = cnt + tid; i < m; i += DEC_THREADS) S.keys[i] = ~0ull;
+            __syncthreads();
+            for (int k = 2; k <= m; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < m; i += DEC_THREADS) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const uint64_t x = S.keys[i], y = S.keys[ixj];
+                            const bool up = ((i & k) == 0);
+                            if ((x > y) == up) { S.keys[i] = y; S.keys[ixj] = x; }
+                        }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
         }
+        DEC_STAMP(2);
         // ---- 3. greedy pass over this chunk, in rounds of up to DEC_BATCH speculatively decoded candidates
         int ci = 0;
         while (ci < cnt && npose < P) {
@@ -301,6 +328,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
                 nb = min(total, DEC_BATCH);
                 __syncthreads();
             }
+            DEC_STAMP(3);
             // (b) one thread per slot: decode.py:131-182 on its own record
             if (tid < nb) {
                 const int s = tid;
@@ -327,6 +355,10 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
                 }
             }
             __syncthreads();
+            DEC_STAMP(4);
+#ifdef PN_DEC_TRACE
+            ++tr_rounds; tr_slots += nb;
+#endif
             // (c) warp 0: the reference's greedy loop over the slots, in candidate order
             if (warp == 0) {
                 for (int s = 0; s < nb && npose < P; ++s) {
@@ -363,13 +395,14 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
                             if (npose < DEC_ACC) { S.acc[npose][lane][0] = ky; S.acc[npose][lane][1] = kx; }
                         }
                         ++npose;
-                        __threadfence_block();
+                        if (npose > DEC_ACC) __threadfence_block();   // poses beyond the shared-memory cache are re-read from global
                     }
                     __syncwarp();
                 }
                 if (lane == 0) S.npose = npose;
             }
             __syncthreads();
+            DEC_STAMP(5);
             npose = S.npose;
             ci = next;
         }
@@ -378,6 +411,11 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
         __syncthreads();
     }
     if (tid == 0) a.pose_counts[img] = npose;
+#ifdef PN_DEC_TRACE
+    if (tid == 0 && (img == 0 || img == 7))
+        printf("decode img %d: n %d poses %d rounds %d slots %d | cycles: pivot %lld gather %lld sort %lld screen %lld spec %lld commit %lld\n", img, n,
+               npose, tr_rounds, tr_slots, tr[0], tr[1], tr[2], tr[3], tr[4], tr[5]);
+#endif
 }
 
 }  // namespace pn
