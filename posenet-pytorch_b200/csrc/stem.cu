@@ -208,6 +208,10 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         bool okx[3];
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) okx[kx] = live && ix0 + kx >= 0 && ix0 + kx < a.w;
+        const int iy0 = oy * a.stride - 1;
+        // interior pixels (all 27 taps inside the image) take a copy of the loop without the padding selects
+        const bool interior_px = live && ix0 >= 0 && ix0 + 2 < a.w && iy0 >= 0 && iy0 + 2 < a.h;
+        auto im2col = [&](const bool interior) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = oy * a.stride - 1 + ky;
@@ -229,10 +233,13 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
                     const int i = kx * 3 + (2 - ci);                       // byte index inside the 9-byte window row
                     const uint32_t src = i < 4 ? v0 : i < 8 ? v1 : v2;
                     const uint32_t bits = __byte_perm(src, 0x4B000000u, 0x7540u + (uint32_t)(i & 3));
-                    f[(ky * 3 + kx) * 3 + ci] = ok ? __uint_as_float(bits) - 8388736.0f : -0.5f;
+                    const float val = __uint_as_float(bits) - 8388736.0f;
+                    f[(ky * 3 + kx) * 3 + ci] = (interior || ok) ? val : -0.5f;   // interior: the select folds away
                 }
             }
         }
+        };
+        if (interior_px) im2col(true); else im2col(false);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             uint32_t pk[4];
@@ -267,7 +274,6 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         tc_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
         tc_ld_wait();
         if (live) {
-            const __nv_bfloat162 lo2 = __floats2bfloat162_rn(0.f, 0.f), hi2 = __floats2bfloat162_rn(6.f, 6.f);
             uint4 *dst = reinterpret_cast<uint4 *>(a.y + (size_t)m * a.cout);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -276,9 +282,8 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int col = c * 8 + 2 * j;
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[col]) + sBias[col], __uint_as_float(v[col + 1]) + sBias[col + 1]);
-                        h2 = __hmin2(__hmax2(h2, lo2), hi2);
-                        o[j] = *reinterpret_cast<uint32_t *>(&h2);
+                        o[j] = relu6_bf16x2(fadd2(make_float2(__uint_as_float(v[col]), __uint_as_float(v[col + 1])),
+                                                  *reinterpret_cast<const float2 *>(sBias + col)));
                     }
                     dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
                 }
