@@ -61,6 +61,9 @@ __device__ __forceinline__ void swp_sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// KS_T / NT_T: compile-time k16 slices and n8 tiles of the pointwise GEMM (0 = take them from the geometry at run time); the
+// common widths get a fully unrolled tensor phase with immediate shared-memory offsets.
+template <int KS_T, int NT_T>
 __global__ void __launch_bounds__(SWP_THREADS, 1)
 sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restrict__ dw_w, const float *__restrict__ dw_b,
                const __nv_bfloat16 *__restrict__ pw_w, const float *__restrict__ pw_b, __nv_bfloat16 *__restrict__ y, const SwpGeom g) {
@@ -99,6 +102,7 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
         bias2 = ok ? *reinterpret_cast<const float2 *>(dw_b + 2 * cp) : make_float2(0.f, 0.f);
     }
     auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
+    const int ks_n = KS_T ? KS_T : g.ks, nt_n = NT_T ? NT_T : g.nt;
     const uint32_t lane_off = (uint32_t)hsel * SWP_PIX + (uint32_t)cp * 4u;
     const uint32_t a_lane_addr = sA + (uint32_t)hsel * SWP_A_STRIDE + (uint32_t)cp * 4u;                 // + (half * 8 + 2 p) rows
     const uint32_t a_ld_addr = sA + (uint32_t)(lane & 15) * SWP_A_STRIDE + (uint32_t)(lane >> 4) * 16u;    // ldmatrix row / k-chunk
@@ -172,19 +176,25 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
                 __syncwarp();
                 uint32_t a0[4], a1[4] = {0u, 0u, 0u, 0u};
                 ldmatrix_x4(a_ld_addr, a0);
-                if (g.ks > 1) ldmatrix_x4(a_ld_addr + 32u, a1);
-#pragma unroll 1
-                for (int nt = 0; nt < g.nt; ++nt) {
+                if (ks_n > 1) ldmatrix_x4(a_ld_addr + 32u, a1);
+                auto tile_n = [&](const int nt) {
                     uint32_t b[4];
                     ldmatrix_x4(w_ld_addr + (uint32_t)(nt * 8) * SWP_W_STRIDE, b);
                     float d[4] = {0.f, 0.f, 0.f, 0.f};
                     mma_bf16_16816(d, a0, b[0], b[1]);
-                    if (g.ks > 1) mma_bf16_16816(d, a1, b[2], b[3]);
+                    if (ks_n > 1) mma_bf16_16816(d, a1, b[2], b[3]);
                     float2 bv;
                     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bv.x), "=f"(bv.y) : "r"(sBias + (uint32_t)(nt * 8 + 2 * qq) * 4u));
                     const uint32_t o = sO + (uint32_t)gq * SWP_O_STRIDE + (uint32_t)(nt * 16 + qq * 4);
-                    swp_sts_u32(o, relu6_bf16x2(d[0] + bv.x, d[1] + bv.y));
-                    swp_sts_u32(o + 8u * SWP_O_STRIDE, relu6_bf16x2(d[2] + bv.x, d[3] + bv.y));
+                    swp_sts_u32(o, relu6_bf16x2(fadd2(make_float2(d[0], d[1]), bv)));
+                    swp_sts_u32(o + 8u * SWP_O_STRIDE, relu6_bf16x2(fadd2(make_float2(d[2], d[3]), bv)));
+                };
+                if (NT_T) {
+#pragma unroll
+                    for (int nt = 0; nt < (NT_T ? NT_T : 1); ++nt) tile_n(nt);
+                } else {
+#pragma unroll 2
+                    for (int nt = 0; nt < nt_n; ++nt) tile_n(nt);
                 }
                 __syncwarp();
                 // 16-byte coalesced stores: 8 lanes cover one pixel's channels, 4 pixels per instruction
@@ -193,7 +203,7 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
                 for (int i = 0; i < 4; ++i) {
                     const int row = i * 4 + (lane >> 3), ch = lane & 7;   // staging row = (output row parity) * 8 + pixel
                     const int tt = t_first + (row >> 3), px = row & 7;
-                    if (ch < g.nt && tt <= t && px < ncol_ok) {
+                    if (ch < nt_n && tt <= t && px < ncol_ok) {
                         const uint4 v = ld_shared_v4(sO + (uint32_t)row * SWP_O_STRIDE + (uint32_t)ch * 16u);
                         *reinterpret_cast<uint4 *>(y + ((((size_t)img * g.h + (y0 + tt)) * g.w + (x0 + px)) * g.nc + ch * 8)) = v;
                     }
@@ -256,17 +266,23 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
                  "pn_sepconv_block: misaligned pointer");
     SwpGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    static bool configured = false;
-    if (!configured) {
-        PN_CHECK_CUDA(cudaFuncSetAttribute(sepwarp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWP_SMEM));
-        configured = true;
-    }
     const long long ctas = (g.items + SWP_WARPS - 1) / SWP_WARPS;
     const int grid = (int)(ctas < num_sms() ? ctas : num_sms());
-    sepwarp_kernel<<<grid, SWP_THREADS, SWP_SMEM, st>>>(*reinterpret_cast<const CUtensorMap *>(op->tmap_x), dw_w, dw_b,
-                                                         (const __nv_bfloat16 *)pw_w, pw_b, (__nv_bfloat16 *)y, g);
-    PN_CHECK_LAUNCH();
-    return PN_OK;
+    auto launch = [&](auto kern, bool &configured) -> int {
+        if (!configured) {
+            PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SWP_SMEM));
+            configured = true;
+        }
+        kern<<<grid, SWP_THREADS, SWP_SMEM, st>>>(*reinterpret_cast<const CUtensorMap *>(op->tmap_x), dw_w, dw_b, (const __nv_bfloat16 *)pw_w, pw_b,
+                                                   (__nv_bfloat16 *)y, g);
+        PN_CHECK_LAUNCH();
+        return PN_OK;
+    };
+    static bool c28 = false, c26 = false, c14 = false, c00 = false;
+    if (g.ks == 2 && g.nt == 8) return launch(sepwarp_kernel<2, 8>, c28);      // 32 -> 64 (model 100 / 101)
+    if (g.ks == 2 && g.nt == 6) return launch(sepwarp_kernel<2, 6>, c26);      // 24 -> 48 (model 75)
+    if (g.ks == 1 && g.nt == 4) return launch(sepwarp_kernel<1, 4>, c14);      // 16 -> 32 (model 50)
+    return launch(sepwarp_kernel<0, 0>, c00);
 }
 
 void sepwarp_describe(const SepWarpOp *op, char *out, size_t cap) {
