@@ -147,7 +147,7 @@ struct SepOp {
     alignas(64) unsigned char tmap_dwb[128];
     alignas(64) unsigned char tmap_w[128];
     alignas(64) unsigned char tmap_y[128];
-    alignas(8) unsigned char geom[256];
+    alignas(8) unsigned char geom[640];
     int smem_bytes, cb, stride, dil, ho, wo, n, h, w, k, nc;
     // narrow blocks run the warp-autonomous kernel instead (warp_kind): it takes plain pointers, kept here for the launch
     bool warp_kind;

@@ -48,6 +48,7 @@ struct SepGeom {
     int k, nc, ho, wo, pad;
     int th, tw, subs, ths, thi, twi;      // output tile, sub-tiles (rows per sub), input box
     int spr, seg_rows, segs_per_sub;      // 4-pixel column strips per tile row; rows per segment; segments per sub-tile
+    unsigned segtab[64];                  // per segment: strip column | first output row << 8 | rows << 16 (rows are RSTEP apart)
     int tiles_x, tiles_y, n_tiles, n_tile, panels, tmem_cols;
     int n_halves, n_half, acc_bufs;       // a tile's accumulator = n_halves UMMA column blocks of n_half (<= 256) columns
     int kblocks;
@@ -127,17 +128,21 @@ __device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool on) {
 }
 
 // Register window of the depthwise stencil for a strip of 4 output pixels: output row t reads input rows
-// t*S + ky*D.  Sliding (D == 1): a ring of NR = 2D+1 rows, S new rows per step, PRE rows preloaded; otherwise the
-// three rows are loaded afresh each step.
+// t*S + ky*D.  The window slides: a ring of NR rows, S new rows per step, PRE rows preloaded.  With dilation D > 1
+// (stride 1) a segment walks the output rows of ONE residue class mod D (t, t+D, t+2D, ...): in that row space the
+// stencil is dense again (rows t, t+D, t+2D -> one new row per step), so RSTEP = D scales the row pitch and the
+// ring logic is the dilation-1 one (DR = 1).
 // HALF (K <= 32 channels): lanes 0-15 own the even pixels of an 8-pixel strip, lanes 16-31 the odd ones, i.e. each lane
 // walks 4 pixels that are HS = 2 S input columns apart -- no lane idles on zero-filled channels.
 template <int S, int D, bool HALF> struct SepDwCfg {
-    static constexpr bool SLIDE = (D == 1);
-    static constexpr bool UNPACKED = (D == 1);       // window kept as fp32 pairs (18-27 pairs); wider windows stay packed
-    static constexpr int NR = SLIDE ? 2 * D + 1 : 3;
+    static constexpr bool SLIDE = true;
+    static constexpr int RSTEP = (S == 1) ? D : 1;   // output / input row stride of a segment
+    static constexpr int DR = (S == 1) ? 1 : D;      // row dilation in the segment's row space
+    static constexpr bool UNPACKED = (D <= 2);       // window kept as fp32 pairs (18-27 pairs); wider windows stay packed
+    static constexpr int NR = 2 * DR + 1;
     static constexpr int HS = HALF ? 2 * S : S;      // input columns between a lane's consecutive output pixels
     static constexpr int NCOLS = 3 * HS + 2 * D + 1;
-    static constexpr int PRE = SLIDE ? 2 * D + 1 - S : 0;
+    static constexpr int PRE = 2 * DR + 1 - S;
 };
 
 
@@ -216,11 +221,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     {   // depthwise segment table (strip column | first row << 8 | rows << 16) and the hand-out counter
         uint32_t *misc = reinterpret_cast<uint32_t *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bar);
         if (threadIdx.x < 8) misc[SepBars::seg_ctr / 4 + threadIdx.x] = 0u;
-        if ((int)threadIdx.x < g.segs_per_sub) {
-            const int seg = threadIdx.x, cs = seg % g.spr, rs = seg / g.spr;
-            const int r0 = rs * g.seg_rows;
-            misc[SepBars::seg_tab / 4 + seg] = (uint32_t)(cs * (HALF ? 8 : 4)) | (uint32_t)r0 << 8 | (uint32_t)min(g.seg_rows, g.ths - r0) << 16;
-        }
+        if ((int)threadIdx.x < g.segs_per_sub) misc[SepBars::seg_tab / 4 + threadIdx.x] = g.segtab[threadIdx.x];
     }
     {   // pointwise bias -> shared memory once (the epilogue reads it per panel)
         float *sbias = reinterpret_cast<float *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bias);
@@ -438,12 +439,12 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         // is one conflict-free 128 B wavefront per warp.  Items are handed out in order, so a warp that finishes early
         // simply starts on the next item's patch (if it has landed) while the others complete the current A stage.
         using Cfg = SepDwCfg<S, D, HALF>;
-        constexpr int NR = Cfg::NR, NCOLS = Cfg::NCOLS, PRE = Cfg::PRE, HS = Cfg::HS;
+        constexpr int NR = Cfg::NR, NCOLS = Cfg::NCOLS, PRE = Cfg::PRE, HS = Cfg::HS, RSTEP = Cfg::RSTEP, DR = Cfg::DR;
         constexpr bool SLIDE = Cfg::SLIDE, UNPACKED = Cfg::UNPACKED, PREFETCH = Cfg::UNPACKED;
-        constexpr int NNEW = SLIDE ? S : 3;                          // input rows loaded per step
+        constexpr int NNEW = S;                                      // input rows loaded per step
         constexpr uint32_t PIX = HALF ? 64u : 128u;                  // bytes per patch pixel
         const int hsel = HALF ? (lane >> 4) : 0, cp = HALF ? (lane & 15) : lane;
-        const uint32_t rowb = (uint32_t)g.twi * PIX;
+        const uint32_t rowb1 = (uint32_t)g.twi * PIX, rowb = rowb1 * RSTEP;      // patch row pitch; pitch between a segment's rows
         const uint32_t lane_off = (uint32_t)(hsel * S) * PIX + (uint32_t)cp * 4u;
         const uint32_t a_lane = (uint32_t)(cp >> 2) << 4 | (uint32_t)(cp & 3) << 2;       // 16 B chunk | byte inside it
         auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
@@ -488,9 +489,9 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 const uint32_t tab = lds_u32(tab_addr + (uint32_t)seg * 4u);
                 const int s_col = (int)(tab & 0xffu), s_r0 = (int)((tab >> 8) & 0xffu), s_n = (int)(tab >> 16);
                 const int orow0 = sub * g.ths + s_r0;
-                const int nrows = min(s_n, g.th - orow0);                       // rows of this segment inside the tile
+                const int nrows = min(s_n, (g.th - orow0 + RSTEP - 1) / RSTEP);     // rows of this segment inside the tile
                 if (nrows > 0) {
-                    const uint32_t src = stage + (uint32_t)(s_r0 * S) * rowb + (uint32_t)(s_col * S) * PIX + lane_off;
+                    const uint32_t src = stage + (uint32_t)(s_r0 * S) * rowb1 + (uint32_t)(s_col * S) * PIX + lane_off;
                     const int ncol_ok = g.tw - s_col;                               // strip pixels px < ncol_ok exist
                     int arow = orow0 * g.tw + s_col;                                // A-tile row == TMEM lane == staging row
 
@@ -539,8 +540,8 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                             } else {
     #pragma unroll
                                 for (int n = 0; n < NNEW; ++n) {
-                                    const int slot = SLIDE ? (PRE + j * S + n) % NR : n;
-                                    const uint32_t rp = src + (uint32_t)(SLIDE ? PRE + t * S + n : t * S + n * D) * rowb;
+                                    const int slot = (PRE + j * S + n) % NR;
+                                    const uint32_t rp = src + (uint32_t)(PRE + t * S + n) * rowb;
     #pragma unroll
                                     for (int c = 0; c < NCOLS; ++c) ringp[slot][c] = lds_u32(rp + (uint32_t)c * PIX);
                                 }
@@ -548,7 +549,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                             float2 acc[4] = {bias2, bias2, bias2, bias2};
     #pragma unroll
                             for (int ky = 0; ky < 3; ++ky) {
-                                const int slot = SLIDE ? (j * S + ky * D) % NR : ky;
+                                const int slot = (j * S + ky * DR) % NR;
     #pragma unroll
                                 for (int c = 0; c < NCOLS; ++c) {
                                     const float2 v = UNPACKED ? ringf[slot][c] : unpack(ringp[slot][c]);
@@ -565,7 +566,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                 const uint32_t r = (uint32_t)(arow + px);
                                 sts_u32_if(a_stage + ((r << 7) | a_lane) ^ ((r & 7u) << 4), relu6_bf16x2(acc[p]), px < ncol_ok);
                             }
-                            arow += g.tw;
+                            arow += g.tw * RSTEP;
                         }
                     }
                 }
@@ -692,12 +693,16 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
                 // segments: 4-pixel (8 when half) column strips x seg_rows rows.  They are handed out dynamically across
                 // the items in flight (A stages x segments >= 16 keeps the 10 warps busy); ~4-5 rows amortise the window preload
                 const int spr = ceil_div(tw, sw);
-                int pieces = ceil_div(ths, 5);
-                if (pieces * spr * subs < 8) pieces = ceil_div(8, spr * subs);   // >= 16 segments in flight with 2 A stages
-                if (pieces > ths) pieces = ths;
-                const int seg_rows = ceil_div(ths, pieces);
-                const int segs = spr * ceil_div(ths, seg_rows);
-                if (segs > 64 || seg_rows > 255 || tw > 255) continue;
+                // (dilated blocks: a segment walks one residue class of rows, ths / dil rows per class)
+                const int rstep = stride == 1 ? dil : 1;
+                const int class_rows = ceil_div(ths, rstep);
+                int pieces = ceil_div(class_rows, 5);                                // row chunks per class
+                if (pieces * spr * subs * rstep < 8) pieces = ceil_div(8, spr * subs * rstep);   // >= 16 segments in flight with 2 A stages
+                if (pieces > class_rows) pieces = class_rows;
+                const int seg_rows = ceil_div(class_rows, pieces);
+                int segs = 0;
+                for (int c = 0; c < rstep && c < ths; ++c) segs += spr * ceil_div(ceil_div(ths - c, rstep), seg_rows);
+                if (segs > 64 || seg_rows > 255 || tw > 255 || ths > 255) continue;
                 const long long room = SEP_SMEM_MAX - fixed;
                 const int pst = (int)(room / stage);
                 if (pst < 2 || pst < subs + 1) continue;
@@ -708,7 +713,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
                 // Tensor pipe: 2 cycles per output column.  Patch fill at ~40 B/clk.
                 const double step = 45.0 + 10.0 * ncols * (slide ? (stride + 2.0) / 3.0 : 1.0), prol = 1.3 * pre * ncols + 120.0;
                 const double lat = 0.5 * (seg_rows * step + prol) * 1.6;
-                const double issue = 1.25 * (double)subs * (spr * (ths * step + ceil_div(ths, seg_rows) * prol)) / 4.0;
+                const double issue = 1.25 * (double)subs * (spr * ths * step + segs * prol) / 4.0;
                 const double dwc = lat > issue ? lat : issue;
                 const double mma = 2.0 * g.n_tile;                          // per k-block, all column blocks
                 const double fill = (double)subs * stage / 40.0;
@@ -730,6 +735,19 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
         }
     }
     PN_CHECK_ARG(best < 1e300, "pn_sepconv_block: no tile shape fits (cin %d stride %d dilation %d)", k, stride, dil);
+    {   // segment table: strips x residue classes x row chunks
+        const int rstep = stride == 1 ? dil : 1;
+        int nseg = 0;
+        for (int c = 0; c < rstep && c < g.ths; ++c) {
+            const int rows_c = ceil_div(g.ths - c, rstep);
+            for (int r = 0; r < rows_c; r += g.seg_rows)
+                for (int cs = 0; cs < g.spr; ++cs) {
+                    const int nrow = rows_c - r < g.seg_rows ? rows_c - r : g.seg_rows;
+                    g.segtab[nseg++] = (unsigned)(cs * sw) | (unsigned)(c + r * rstep) << 8 | (unsigned)nrow << 16;
+                }
+        }
+        PN_CHECK_ARG(nseg == g.segs_per_sub, "pn_sepconv_block: internal segment accounting error (%d vs %d)", nseg, g.segs_per_sub);
+    }
     g.tiles_x = ceil_div(g.wo, g.tw);
     g.tiles_y = ceil_div(g.ho, g.th);
     g.tiles = (long long)n * g.tiles_x * g.tiles_y * g.n_tiles;       // cluster: m tiles (one cluster covers all columns)
