@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 2
+#define PN_ABI_VERSION 3
 
 typedef void *pn_stream_t; /* cudaStream_t */
 
@@ -49,6 +49,11 @@ int pn_device_check(void);
  * src: uint8 [n, src_h, src_w, 3] BGR HWC.  dst: f32 [n, 3, dst_h, dst_w] RGB NCHW.  Bit-exact with cv2. */
 int pn_preprocess_u8(const uint8_t *src, int n, int src_h, int src_w, int dst_h, int dst_w,
                      float *dst, pn_stream_t stream);
+/* The resize stage of P1 alone (utils.py:21, cv2.resize INTER_LINEAR on uint8, bit-exact): uint8 [n, src_h, src_w, 3]
+ * -> uint8 [n, dst_h, dst_w, 3], still BGR HWC -- the input format of pn_stem_conv_u8 / a uint8 plan, so frames of any
+ * size (utils.py:51-55 read_cap at 1280x720) reach the uint8 fast path without a float round trip. */
+int pn_resize_u8(const uint8_t *src, int n, int src_h, int src_w, int dst_h, int dst_w, uint8_t *dst,
+                 pn_stream_t stream);
 
 /* ---- B2: posenet/models/mobilenet_v1.py:47-54 (InputConv: relu6(conv3x3(x, stride, pad 1) + b), 3 -> cout)
  * x: f32 NCHW [n,3,h,w].  w: f32 [27, cout], row = (ky*3+kx)*3+ci.  y: NHWC [n,ho,wo,cout] of out_dtype. */

@@ -85,6 +85,10 @@ int pn_preprocess_u8(const uint8_t *src, int n, int src_h, int src_w, int dst_h,
     return launch_preprocess(src, n, src_h, src_w, dst_h, dst_w, dst, as_stream(stream));
 }
 
+int pn_resize_u8(const uint8_t *src, int n, int src_h, int src_w, int dst_h, int dst_w, uint8_t *dst, pn_stream_t stream) {
+    return launch_resize_u8(src, n, src_h, src_w, dst_h, dst_w, dst, as_stream(stream));
+}
+
 int pn_stem_conv(const float *x, const float *w, const float *bias, void *y, int n, int h, int wd, int cout,
                  int stride, int out_dtype, pn_stream_t stream) {
     return launch_stem(x, false, w, bias, y, n, h, wd, cout, stride, out_dtype, as_stream(stream));

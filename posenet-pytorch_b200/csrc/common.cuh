@@ -101,6 +101,7 @@ template <> struct Vec8<__nv_bfloat16> {
 
 // ---- launchers implemented one per .cu file ----------------------------------------------------
 int launch_preprocess(const uint8_t *src, int n, int sh, int sw, int dh, int dw, float *dst, cudaStream_t s);
+int launch_resize_u8(const uint8_t *src, int n, int sh, int sw, int dh, int dw, uint8_t *dst, cudaStream_t s);
 int launch_stem(const void *x, bool x_is_u8, const float *w, const float *b, void *y, int n, int h, int wd,
                 int cout, int stride, int out_dtype, cudaStream_t s);
 int launch_dwconv(const void *x, const float *w, const float *b, void *y, int n, int h, int wd, int c,

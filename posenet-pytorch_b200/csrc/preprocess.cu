@@ -22,8 +22,10 @@ __device__ __forceinline__ float normalise(int v) {
     return __fsub_rn(__fmul_rn((float)v, (float)(2.0 / 255.0)), 1.0f);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t *__restrict__ src, float *__restrict__ dst,
+// OUT_U8: stop after the resize and keep uint8 BGR HWC (the tensor-core stem consumes that and normalises itself), so
+// frames of any size can feed the uint8 fast path; otherwise the reference's normalised f32 RGB NCHW tensor.
+template <int MODE, bool OUT_U8>
+__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t *__restrict__ src, void *__restrict__ dst_,
                                                           int sh, int sw, int dh, int dw, double scale_x,
                                                           double scale_y) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -65,28 +67,41 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t *__restri
             bgr[c] = min(max(v, 0), 255);
         }
     }
+    if (OUT_U8) {
+        uint8_t *o8 = reinterpret_cast<uint8_t *>(dst_) + (((size_t)img * dh + y) * dw + x) * 3;
+        o8[0] = (uint8_t)bgr[0]; o8[1] = (uint8_t)bgr[1]; o8[2] = (uint8_t)bgr[2];
+        return;
+    }
     const size_t plane = (size_t)dh * dw;
-    float *o = dst + (size_t)img * 3 * plane + (size_t)y * dw + x;
+    float *o = reinterpret_cast<float *>(dst_) + (size_t)img * 3 * plane + (size_t)y * dw + x;
     o[0] = normalise(bgr[2]);          // utils.py:22 BGR -> RGB
     o[plane] = normalise(bgr[1]);
     o[2 * plane] = normalise(bgr[0]);
 }
 
-int launch_preprocess(const uint8_t *src, int n, int sh, int sw, int dh, int dw, float *dst, cudaStream_t st) {
-    PN_CHECK_ARG(src && dst && n > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0, "pn_preprocess_u8: bad argument");
-    PN_CHECK_ARG(dh <= 65535 && n <= 65535, "pn_preprocess_u8: dst_h and n must be <= 65535");
+template <bool OUT_U8>
+static int launch_preprocess_t(const uint8_t *src, int n, int sh, int sw, int dh, int dw, void *dst, cudaStream_t st, const char *who) {
+    PN_CHECK_ARG(src && dst && n > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0, "%s: bad argument", who);
+    PN_CHECK_ARG(dh <= 65535 && n <= 65535, "%s: dst_h and n must be <= 65535", who);
     dim3 block(256), grid(ceil_div(dw, 256), dh, n);
     // cv2: inv_scale = dsize / ssize (double); scale = 1. / inv_scale
     const double scale_x = 1.0 / ((double)dw / (double)sw);
     const double scale_y = 1.0 / ((double)dh / (double)sh);
     if (dh == sh && dw == sw)
-        preprocess_kernel<MODE_COPY><<<grid, block, 0, st>>>(src, dst, sh, sw, dh, dw, scale_x, scale_y);
+        preprocess_kernel<MODE_COPY, OUT_U8><<<grid, block, 0, st>>>(src, dst, sh, sw, dh, dw, scale_x, scale_y);
     else if (sh == 2 * dh && sw == 2 * dw)
-        preprocess_kernel<MODE_AREA2><<<grid, block, 0, st>>>(src, dst, sh, sw, dh, dw, scale_x, scale_y);
+        preprocess_kernel<MODE_AREA2, OUT_U8><<<grid, block, 0, st>>>(src, dst, sh, sw, dh, dw, scale_x, scale_y);
     else
-        preprocess_kernel<MODE_LINEAR><<<grid, block, 0, st>>>(src, dst, sh, sw, dh, dw, scale_x, scale_y);
+        preprocess_kernel<MODE_LINEAR, OUT_U8><<<grid, block, 0, st>>>(src, dst, sh, sw, dh, dw, scale_x, scale_y);
     PN_CHECK_LAUNCH();
     return PN_OK;
+}
+
+int launch_preprocess(const uint8_t *src, int n, int sh, int sw, int dh, int dw, float *dst, cudaStream_t st) {
+    return launch_preprocess_t<false>(src, n, sh, sw, dh, dw, dst, st, "pn_preprocess_u8");
+}
+int launch_resize_u8(const uint8_t *src, int n, int sh, int sw, int dh, int dw, uint8_t *dst, cudaStream_t st) {
+    return launch_preprocess_t<true>(src, n, sh, sw, dh, dw, dst, st, "pn_resize_u8");
 }
 
 }  // namespace pn

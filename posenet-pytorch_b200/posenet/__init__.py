@@ -15,4 +15,4 @@ from posenet.models.model_factory import load_model, write_random_checkpoint  # 
 from posenet.models import MobileNetV1, MOBILENET_V1_CHECKPOINTS  # noqa: F401
 from posenet.pipeline import BatchPipeline  # noqa: F401  (streaming batches: copies overlap the kernels)
 from posenet.utils import *  # noqa: F401,F403
-from posenet.utils import _process_input, process_input_gpu  # noqa: F401
+from posenet.utils import _process_input, process_input_gpu, resize_u8_gpu  # noqa: F401

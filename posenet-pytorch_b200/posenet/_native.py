@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("POSENET_B200_LIB", os.path.join(_PKG_ROOT, "lib", "li
 PN_OK = 0
 PN_F32, PN_BF16 = 0, 1
 NUM_PARTS, NUM_EDGES, HEAD_CHANNELS, HEAD_ROWS = 17, 16, 115, 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 PLAN_UNFUSED = 1
 
 
@@ -48,6 +48,7 @@ _SIGNATURES = {
     "pn_last_error_string": (C.c_char_p, []),
     "pn_device_check": (C.c_int, []),
     "pn_preprocess_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "pn_resize_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "pn_stem_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_void_p]),
     "pn_stem_conv_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

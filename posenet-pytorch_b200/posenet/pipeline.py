@@ -18,13 +18,20 @@ from posenet.decode_multi import decode_multiple_poses_batch, split_pose_records
 
 
 class BatchPipeline:
-    def __init__(self, model, batch, height, width, depth=2, use_graph=True, output_stride=None, **decode_kw):
+    def __init__(self, model, batch, height, width, depth=2, use_graph=True, output_stride=None, scale_factor=1.0, **decode_kw):
+        """``height`` x ``width``: size of the uint8 frames handed to ``submit``.  The network runs at
+        ``valid_resolution(width * scale_factor, height * scale_factor)`` (utils.py:7-10); when that differs from the frame size
+        the bit-exact cv2 resize (``pn_resize_u8``) runs on the GPU in front of the stem, inside the same graph."""
         nat.require_device()
         assert depth >= 1
         self.model, self.batch, self.h, self.w = model, int(batch), int(height), int(width)
+        from posenet.utils import valid_resolution
+        self.os = output_stride or model.output_stride
+        self.tw, self.th = valid_resolution(self.w * scale_factor, self.h * scale_factor, output_stride=self.os)
+        self.resize = (self.th, self.tw) != (self.h, self.w)
+        self.scale = np.array([self.h / self.th, self.w / self.tw])           # utils.py:19, for mapping coordinates back
         self.decode_kw = dict(decode_kw)
         self.P = int(self.decode_kw.get("max_pose_detections", 10))
-        self.os = output_stride or model.output_stride
         dev = model._device()
         self.dev = dev
         self.h2d, self.d2h, self.compute = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -33,6 +40,7 @@ class BatchPipeline:
         self._ws = {}
         for _ in range(depth):
             s = dict(x=torch.empty((self.batch, self.h, self.w, 3), dtype=torch.uint8, device=dev),
+                     xr=torch.empty((self.batch, self.th, self.tw, 3), dtype=torch.uint8, device=dev) if self.resize else None,
                      rec=torch.zeros(nrec, dtype=torch.float64, device=dev),
                      rec_host=torch.zeros(nrec, dtype=torch.float64).pin_memory(),
                      copied=torch.cuda.Event(), done=torch.cuda.Event(), out=torch.cuda.Event(), graph=None, busy=False)
@@ -56,7 +64,12 @@ class BatchPipeline:
         self._next = 0
 
     def _enqueue(self, s):
-        heads = self.model.forward_u8(s["x"])
+        x = s["x"]
+        if self.resize:
+            nat.check(nat.load().pn_resize_u8(x.data_ptr(), self.batch, self.h, self.w, self.th, self.tw, s["xr"].data_ptr(),
+                                              nat.stream_ptr()), "pn_resize_u8")
+            x = s["xr"]
+        heads = self.model.forward_u8(x)
         decode_multiple_poses_batch(*heads, output_stride=self.os, workspace=self._ws, out=s["rec"], **self.decode_kw)
 
     def submit(self, host_batch):

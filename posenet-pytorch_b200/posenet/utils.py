@@ -43,6 +43,28 @@ def process_input_gpu(source_img, scale_factor=1.0, output_stride=16, out=None):
     return out, scale
 
 
+def resize_u8_gpu(source_img, scale_factor=1.0, output_stride=16, out=None):
+    """The resize stage of ``_process_input`` alone (utils.py:21 of the reference, cv2.resize INTER_LINEAR, bit-exact):
+    uint8 BGR [h,w,3] / [N,h,w,3] -> uint8 BGR [N,th,tw,3] on the GPU, the input of ``MobileNetV1.forward_u8`` (which
+    normalises inside the stem).  Returns ``(frames uint8 cuda, scale float64[2])``."""
+    nat.require_device()
+    img = source_img if torch.is_tensor(source_img) else torch.from_numpy(np.ascontiguousarray(source_img))
+    if img.dim() == 3:
+        img = img.unsqueeze(0)
+    assert img.dim() == 4 and img.shape[3] == 3 and img.dtype == torch.uint8, "expected uint8 [h,w,3] / [N,h,w,3]"
+    n, h, w = img.shape[0], img.shape[1], img.shape[2]
+    tw, th = valid_resolution(w * scale_factor, h * scale_factor, output_stride=output_stride)
+    scale = np.array([h / th, w / tw])
+    dev = img.device if img.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    img = img.to(dev).contiguous()
+    if out is None:
+        out = torch.empty((n, th, tw, 3), dtype=torch.uint8, device=dev)
+    assert tuple(out.shape) == (n, th, tw, 3) and out.dtype == torch.uint8 and out.is_contiguous()
+    nat.check(nat.load().pn_resize_u8(C.c_void_p(img.data_ptr()), n, h, w, th, tw, C.c_void_p(out.data_ptr()), nat.stream_ptr()),
+              "pn_resize_u8")
+    return out, scale
+
+
 def _process_input(source_img, scale_factor=1.0, output_stride=16):
     x, scale = process_input_gpu(source_img, scale_factor, output_stride)
     return x.cpu().numpy(), source_img, scale

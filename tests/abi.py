@@ -22,6 +22,13 @@ def preprocess(img_u8, th, tw):
     return out
 
 
+def resize_u8(img_u8, th, tw):
+    n, h, w, _ = img_u8.shape
+    out = torch.empty((n, th, tw, 3), dtype=torch.uint8, device=img_u8.device)
+    nat.check(nat.load().pn_resize_u8(P(img_u8), n, h, w, th, tw, P(out), nat.stream_ptr()), "pn_resize_u8")
+    return out
+
+
 def stem(x, w27, b, stride, dtype, u8=False):
     lib = nat.load()
     if u8:

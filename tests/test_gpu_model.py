@@ -152,3 +152,24 @@ def test_batch_pipeline_matches_direct_calls():
     again = list(pipe2.run(batches[:2]))
     for a, b in zip(again, got[:2]):
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_batch_pipeline_resizes_webcam_frames():
+    """Frames that are not at a valid resolution (the reference's read_cap path, utils.py:51-55: 1280x720 -> 721x1281 at
+    OS8) go through pn_resize_u8 inside the pipeline's graph: same records as resize_u8_gpu + forward_u8 + decode."""
+    sd = onet.init_params(50, seed=9, scheme="scaled", gain=0.8)
+    m = build(50, 8, sd, "bf16")
+    N, H, W = 2, 180, 320                                   # 16:9 like 720p, small: -> 177 x 321 at OS8
+    frames = [torch.from_numpy(np.stack([synth.smooth_image(H, W, 3 * b + i) for i in range(N)])).pin_memory() for b in range(3)]
+    kw = dict(max_pose_detections=5, min_pose_score=0.1)
+    pipe = posenet.BatchPipeline(m, N, H, W, depth=2, output_stride=8, **kw)
+    assert pipe.resize and (pipe.th, pipe.tw) == (177, 321)
+    got = list(pipe.run(frames))
+    for hb, rec in zip(frames, got):
+        x, scale = posenet.resize_u8_gpu(hb, 1.0, 8)
+        assert tuple(x.shape) == (N, 177, 321, 3) and np.allclose(scale, pipe.scale)
+        for i in range(N):                                  # the resize is the oracle's (cv2's), bit for bit
+            assert np.array_equal(x[i].cpu().numpy(), opre.resize_linear_u8(hb[i].numpy(), 321, 177))
+        ref = posenet.decode_multiple_poses_batch(*m.forward_u8(x), output_stride=8, **kw)[:4]
+        for a, b in zip(rec, ref):
+            assert np.array_equal(a, b.cpu().numpy())

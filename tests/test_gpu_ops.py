@@ -38,6 +38,18 @@ def test_preprocess_bit_exact(golden_dir, i):
     assert hashlib.sha256(out.tobytes()).hexdigest() == str(g["sha_%d" % i])
 
 
+@pytest.mark.parametrize("i", range(len(PRE_CASES)))
+def test_resize_u8_bit_exact(i):
+    """pn_resize_u8 = the resize stage of P1 alone (cv2.resize INTER_LINEAR on uint8, utils.py:21), uint8 in / uint8 out."""
+    h, w, sf, os_, seed, _ = PRE_CASES[i]
+    img = synth.noise_image(h, w, seed)
+    tw, th = opre.valid_resolution(w * sf, h * sf, os_)
+    ref = opre.resize_linear_u8(img, tw, th)
+    out = abi.resize_u8(torch.from_numpy(np.stack([img, img[::-1].copy()])).to(DEV), th, tw).cpu().numpy()
+    assert np.array_equal(out[0], ref)
+    assert np.array_equal(out[1], opre.resize_linear_u8(img[::-1].copy(), tw, th))
+
+
 def test_preprocess_batch():
     imgs = np.stack([synth.noise_image(120, 200, s) for s in range(3)])
     tw, th = opre.valid_resolution(200 * 0.8, 120 * 0.8, 8)

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = nat.load()                                       # raises if missing / symbol absent / ABI mismatch
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.pn_abi_version() == nat.ABI_VERSION == 2
+    assert lib.pn_abi_version() == nat.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
