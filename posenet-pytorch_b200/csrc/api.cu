@@ -20,6 +20,12 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) on = getenv("PN_NO_PDL") == nullptr ? 1 : 0;
+    return on == 1;
+}
+
 int num_sms() {
     static int sms = 0;
     if (!sms) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/posenet_b200.h"
 
@@ -32,6 +33,23 @@ void set_error(const char *fmt, ...);
 #define PN_CHECK_LAUNCH() PN_CHECK_CUDA(cudaGetLastError())
 
 inline cudaStream_t as_stream(pn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Kernel launch with programmatic stream serialization (PDL): the persistent kernels of consecutive layers overlap the
+// prologue of layer i+1 (barrier init, TMEM allocation, weight staging) with the tail of layer i.  Every kernel launched
+// this way executes griddepcontrol.wait (pdl_wait, ptx.cuh) before it touches activations.  PN_NO_PDL=1 disables it.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int num_sms();
 

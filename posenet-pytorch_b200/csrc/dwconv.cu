@@ -104,7 +104,9 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restr
         }
         mbar_fence_init();
     }
+    pdl_launch_dependents();
     __syncthreads();
+    pdl_wait();                                           // (ptx.cuh) the previous layer has completed
 
     if (warp == DW_CONSUMER_WARPS) {
         // ===================== TMA producer =====================
@@ -327,8 +329,7 @@ static int launch_tma(const DwOp *op, const DwGeom &g, const float *w, const flo
     const int smem = 256 + g.stages * (int)g.stage_bytes;
     const long long max_ctas = num_sms();
     const int grid = (int)(g.items < max_ctas ? g.items : max_ctas);
-    kern<<<grid, DW_THREADS, smem, st>>>(*reinterpret_cast<const CUtensorMap *>(op->tmap), w, b, (T *)y, g);
-    PN_CHECK_LAUNCH();
+    PN_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(DW_THREADS), (size_t)smem, st, *reinterpret_cast<const CUtensorMap *>(op->tmap), w, b, (T *)y, g));
     return PN_OK;
 }
 

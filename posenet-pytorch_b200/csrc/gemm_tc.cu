@@ -119,10 +119,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (EPI == EPI_HEADS && threadIdx.x < 128) {                             // head bias (128 padded entries) -> the staging area
         reinterpret_cast<float *>(smem_gen + STAGES * STAGE_BYTES)[threadIdx.x] = threadIdx.x < (unsigned)N ? __ldg(ep.bias + threadIdx.x) : 0.f;
     }
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                                                              // (ptx.cuh) the previous layer has completed
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -343,10 +345,9 @@ static int launch_tc(const GemmTc *g, const EpiParams &ep, cudaStream_t st) {
     }
     const int tiles = ceil_div(g->m, TC_BLOCK_M) * (g->n / BLOCK_N);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, TC_THREADS, smem, st>>>(*reinterpret_cast<const CUtensorMap *>(g->tmap_a),
-                                         *reinterpret_cast<const CUtensorMap *>(g->tmap_b),
-                                         *reinterpret_cast<const CUtensorMap *>(g->tmap_c), ep, g->m, g->n, g->k);
-    PN_CHECK_LAUNCH();
+    PN_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(TC_THREADS), (size_t)smem, st, *reinterpret_cast<const CUtensorMap *>(g->tmap_a),
+                             *reinterpret_cast<const CUtensorMap *>(g->tmap_b), *reinterpret_cast<const CUtensorMap *>(g->tmap_c), ep, g->m,
+                             g->n, g->k));
     return PN_OK;
 }
 

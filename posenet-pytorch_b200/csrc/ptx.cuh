@@ -158,6 +158,13 @@ __device__ __forceinline__ uint32_t relu6_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ uint32_t relu6_bf16x2(float2 v) { return relu6_bf16x2(v.x, v.y); }
 
+// ---- programmatic dependent launch: a kernel launched with launch_pdl (common.cuh) may run its prologue while its
+// predecessor in the stream drains; pdl_wait() blocks until the predecessor has completed and its memory is visible, so it
+// goes before the first access to anything the predecessor writes or reads.  pdl_launch_dependents() lets the successor do
+// the same with this kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- host: tensor-map encoding (implemented in tmap.cu) ----------------------------------------------
 // rank <= 4; dims/box innermost first; strides_bytes[rank-1] are the byte strides of dims 1..rank-1.
 // esize 2 -> bf16, 4 -> fp32.  swizzle: 0 none, 1 32B, 2 64B, 3 128B.  OOB elements read as zero.

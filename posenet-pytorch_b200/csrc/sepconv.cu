@@ -228,10 +228,12 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const int ncp = g.n_tiles * g.panels * 64;                // padded so that ragged panels read zeros
         for (int i = threadIdx.x; i < ncp; i += SEP_THREADS) sbias[i] = col_base + i < g.nc ? __ldg(pw_bias + col_base + i) : 0.f;
     }
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     if (CLUSTER) cluster_sync_all();                          // the peers' barriers exist before anything remote targets them
     tc_fence_after();
+    pdl_wait();                                               // everything above overlapped the previous layer's tail
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
@@ -858,13 +860,18 @@ static int sep_launch_t(const SepOp *op, const SepGeom &g, const float *pw_bias,
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    if (CL > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    } else {                                                      // PDL (common.cuh: launch_pdl) for the single-CTA variant
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+    }
     cfg.blockDim = dim3(SEP_THREADS, 1, 1);
     cfg.dynamicSmemBytes = (size_t)op->smem_bytes;
     cfg.stream = st;
     cfg.attrs = attr;
-    cfg.numAttrs = CL > 1 ? 1 : 0;
+    cfg.numAttrs = (CL > 1 || pdl_enabled()) ? 1 : 0;
     if (!configured) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SEP_SMEM_MAX));
         if (CL > 1) {                                             // how many clusters fit at once (GPC boundaries cost a few SMs)

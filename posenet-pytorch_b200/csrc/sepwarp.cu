@@ -90,7 +90,9 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
         mbar_fence_init();
         if (warp == 0) tma_prefetch_desc(&tmap_x);
     }
+    pdl_launch_dependents();
     __syncthreads();
+    pdl_wait();                                                           // the weight staging above overlapped the stem's tail
 
     // ---- per lane: pixel parity, channel pair, the 9 x 2 depthwise weights + bias in registers for the whole kernel
     const int hsel = lane >> 4, cp = lane & 15;
@@ -273,9 +275,8 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
             PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SWP_SMEM));
             configured = true;
         }
-        kern<<<grid, SWP_THREADS, SWP_SMEM, st>>>(*reinterpret_cast<const CUtensorMap *>(op->tmap_x), dw_w, dw_b, (const __nv_bfloat16 *)pw_w, pw_b,
-                                                   (__nv_bfloat16 *)y, g);
-        PN_CHECK_LAUNCH();
+        PN_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(SWP_THREADS), SWP_SMEM, st, *reinterpret_cast<const CUtensorMap *>(op->tmap_x), dw_w, dw_b,
+                                 (const __nv_bfloat16 *)pw_w, pw_b, (__nv_bfloat16 *)y, g));
         return PN_OK;
     };
     static bool c28 = false, c26 = false, c14 = false, c00 = false;

@@ -162,11 +162,13 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
             for (int k = 0; k < 27; ++k) sum += a.w27[k * a.cout + tid];
         sBias[tid] = tid < a.cout ? a.bias[tid] + sum * (float)(1.0 / 255.0) : 0.f;
     }
+    pdl_launch_dependents();
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                                                   // (ptx.cuh) whatever produced the image / used the output buffer is done
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
     long long tile = blockIdx.x;
@@ -329,8 +331,7 @@ static int launch_stem_tc(const uint8_t *img, const float *w, const float *b, vo
     if (per_sm < 1) per_sm = 1;
     const long long max_ctas = (long long)num_sms() * per_sm;
     const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
-    stem_tc_kernel<<<grid, STC_THREADS, (size_t)smem, st>>>(a);
-    PN_CHECK_LAUNCH();
+    PN_CHECK_CUDA(launch_pdl(stem_tc_kernel, dim3(grid), dim3(STC_THREADS), (size_t)smem, st, a));
     return PN_OK;
 }
 
