@@ -124,6 +124,16 @@ int launch_stem(const void *x, bool x_is_u8, const float *w, const float *b, voi
                 int cout, int stride, int out_dtype, cudaStream_t s);
 int launch_dwconv(const void *x, const float *w, const float *b, void *y, int n, int h, int wd, int c,
                   int stride, int dilation, int dtype, cudaStream_t s);
+// stride-1 bf16 depthwise as warp-autonomous strips (dwwarp.cu)
+struct DwWarpOp {
+    alignas(64) unsigned char tmap_x[128];
+    alignas(8) unsigned char geom[64];
+    int dil;
+};
+bool dwwarp_supported(int c, int stride, int dil, int dtype);
+int dwwarp_prepare(DwWarpOp *op, const void *x, int n, int h, int wd, int c, int dil);
+int dwwarp_launch(const DwWarpOp *op, const float *w, const float *b, void *y, cudaStream_t s);
+
 // depthwise op bound to one input buffer: tensor map + tile geometry are computed once (per plan, or per call)
 struct DwOp {
     alignas(64) unsigned char tmap[128];
@@ -131,6 +141,8 @@ struct DwOp {
     const void *x;
     int n, h, w, c, stride, dil, dtype, ho, wo;
     bool use_tma;
+    bool warp_kind;          // stride 1, dilation 1 / 2, bf16: the strip kernel of dwwarp.cu
+    DwWarpOp warp;
 };
 int dw_prepare(DwOp *op, const void *x, int n, int h, int wd, int c, int stride, int dil, int dtype);
 int dw_launch(const DwOp *op, const float *w, const float *b, void *y, cudaStream_t s);

@@ -260,6 +260,10 @@ int dw_prepare(DwOp *op, const void *x, int n, int h, int wd, int c, int stride,
     g.wo = (wd + 2 * g.pad - 2 * dil - 1) / stride + 1;
     PN_CHECK_ARG(g.ho > 0 && g.wo > 0, "pn_dwconv3x3: empty output");
     op->ho = g.ho; op->wo = g.wo;
+    if (dwwarp_supported(c, stride, dil, dtype)) {
+        op->warp_kind = true;
+        return dwwarp_prepare(&op->warp, x, n, h, wd, c, dil);
+    }
     op->use_tma = dw_tma_supported(stride, dil);
     if (!op->use_tma) return PN_OK;
 
@@ -357,6 +361,7 @@ static int launch_typed(const DwOp *op, const float *w, const float *b, void *y,
 int dw_launch(const DwOp *op, const float *w, const float *b, void *y, cudaStream_t st) {
     PN_CHECK_ARG(op && w && b && y, "pn_dwconv3x3: null pointer");
     PN_CHECK_ARG(((uintptr_t)y & 15) == 0, "pn_dwconv3x3: output must be 16-byte aligned");
+    if (op->warp_kind) return dwwarp_launch(&op->warp, w, b, y, st);
     return op->dtype == PN_BF16 ? launch_typed<__nv_bfloat16>(op, w, b, y, st) : launch_typed<float>(op, w, b, y, st);
 }
 

@@ -1,0 +1,209 @@
+// B3, stand-alone, stride 1 (dilation 1 or 2), bf16 -- the depthwise 3x3 + bias + ReLU6 of the blocks that are not fused with
+// their pointwise conv (posenet/models/mobilenet_v1.py:60-62,66; at C2: blocks 12 and 13, 512 / 1024 channels at 33 x 33), as
+// warp-autonomous pipelines (the design of sepwarp.cu without the tensor phase):
+//   * a work item is a column strip of 4 output pixels x 64 channels x a run of output rows of ONE residue class mod the
+//     dilation (rows c, c + D, c + 2D, ...: in that row space the dilated stencil is dense again, so the 3-row window slides
+//     with one new row per output row); the TMA tensor map traverses the row dimension with element stride D, so the rows of
+//     the class arrive densely packed;
+//   * lane l owns the channel pair (2l, 2l + 1): 4 bytes of every pixel, one conflict-free 128 B wavefront per warp load,
+//     the window as fp32 pairs in registers, 36 packed FFMA2 per output row, results stored as 128 B coalesced pixel rows;
+//   * lane 0 streams the strip through a private two-stage TMA ring (OOB zero fill == zero padding); no CTA-wide barrier.
+// ~11 thread-instructions per output element against ~23 for the tile kernel in dwconv.cu (which reloads the window for
+// every output row and its weights for every strip); that kernel remains for fp32, stride 2 and dilation 4.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace pn {
+
+constexpr int DWW_ROWS = 8;                               // rows (of one class) per TMA chunk
+constexpr int DWW_PIX = 128;                              // bytes per patch pixel: 64 channels bf16
+__host__ __device__ constexpr int dww_ncols(int d) { return 4 + 2 * d; }
+__host__ __device__ constexpr int dww_chunk(int d) { return DWW_ROWS * dww_ncols(d) * DWW_PIX; }
+__host__ __device__ constexpr int dww_warp_smem(int d) { return 2 * dww_chunk(d) + 128; }
+__host__ __device__ constexpr int dww_warps(int d) { return d == 1 ? 16 : 12; }
+__host__ __device__ constexpr int dww_smem(int d) { return dww_warps(d) * dww_warp_smem(d) + 1024; }
+
+struct DwwGeom {
+    int n, h, w, c;
+    int cblocks, strips, nq, rb;   // 64-channel blocks, 4-pixel column strips, row blocks per class, class rows per block
+    long long items;               // n * nq * D * strips * cblocks
+};
+
+__device__ __forceinline__ void dww_stg_u32_if(void *p, uint32_t v, bool on) {          // predicated, branch-free
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.b32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"((uint32_t)on) : "memory");
+}
+__device__ __forceinline__ uint32_t dww_lds_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+
+template <int D>
+__global__ void __launch_bounds__(dww_warps(D) * 32, 1)
+dwwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restrict__ dw_w, const float *__restrict__ dw_b,
+              __nv_bfloat16 *__restrict__ y, const DwwGeom g) {
+    constexpr int NCOLS = dww_ncols(D), CHUNK = dww_chunk(D), WARPS = dww_warps(D);
+    extern __shared__ uint8_t dww_raw[];
+    const uint32_t base = (smem_u32(dww_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sRing = base + (uint32_t)warp * dww_warp_smem(D), bars = sRing + 2 * CHUNK;
+    if (lane == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 8, 1);
+        mbar_fence_init();
+        if (warp == 0) tma_prefetch_desc(&tmap_x);
+    }
+    pdl_launch_dependents();
+    __syncthreads();
+    pdl_wait();
+
+    auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
+    uint32_t phase_bits = 0, chunk_ctr = 0;
+    const long long total_warps = (long long)gridDim.x * WARPS;
+
+    for (long long item = (long long)blockIdx.x * WARPS + warp; item < g.items; item += total_warps) {
+        // item -> (image, row block, class, strip, channel block); channel blocks fastest: neighbouring warps read the same pixels
+        long long r_ = item;
+        const int cb = (int)(r_ % g.cblocks); r_ /= g.cblocks;
+        const int xs = (int)(r_ % g.strips); r_ /= g.strips;
+        const int cls = (int)(r_ % D); r_ /= D;
+        const int q = (int)(r_ % g.nq), img = (int)(r_ / g.nq);
+        const int rows_c = (g.h - cls + D - 1) / D;                      // output rows of this class
+        const int i0 = q * g.rb;                                         // first class row of the block
+        const int rows_out = min(g.rb, rows_c - i0);
+        if (rows_out <= 0) continue;
+        const int rows_in = rows_out + 2, nchunks = (rows_in + DWW_ROWS - 1) / DWW_ROWS;
+        const int x0 = xs * 4, ch0 = cb * 64 + 2 * lane;
+        const bool ch_ok = ch0 < g.c;                                    // c is a multiple of 8: the pair is in or out as a whole
+        float2 wk[9], bias2;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wk[t] = ch_ok ? __ldg(reinterpret_cast<const float2 *>(dw_w + (size_t)t * g.c + ch0)) : make_float2(0.f, 0.f);
+        bias2 = ch_ok ? __ldg(reinterpret_cast<const float2 *>(dw_b + ch0)) : make_float2(0.f, 0.f);
+        auto issue = [&](int ci) {                                       // lane 0: chunk ci (8 class rows) of this item
+            const uint32_t s = (chunk_ctr + (uint32_t)ci) & 1u;
+            mbar_expect_tx(bars + 8u * s, CHUNK);
+            tma_load_4d(sRing + s * CHUNK, &tmap_x, bars + 8u * s, cb * 64, x0 - D, cls + D * (i0 - 1 + ci * DWW_ROWS), img);
+        };
+        if (lane == 0) {
+            issue(0);
+            if (nchunks > 1) issue(1);
+        }
+        // output addressing: one 64-bit row pointer advanced per output row, the strip's pixels one channel row apart
+        const size_t pix_bytes = (size_t)g.c * 2, row_bytes = (size_t)D * g.w * pix_bytes;
+        char *o_row = reinterpret_cast<char *>(y) + ((((size_t)img * g.h + (cls + D * i0)) * g.w + x0) * g.c + ch0) * 2;
+        bool okp[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) okp[p] = ch_ok && x0 + p < g.w;
+        float2 ring[3][NCOLS];
+        uint32_t stage_addr = 0;
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows_in; r0 += 3) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int r = r0 + j;
+                if (r >= rows_in) break;
+                const int ci = r >> 3, rr = r & 7;
+                if (rr == 0) {                                            // entering a new chunk: wait for its bytes
+                    const uint32_t s = (chunk_ctr + (uint32_t)ci) & 1u;
+                    mbar_wait(bars + 8u * s, (phase_bits >> s) & 1u);
+                    phase_bits ^= 1u << s;
+                    stage_addr = sRing + s * CHUNK + (uint32_t)lane * 4u;
+                }
+                {
+                    const uint32_t rp = stage_addr + (uint32_t)rr * (NCOLS * DWW_PIX);
+#pragma unroll
+                    for (int c = 0; c < NCOLS; ++c) ring[j][c] = unpack(dww_lds_u32(rp + (uint32_t)c * DWW_PIX));
+                }
+                const bool refill = (rr == DWW_ROWS - 1 || r == rows_in - 1);
+                if (r >= 2) {
+                    float2 acc[4] = {bias2, bias2, bias2, bias2};
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int slot = (j + 1 + ky) % 3;                // class rows r-2, r-1, r
+#pragma unroll
+                        for (int c = 0; c < NCOLS; ++c)
+#pragma unroll
+                            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                                for (int kx = 0; kx < 3; ++kx)
+                                    if (p + kx * D == c) acc[p] = ffma2(ring[slot][c], wk[ky * 3 + kx], acc[p]);
+                    }
+                    char *o = o_row;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        dww_stg_u32_if(o, relu6_bf16x2(acc[p]), okp[p]);
+                        o += pix_bytes;
+                    }
+                    o_row += row_bytes;
+                }
+                if (refill) {                                             // every lane has consumed the chunk's last row
+                    __syncwarp();
+                    if (lane == 0 && ci + 2 < nchunks) issue(ci + 2);
+                }
+            }
+        }
+        chunk_ctr += (uint32_t)nchunks;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+bool dwwarp_supported(int c, int stride, int dil, int dtype) {
+    return dtype == PN_BF16 && stride == 1 && (dil == 1 || dil == 2) && c % 8 == 0 && getenv("PN_NO_DWWARP") == nullptr;
+}
+
+int dwwarp_prepare(DwWarpOp *op, const void *x, int n, int h, int wd, int c, int dil) {
+    PN_CHECK_ARG(x && n > 0 && h > 0 && wd > 0 && dwwarp_supported(c, 1, dil, PN_BF16), "pn_dwconv3x3: bad shape for the strip kernel");
+    memset(op, 0, sizeof(*op));
+    DwwGeom g;
+    memset(&g, 0, sizeof(g));
+    g.n = n; g.h = h; g.w = wd; g.c = c;
+    g.cblocks = ceil_div(c, 64);
+    g.strips = ceil_div(wd, 4);
+    const int rows_c = ceil_div(h, dil);                                  // rows of the largest class
+    const long long warps = (long long)num_sms() * dww_warps(dil);
+    const long long per_q = (long long)n * dil * g.strips * g.cblocks;
+    long long nq = (4 * warps + per_q - 1) / per_q;                        // about four items per warp ...
+    const int max_nq = ceil_div(rows_c, 8);                               // ... of at least 8 rows
+    if (nq > max_nq) nq = max_nq;
+    if (nq < 1) nq = 1;
+    g.rb = ceil_div(rows_c, (int)nq);
+    g.nq = ceil_div(rows_c, g.rb);
+    g.items = (long long)n * g.nq * dil * g.strips * g.cblocks;
+    op->dil = dil;
+    static_assert(sizeof(DwwGeom) <= sizeof(op->geom), "DwWarpOp::geom too small");
+    memcpy(op->geom, &g, sizeof(g));
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)c * 2, (uint64_t)wd * c * 2, (uint64_t)h * wd * c * 2};
+    const uint32_t box[4] = {64u, (uint32_t)dww_ncols(dil), (uint32_t)(DWW_ROWS * dil), 1u};   // every dil-th row: 8 rows land
+    const uint32_t estr[4] = {1u, 1u, (uint32_t)dil, 1u};
+    return encode_tmap(op->tmap_x, x, 2, 4, dims, strides, box, 0, estr);
+}
+
+template <int D>
+static int dwwarp_launch_t(const DwWarpOp *op, const DwwGeom &g, const float *w, const float *b, void *y, cudaStream_t st) {
+    static bool configured = false;
+    auto kern = dwwarp_kernel<D>;
+    if (!configured) {
+        PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dww_smem(D)));
+        configured = true;
+    }
+    const long long ctas = (g.items + dww_warps(D) - 1) / dww_warps(D);
+    const int grid = (int)(ctas < num_sms() ? ctas : num_sms());
+    PN_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(dww_warps(D) * 32), (size_t)dww_smem(D), st, *reinterpret_cast<const CUtensorMap *>(op->tmap_x), w,
+                             b, (__nv_bfloat16 *)y, g));
+    return PN_OK;
+}
+
+int dwwarp_launch(const DwWarpOp *op, const float *w, const float *b, void *y, cudaStream_t st) {
+    PN_CHECK_ARG(op && w && b && y, "pn_dwconv3x3: null pointer");
+    PN_CHECK_ARG(((uintptr_t)y & 3) == 0 && ((uintptr_t)w & 7) == 0 && ((uintptr_t)b & 7) == 0, "pn_dwconv3x3: misaligned pointer");
+    DwwGeom g;
+    memcpy(&g, op->geom, sizeof(g));
+    return op->dil == 1 ? dwwarp_launch_t<1>(op, g, w, b, y, st) : dwwarp_launch_t<2>(op, g, w, b, y, st);
+}
+
+}  // namespace pn

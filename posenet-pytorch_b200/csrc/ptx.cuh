@@ -168,7 +168,8 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // ---- host: tensor-map encoding (implemented in tmap.cu) ----------------------------------------------
 // rank <= 4; dims/box innermost first; strides_bytes[rank-1] are the byte strides of dims 1..rank-1.
 // esize 2 -> bf16, 4 -> fp32.  swizzle: 0 none, 1 32B, 2 64B, 3 128B.  OOB elements read as zero.
+// elem_strides (optional): traversal stride per dimension -- a box of box[i] elements then lands ceil(box[i] / stride) of them.
 int encode_tmap(void *out, const void *base, int esize, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                const uint32_t *box, int swizzle);
+                const uint32_t *box, int swizzle, const uint32_t *elem_strides = nullptr);
 
 }  // namespace pn

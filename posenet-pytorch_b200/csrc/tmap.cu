@@ -27,7 +27,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap(void *out, const void *base, int esize, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                const uint32_t *box, int swizzle) {
+                const uint32_t *box, int swizzle, const uint32_t *elem_strides) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -36,7 +36,7 @@ int encode_tmap(void *out, const void *base, int esize, int rank, const uint64_t
     PN_CHECK_ARG(rank >= 1 && rank <= 5 && (esize == 2 || esize == 4), "encode_tmap: bad rank %d / element size %d", rank, esize);
     cuuint64_t d[5], s[5];
     cuuint32_t b[5], e[5];
-    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides ? elem_strides[i] : 1; }
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
     static const CUtensorMapSwizzle sw[4] = {CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_64B,
                                              CU_TENSOR_MAP_SWIZZLE_128B};
