@@ -57,6 +57,11 @@ __device__ __forceinline__ uint32_t swp_lds_u32(uint32_t addr) {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
     return r;
 }
+__device__ __forceinline__ void swp_stg_v4_if(void *p, const uint4 &v, bool on) {          // predicated, branch-free
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w), "r"((uint32_t)on)
+                 : "memory");
+}
 __device__ __forceinline__ void swp_sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -134,6 +139,12 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
             issue(0);
             if (nchunks > 1) issue(1);
         }
+        // output addressing for the 16-byte stores of the tensor phase: lane -> (pixel lane >> 3 (+4), 8 channels lane & 7); one
+        // 64-bit pointer per lane, advanced by two output rows per phase
+        const size_t pix_bytes = (size_t)g.nc * 2, row_bytes = (size_t)g.w * pix_bytes;
+        char *o_pair = reinterpret_cast<char *>(y) + ((((size_t)img * g.h + y0) * g.w + (x0 + (lane >> 3))) * g.nc + (lane & 7) * 8) * 2;
+        const bool ok_lo = (lane & 7) < nt_n && (lane >> 3) < ncol_ok, ok_hi = (lane & 7) < nt_n && (lane >> 3) + 4 < ncol_ok;
+        const uint32_t so_lane = sO + (uint32_t)(lane >> 3) * SWP_O_STRIDE + (uint32_t)(lane & 7) * 16u;
         float2 ring[3][9];
         uint32_t stage_addr = 0;
 #pragma unroll 1
@@ -199,16 +210,16 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
                     for (int nt = 0; nt < nt_n; ++nt) tile_n(nt);
                 }
                 __syncwarp();
-                // 16-byte coalesced stores: 8 lanes cover one pixel's channels, 4 pixels per instruction
-                const int t_first = (t & 1) ? t - 1 : t;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int row = i * 4 + (lane >> 3), ch = lane & 7;   // staging row = (output row parity) * 8 + pixel
-                    const int tt = t_first + (row >> 3), px = row & 7;
-                    if (ch < nt_n && tt <= t && px < ncol_ok) {
-                        const uint4 v = ld_shared_v4(sO + (uint32_t)row * SWP_O_STRIDE + (uint32_t)ch * 16u);
-                        *reinterpret_cast<uint4 *>(y + ((((size_t)img * g.h + (y0 + tt)) * g.w + (x0 + px)) * g.nc + ch * 8)) = v;
-                    }
+                // 16-byte coalesced stores: 8 lanes cover one pixel's channels, 4 pixels per instruction (staging row =
+                // output-row parity * 8 + pixel); the second row exists when the pair is complete
+                {
+                    const bool two = (t & 1) != 0;
+                    char *o1 = o_pair + 4 * pix_bytes, *o2 = o_pair + row_bytes, *o3 = o2 + 4 * pix_bytes;
+                    swp_stg_v4_if(o_pair, ld_shared_v4(so_lane), ok_lo);
+                    swp_stg_v4_if(o1, ld_shared_v4(so_lane + 4u * SWP_O_STRIDE), ok_hi);
+                    swp_stg_v4_if(o2, ld_shared_v4(so_lane + 8u * SWP_O_STRIDE), ok_lo && two);
+                    swp_stg_v4_if(o3, ld_shared_v4(so_lane + 12u * SWP_O_STRIDE), ok_hi && two);
+                    o_pair += 2 * row_bytes;
                 }
                 __syncwarp();                                             // staging buffers are rewritten by the next rows
                 }
