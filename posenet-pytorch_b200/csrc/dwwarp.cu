@@ -33,8 +33,8 @@ struct DwwGeom {
     long long items;               // n * nq * D * strips * cblocks
 };
 
-__device__ __forceinline__ void dww_stg_u32_if(void *p, uint32_t v, bool on) {          // predicated, branch-free
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.b32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"((uint32_t)on) : "memory");
+__device__ __forceinline__ void dww_stg_u32_if(void *p, uint32_t v, bool on) {          // one predicated STG, no branch
+    if (on) asm volatile("st.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t dww_lds_u32(uint32_t addr) {
     uint32_t r;

@@ -123,8 +123,8 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_m
                  "h"(cta_mask)
                  : "memory");
 }
-__device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool on) {     // predicated, branch-free
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)on) : "memory");
+__device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool on) {     // compiles to one predicated STS; the predicate
+    if (on) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");  // is loop-invariant and stays in a P register
 }
 
 // Register window of the depthwise stencil for a strip of 4 output pixels: output row t reads input rows
@@ -313,9 +313,12 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         progress = true;
                     }
                 }
-                if (!progress && clock64() - t0 > 20000000000ll) {     // ~10 s: a protocol bug, never a slow kernel
-                    printf("posenet_b200: sepconv producer timeout (block %d)\n", blockIdx.x);
-                    __trap();
+                if (!progress) {
+                    __nanosleep(32);                                   // nothing to refill: leave the issue slots to the depthwise warps
+                    if (clock64() - t0 > 20000000000ll) {              // ~10 s: a protocol bug, never a slow kernel
+                        printf("posenet_b200: sepconv producer timeout (block %d)\n", blockIdx.x);
+                        __trap();
+                    }
                 }
             }
         }

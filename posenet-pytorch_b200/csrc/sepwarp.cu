@@ -57,10 +57,8 @@ __device__ __forceinline__ uint32_t swp_lds_u32(uint32_t addr) {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
     return r;
 }
-__device__ __forceinline__ void swp_stg_v4_if(void *p, const uint4 &v, bool on) {          // predicated, branch-free
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "r"(v.x), "r"(v.y),
-                 "r"(v.z), "r"(v.w), "r"((uint32_t)on)
-                 : "memory");
+__device__ __forceinline__ void swp_stg_v4_if(void *p, const uint4 &v, bool on) {          // one predicated STG.128, no branch
+    if (on) asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void swp_sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
