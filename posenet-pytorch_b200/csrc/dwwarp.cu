@@ -30,7 +30,7 @@ __host__ __device__ constexpr int dww_smem(int d) { return dww_warps(d) * dww_wa
 struct DwwGeom {
     int n, h, w, c;
     int cblocks, strips, nq, rb;   // 64-channel blocks, 4-pixel column strips, row blocks per class, class rows per block
-    long long items;               // n * nq * D * strips * cblocks
+    int items;                     // n * nq * D * strips * cblocks (< 2^31: 32-bit index arithmetic in the kernel)
 };
 
 __device__ __forceinline__ void dww_stg_u32_if(void *p, uint32_t v, bool on) {          // one predicated STG, no branch
@@ -63,35 +63,59 @@ dwwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restric
 
     auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
     uint32_t phase_bits = 0, chunk_ctr = 0;
-    const long long total_warps = (long long)gridDim.x * WARPS;
+    const int total_warps = (int)gridDim.x * WARPS, first_item = (int)blockIdx.x * WARPS + warp;
 
-    for (long long item = (long long)blockIdx.x * WARPS + warp; item < g.items; item += total_warps) {
-        // item -> (image, row block, class, strip, channel block); channel blocks fastest: neighbouring warps read the same pixels
-        long long r_ = item;
-        const int cb = (int)(r_ % g.cblocks); r_ /= g.cblocks;
-        const int xs = (int)(r_ % g.strips); r_ /= g.strips;
-        const int cls = (int)(r_ % D); r_ /= D;
-        const int q = (int)(r_ % g.nq), img = (int)(r_ / g.nq);
-        const int rows_c = (g.h - cls + D - 1) / D;                      // output rows of this class
-        const int i0 = q * g.rb;                                         // first class row of the block
-        const int rows_out = min(g.rb, rows_c - i0);
+    // item -> (image, row block, class, strip, channel block); channel blocks fastest: neighbouring warps read the same pixels
+    struct Item { int cb, xs, cls, img, i0, rows_out, nchunks; };
+    auto decode = [&](int it) {
+        Item t;
+        int r_ = it;
+        t.cb = (int)(r_ % g.cblocks); r_ /= g.cblocks;
+        t.xs = (int)(r_ % g.strips); r_ /= g.strips;
+        t.cls = (int)(r_ % D); r_ /= D;
+        const int q = (int)(r_ % g.nq);
+        t.img = (int)(r_ / g.nq);
+        const int rows_c = (g.h - t.cls + D - 1) / D;                    // output rows of this class
+        t.i0 = q * g.rb;                                                 // first class row of the block
+        t.rows_out = min(g.rb, rows_c - t.i0);
+        t.nchunks = t.rows_out > 0 ? (t.rows_out + 2 + DWW_ROWS - 1) / DWW_ROWS : 0;
+        return t;
+    };
+    // Lane 0 runs a producer cursor two chunks ahead of the consumer, across item boundaries: the ring never drains
+    // between items, so the first chunk of an item is (normally) already in flight when the previous item ends.
+    int p_item = first_item;
+    int p_ci = 0;
+    uint32_t p_chunks = 0;                                               // chunks issued so far (stage = count & 1)
+    Item pit = p_item < g.items ? decode(p_item) : Item{0, 0, 0, 0, 0, 0, 0};
+    auto issue_next = [&]() {                                            // lane 0: the next chunk in (item, chunk) order, if any
+        while (p_item < g.items && p_ci >= pit.nchunks) {                // (skips empty row blocks)
+            p_item += total_warps;
+            p_ci = 0;
+            if (p_item < g.items) pit = decode(p_item);
+        }
+        if (p_item >= g.items) return;
+        const uint32_t s_ = p_chunks & 1u;
+        mbar_expect_tx(bars + 8u * s_, CHUNK);
+        tma_load_4d(sRing + s_ * CHUNK, &tmap_x, bars + 8u * s_, pit.cb * 64, pit.xs * 4 - D, pit.cls + D * (pit.i0 - 1 + p_ci * DWW_ROWS), pit.img);
+        ++p_chunks;
+        ++p_ci;
+    };
+    if (lane == 0) {
+        issue_next();
+        issue_next();
+    }
+
+    for (int item = first_item; item < g.items; item += total_warps) {
+        const Item it = decode(item);
+        const int cb = it.cb, cls = it.cls, img = it.img, i0 = it.i0, rows_out = it.rows_out;
         if (rows_out <= 0) continue;
-        const int rows_in = rows_out + 2, nchunks = (rows_in + DWW_ROWS - 1) / DWW_ROWS;
-        const int x0 = xs * 4, ch0 = cb * 64 + 2 * lane;
+        const int rows_in = rows_out + 2;
+        const int x0 = it.xs * 4, ch0 = cb * 64 + 2 * lane;
         const bool ch_ok = ch0 < g.c;                                    // c is a multiple of 8: the pair is in or out as a whole
         float2 wk[9], bias2;
 #pragma unroll
         for (int t = 0; t < 9; ++t) wk[t] = ch_ok ? __ldg(reinterpret_cast<const float2 *>(dw_w + (size_t)t * g.c + ch0)) : make_float2(0.f, 0.f);
         bias2 = ch_ok ? __ldg(reinterpret_cast<const float2 *>(dw_b + ch0)) : make_float2(0.f, 0.f);
-        auto issue = [&](int ci) {                                       // lane 0: chunk ci (8 class rows) of this item
-            const uint32_t s = (chunk_ctr + (uint32_t)ci) & 1u;
-            mbar_expect_tx(bars + 8u * s, CHUNK);
-            tma_load_4d(sRing + s * CHUNK, &tmap_x, bars + 8u * s, cb * 64, x0 - D, cls + D * (i0 - 1 + ci * DWW_ROWS), img);
-        };
-        if (lane == 0) {
-            issue(0);
-            if (nchunks > 1) issue(1);
-        }
         // output addressing: one 64-bit row pointer advanced per output row, the strip's pixels one channel row apart
         const size_t pix_bytes = (size_t)g.c * 2, row_bytes = (size_t)D * g.w * pix_bytes;
         char *o_row = reinterpret_cast<char *>(y) + ((((size_t)img * g.h + (cls + D * i0)) * g.w + x0) * g.c + ch0) * 2;
@@ -140,13 +164,13 @@ dwwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restric
                     }
                     o_row += row_bytes;
                 }
-                if (refill) {                                             // every lane has consumed the chunk's last row
-                    __syncwarp();
-                    if (lane == 0 && ci + 2 < nchunks) issue(ci + 2);
+                if (refill) {                                             // every lane has consumed the chunk's last row: its stage
+                    __syncwarp();                                         // takes the chunk two ahead (of this item or the next)
+                    if (lane == 0) issue_next();
                 }
             }
         }
-        chunk_ctr += (uint32_t)nchunks;
+        chunk_ctr += (uint32_t)it.nchunks;
     }
 }
 
@@ -166,13 +190,15 @@ int dwwarp_prepare(DwWarpOp *op, const void *x, int n, int h, int wd, int c, int
     const int rows_c = ceil_div(h, dil);                                  // rows of the largest class
     const long long warps = (long long)num_sms() * dww_warps(dil);
     const long long per_q = (long long)n * dil * g.strips * g.cblocks;
-    long long nq = (4 * warps + per_q - 1) / per_q;                        // about four items per warp ...
+    long long nq = (2 * warps + per_q - 1) / per_q;                        // about two items per warp (the ring runs across items) ...
     const int max_nq = ceil_div(rows_c, 8);                               // ... of at least 8 rows
     if (nq > max_nq) nq = max_nq;
     if (nq < 1) nq = 1;
     g.rb = ceil_div(rows_c, (int)nq);
     g.nq = ceil_div(rows_c, g.rb);
-    g.items = (long long)n * g.nq * dil * g.strips * g.cblocks;
+    const long long items = (long long)n * g.nq * dil * g.strips * g.cblocks;
+    PN_CHECK_ARG(items + (long long)num_sms() * 16 < (1ll << 31), "pn_dwconv3x3: problem too large for one launch");
+    g.items = (int)items;
     op->dil = dil;
     static_assert(sizeof(DwwGeom) <= sizeof(op->geom), "DwWarpOp::geom too small");
     memcpy(op->geom, &g, sizeof(g));
@@ -191,7 +217,7 @@ static int dwwarp_launch_t(const DwWarpOp *op, const DwwGeom &g, const float *w,
         PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dww_smem(D)));
         configured = true;
     }
-    const long long ctas = (g.items + dww_warps(D) - 1) / dww_warps(D);
+    const long long ctas = ((long long)g.items + dww_warps(D) - 1) / dww_warps(D);
     const int grid = (int)(ctas < num_sms() ? ctas : num_sms());
     PN_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(dww_warps(D) * 32), (size_t)dww_smem(D), st, *reinterpret_cast<const CUtensorMap *>(op->tmap_x), w,
                              b, (__nv_bfloat16 *)y, g));
