@@ -40,7 +40,7 @@ struct SwpGeom {
     int n, h, w, k, nc;
     int strips, nq, rb;            // 8-pixel column strips per image row, row blocks per strip, output rows per block
     int ks, nt;                    // k16 slices (1 or 2), n8 tiles (cout / 8)
-    long long items;               // n * strips * nq
+    int items;                     // n * strips * nq (< 2^31: 32-bit index arithmetic in the kernel)
 };
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
@@ -116,27 +116,49 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
 
     uint32_t phase_bits = 0;                                              // bit s = parity of ring stage s
     uint32_t chunk_ctr = 0;                                               // chunks this warp has consumed so far (stage = ctr & 1)
-    const long long total_warps = (long long)gridDim.x * SWP_WARPS;
+    const int total_warps = (int)gridDim.x * SWP_WARPS, first_item = (int)blockIdx.x * SWP_WARPS + warp;
 
-    for (long long item = (long long)blockIdx.x * SWP_WARPS + warp; item < g.items; item += total_warps) {
-        // item -> (image, row block, strip); consecutive warps take neighbouring strips (they share halo columns in L2)
-        const int xs = (int)(item % g.strips);
-        const long long rest = item / g.strips;
-        const int q = (int)(rest % g.nq), img = (int)(rest / g.nq);
-        const int x0 = xs * 8, y0 = q * g.rb;
-        const int rows_out = min(g.rb, g.h - y0);
-        if (rows_out <= 0) continue;
-        const int rows_in = rows_out + 2, nchunks = (rows_in + SWP_ROWS - 1) / SWP_ROWS;
-        const int ncol_ok = g.w - x0;                                     // strip pixels px < ncol_ok exist
-        auto issue = [&](int ci) {                                        // lane 0: chunk ci of this item -> its ring stage
-            const uint32_t s = (chunk_ctr + (uint32_t)ci) & 1u;
-            mbar_expect_tx(bars + 8u * s, SWP_CHUNK);
-            tma_load_4d(sRing + s * SWP_CHUNK, &tmap_x, bars + 8u * s, 0, x0 - 1, y0 - 1 + ci * SWP_ROWS, img);
-        };
-        if (lane == 0) {
-            issue(0);
-            if (nchunks > 1) issue(1);
+    // item -> (image, row block, strip); consecutive warps take neighbouring strips (they share halo columns in L2)
+    struct Item { int x0, y0, img, rows_out, nchunks; };
+    auto decode = [&](int it) {
+        Item t;
+        const int xs = it % g.strips, rest = it / g.strips;
+        t.x0 = xs * 8;
+        t.y0 = (rest % g.nq) * g.rb;
+        t.img = rest / g.nq;
+        t.rows_out = min(g.rb, g.h - t.y0);
+        t.nchunks = t.rows_out > 0 ? (t.rows_out + 2 + SWP_ROWS - 1) / SWP_ROWS : 0;
+        return t;
+    };
+    // Lane 0 runs a producer cursor two chunks ahead of the consumer, across item boundaries, so the ring does not drain
+    // between items.
+    int p_item = first_item, p_ci = 0;
+    uint32_t p_chunks = 0;                                                // chunks issued so far (stage = count & 1)
+    Item pit = p_item < g.items ? decode(p_item) : Item{0, 0, 0, 0, 0};
+    auto issue_next = [&]() {                                             // lane 0: the next chunk in (item, chunk) order, if any
+        while (p_item < g.items && p_ci >= pit.nchunks) {
+            p_item += total_warps;
+            p_ci = 0;
+            if (p_item < g.items) pit = decode(p_item);
         }
+        if (p_item >= g.items) return;
+        const uint32_t s_ = p_chunks & 1u;
+        mbar_expect_tx(bars + 8u * s_, SWP_CHUNK);
+        tma_load_4d(sRing + s_ * SWP_CHUNK, &tmap_x, bars + 8u * s_, 0, pit.x0 - 1, pit.y0 - 1 + p_ci * SWP_ROWS, pit.img);
+        ++p_chunks;
+        ++p_ci;
+    };
+    if (lane == 0) {
+        issue_next();
+        issue_next();
+    }
+
+    for (int item = first_item; item < g.items; item += total_warps) {
+        const Item it = decode(item);
+        const int x0 = it.x0, y0 = it.y0, img = it.img, rows_out = it.rows_out;
+        if (rows_out <= 0) continue;
+        const int rows_in = rows_out + 2;
+        const int ncol_ok = g.w - x0;                                     // strip pixels px < ncol_ok exist
         // output addressing for the 16-byte stores of the tensor phase: lane -> (pixel lane >> 3 (+4), 8 channels lane & 7); one
         // 64-bit pointer per lane, advanced by two output rows per phase
         const size_t pix_bytes = (size_t)g.nc * 2, row_bytes = (size_t)g.w * pix_bytes;
@@ -223,11 +245,11 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
                 }
                 if (refill) {                                             // every lane has consumed the chunk (its FMAs are issued)
                     __syncwarp();
-                    if (lane == 0 && ci + 2 < nchunks) issue(ci + 2);
+                    if (lane == 0) issue_next();                          // (of this item or the next)
                 }
             }
         }
-        chunk_ctr += (uint32_t)nchunks;
+        chunk_ctr += (uint32_t)it.nchunks;
     }
 }
 
@@ -255,7 +277,9 @@ int sepwarp_geometry(SepWarpOp *op, int n, int h, int wd, int k, int nc) {
     if (nq < 1) nq = 1;
     g.rb = ceil_div(h, (int)nq);
     g.nq = ceil_div(h, g.rb);
-    g.items = (long long)n * g.strips * g.nq;
+    const long long items = (long long)n * g.strips * g.nq;
+    PN_CHECK_ARG(items + (long long)num_sms() * SWP_WARPS < (1ll << 31), "pn_sepconv_block: problem too large for one launch");
+    g.items = (int)items;
     static_assert(sizeof(SwpGeom) <= sizeof(op->geom), "SepWarpOp::geom too small");
     memcpy(op->geom, &g, sizeof(g));
     return PN_OK;
@@ -277,7 +301,7 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
                  "pn_sepconv_block: misaligned pointer");
     SwpGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    const long long ctas = (g.items + SWP_WARPS - 1) / SWP_WARPS;
+    const long long ctas = ((long long)g.items + SWP_WARPS - 1) / SWP_WARPS;
     const int grid = (int)(ctas < num_sms() ? ctas : num_sms());
     auto launch = [&](auto kern, bool &configured) -> int {
         if (!configured) {
@@ -298,7 +322,7 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
 void sepwarp_describe(const SepWarpOp *op, char *out, size_t cap) {
     SwpGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    snprintf(out, cap, "warp-autonomous strips %d x %d row blocks of %d rows, k16 slices %d, n8 tiles %d, items %lld, smem %d", g.strips,
+    snprintf(out, cap, "warp-autonomous strips %d x %d row blocks of %d rows, k16 slices %d, n8 tiles %d, items %d, smem %d", g.strips,
              g.nq, g.rb, g.ks, g.nt, g.items, SWP_SMEM);
 }
 
