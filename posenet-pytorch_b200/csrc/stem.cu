@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
     const uint32_t mma_bar = bars + 8u * STC_NBUF, tmem_slot_addr = mma_bar + 8u;
     volatile uint32_t *tmem_slot =
         reinterpret_cast<volatile uint32_t *>(gen + 16384 + 4096 + STC_NBUF * a.span_cap + 128 + 8 * STC_NBUF + 8);
+    // span base (byte offset of the ring slot's first byte in the image batch), written by thread 0 when it issues the load
+    volatile long long *span_lo = reinterpret_cast<volatile long long *>(gen + 16384 + 4096 + STC_NBUF * a.span_cap + 128 + 32);
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long row_bytes = (long long)a.w * 3;
     const long long num_tiles = (a.total_px + 127) / 128;
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
             if (t >= num_tiles) break;
             long long lo16; uint32_t size;
             span_of(t, lo16, size);
+            span_lo[i] = lo16;
             mbar_expect_tx(bars + 8u * i, size);
             bulk_load_1d(sSpan + (uint32_t)i * (uint32_t)a.span_cap, a.img + lo16, size, bars + 8u * i);
         }
@@ -185,8 +188,6 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
     uint32_t span_phase = 0, mma_phase = 0;             // bit b of span_phase = parity of ring slot b
     int buf = 0;
     for (; tile < num_tiles; tile += gridDim.x, buf = (buf + 1) % STC_NBUF) {
-        long long lo16; uint32_t size;
-        span_of(tile, lo16, size);
         const long long m = tile * 128 + tid;
         const bool live = m < a.total_px;
         int img_i = 0, oy = 0, ox = 0;
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         }
         mbar_wait(bars + 8u * buf, (span_phase >> buf) & 1u);
         span_phase ^= 1u << buf;
+        const long long lo16 = span_lo[buf];                     // (published before the load was issued)
         // ---- im2col: this thread's pixel -> row `tid` of A
         float f[32];
 #pragma unroll
@@ -213,13 +215,14 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         const int iy0 = oy * a.stride - 1;
         // interior pixels (all 27 taps inside the image) take a copy of the loop without the padding selects
         const bool interior_px = live && ix0 >= 0 && ix0 + 2 < a.w && iy0 >= 0 && iy0 + 2 < a.h;
+        // byte offset of the window's first row / first used column inside the span (32-bit: spans are < 200 KB)
+        const int rowoff0 = (int)(((long long)img_i * a.h + iy0) * row_bytes - lo16) + (ix0 + lead) * 3;
         auto im2col = [&](const bool interior) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = oy * a.stride - 1 + ky;
             const bool row_ok = live && iy >= 0 && iy < a.h;
-            const long long rowoff = ((long long)img_i * a.h + iy) * row_bytes - lo16;
-            const uint32_t b0 = row_ok ? (uint32_t)(rowoff + (long long)(ix0 + lead) * 3) : 0u;
+            const uint32_t b0 = row_ok ? (uint32_t)(rowoff0 + ky * (int)row_bytes) : 0u;
             const uint32_t a0 = sp + (b0 & ~3u), sh = (b0 & 3u) * 8u;
             const uint32_t w0 = lds_u32s(a0), w1 = lds_u32s(a0 + 4), w2 = lds_u32s(a0 + 8);
             uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = w2 >> sh;
@@ -261,6 +264,7 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
                 const int nb = (buf + STC_NBUF - 1) % STC_NBUF;
                 long long nlo; uint32_t nsize;
                 span_of(next, nlo, nsize);
+                span_lo[nb] = nlo;
                 mbar_expect_tx(bars + 8u * nb, nsize);
                 bulk_load_1d(sSpan + (uint32_t)nb * (uint32_t)a.span_cap, a.img + nlo, nsize, bars + 8u * nb);
             }
