@@ -19,12 +19,15 @@
 
 namespace pn {
 
-constexpr int DWW_ROWS = 8;                               // rows (of one class) per TMA chunk
+// rows (of one class) per TMA chunk / chunks in flight per warp / warps per CTA, per dilation (measured: dilation 1 prefers
+// two 8-row chunks, dilation 2 -- wider patches, more registers -- three 4-row chunks; both 16 warps)
+__host__ __device__ constexpr int dww_rows(int d) { return d == 1 ? 8 : 4; }
+__host__ __device__ constexpr int dww_stages(int d) { return d == 1 ? 2 : 3; }
 constexpr int DWW_PIX = 128;                              // bytes per patch pixel: 64 channels bf16
 __host__ __device__ constexpr int dww_ncols(int d) { return 4 + 2 * d; }
-__host__ __device__ constexpr int dww_chunk(int d) { return DWW_ROWS * dww_ncols(d) * DWW_PIX; }
-__host__ __device__ constexpr int dww_warp_smem(int d) { return 2 * dww_chunk(d) + 128; }
-__host__ __device__ constexpr int dww_warps(int d) { return d == 1 ? 16 : 12; }
+__host__ __device__ constexpr int dww_chunk(int d) { return dww_rows(d) * dww_ncols(d) * DWW_PIX; }
+__host__ __device__ constexpr int dww_warp_smem(int d) { return dww_stages(d) * dww_chunk(d) + 128; }
+__host__ __device__ constexpr int dww_warps(int d) { return 16; }
 __host__ __device__ constexpr int dww_smem(int d) { return dww_warps(d) * dww_warp_smem(d) + 1024; }
 
 struct DwwGeom {
@@ -46,14 +49,13 @@ template <int D>
 __global__ void __launch_bounds__(dww_warps(D) * 32, 1)
 dwwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restrict__ dw_w, const float *__restrict__ dw_b,
               __nv_bfloat16 *__restrict__ y, const DwwGeom g) {
-    constexpr int NCOLS = dww_ncols(D), CHUNK = dww_chunk(D), WARPS = dww_warps(D);
+    constexpr int NCOLS = dww_ncols(D), CHUNK = dww_chunk(D), WARPS = dww_warps(D), DWW_ROWS = dww_rows(D), DWW_STAGES = dww_stages(D);
     extern __shared__ uint8_t dww_raw[];
     const uint32_t base = (smem_u32(dww_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t sRing = base + (uint32_t)warp * dww_warp_smem(D), bars = sRing + 2 * CHUNK;
+    const uint32_t sRing = base + (uint32_t)warp * dww_warp_smem(D), bars = sRing + DWW_STAGES * CHUNK;
     if (lane == 0) {
-        mbar_init(bars, 1);
-        mbar_init(bars + 8, 1);
+        for (int s_ = 0; s_ < DWW_STAGES; ++s_) mbar_init(bars + 8u * s_, 1);
         mbar_fence_init();
         if (warp == 0) tma_prefetch_desc(&tmap_x);
     }
@@ -62,7 +64,7 @@ dwwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restric
     pdl_wait();
 
     auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
-    uint32_t phase_bits = 0, chunk_ctr = 0;
+    uint32_t phase_bits = 0;
     const int total_warps = (int)gridDim.x * WARPS, first_item = (int)blockIdx.x * WARPS + warp;
 
     // item -> (image, row block, class, strip, channel block); channel blocks fastest: neighbouring warps read the same pixels
@@ -85,7 +87,7 @@ dwwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restric
     // between items, so the first chunk of an item is (normally) already in flight when the previous item ends.
     int p_item = first_item;
     int p_ci = 0;
-    uint32_t p_chunks = 0;                                               // chunks issued so far (stage = count & 1)
+    uint32_t p_stage = 0;                                                // ring stage of the next chunk to issue
     Item pit = p_item < g.items ? decode(p_item) : Item{0, 0, 0, 0, 0, 0, 0};
     auto issue_next = [&]() {                                            // lane 0: the next chunk in (item, chunk) order, if any
         while (p_item < g.items && p_ci >= pit.nchunks) {                // (skips empty row blocks)
@@ -94,16 +96,15 @@ dwwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restric
             if (p_item < g.items) pit = decode(p_item);
         }
         if (p_item >= g.items) return;
-        const uint32_t s_ = p_chunks & 1u;
+        const uint32_t s_ = p_stage;
         mbar_expect_tx(bars + 8u * s_, CHUNK);
         tma_load_4d(sRing + s_ * CHUNK, &tmap_x, bars + 8u * s_, pit.cb * 64, pit.xs * 4 - D, pit.cls + D * (pit.i0 - 1 + p_ci * DWW_ROWS), pit.img);
-        ++p_chunks;
+        if (++p_stage == DWW_STAGES) p_stage = 0;
         ++p_ci;
     };
-    if (lane == 0) {
-        issue_next();
-        issue_next();
-    }
+    if (lane == 0)
+        for (int s_ = 0; s_ < DWW_STAGES; ++s_) issue_next();
+    uint32_t c_stage = 0;                                                // ring stage of the chunk the consumer enters next
 
     for (int item = first_item; item < g.items; item += total_warps) {
         const Item it = decode(item);
@@ -130,12 +131,13 @@ dwwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restric
             for (int j = 0; j < 3; ++j) {
                 const int r = r0 + j;
                 if (r >= rows_in) break;
-                const int ci = r >> 3, rr = r & 7;
+                const int rr = r & (DWW_ROWS - 1);
                 if (rr == 0) {                                            // entering a new chunk: wait for its bytes
-                    const uint32_t s = (chunk_ctr + (uint32_t)ci) & 1u;
+                    const uint32_t s = c_stage;
                     mbar_wait(bars + 8u * s, (phase_bits >> s) & 1u);
                     phase_bits ^= 1u << s;
                     stage_addr = sRing + s * CHUNK + (uint32_t)lane * 4u;
+                    if (++c_stage == DWW_STAGES) c_stage = 0;
                 }
                 {
                     const uint32_t rp = stage_addr + (uint32_t)rr * (NCOLS * DWW_PIX);
@@ -170,7 +172,6 @@ dwwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restric
                 }
             }
         }
-        chunk_ctr += (uint32_t)it.nchunks;
     }
 }
 
@@ -204,7 +205,7 @@ int dwwarp_prepare(DwWarpOp *op, const void *x, int n, int h, int wd, int c, int
     memcpy(op->geom, &g, sizeof(g));
     const uint64_t dims[4] = {(uint64_t)c, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)c * 2, (uint64_t)wd * c * 2, (uint64_t)h * wd * c * 2};
-    const uint32_t box[4] = {64u, (uint32_t)dww_ncols(dil), (uint32_t)(DWW_ROWS * dil), 1u};   // every dil-th row: 8 rows land
+    const uint32_t box[4] = {64u, (uint32_t)dww_ncols(dil), (uint32_t)(dww_rows(dil) * dil), 1u};   // every dil-th row: dww_rows land
     const uint32_t estr[4] = {1u, 1u, (uint32_t)dil, 1u};
     return encode_tmap(op->tmap_x, x, 2, 4, dims, strides, box, 0, estr);
 }
