@@ -36,7 +36,6 @@ namespace pn {
 constexpr int SEP_DW_WARPS = 10;
 constexpr int SEP_FIRST_DW_WARP = 6;
 constexpr int SEP_THREADS = (SEP_FIRST_DW_WARP + SEP_DW_WARPS) * 32;   // 512
-constexpr int SEP_DW_THREADS = SEP_DW_WARPS * 32;                      // 320
 constexpr int SEP_MAX_A = 6;
 constexpr int SEP_A_BYTES = 128 * 128;                                 // 128 rows x 64 bf16
 constexpr int SEP_STG_BYTES = 128 * 128;                               // one 128 x 64 bf16 output panel
@@ -824,7 +823,6 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
     }
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    const int cb = op->cb;
     {   // input patches: (C, W, H, N) bf16, box [cb, twi, thi, 1], no swizzle, OOB -> 0
         const uint64_t dims[4] = {(uint64_t)k, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
         const uint64_t strides[3] = {(uint64_t)k * 2, (uint64_t)wd * k * 2, (uint64_t)h * wd * k * 2};
