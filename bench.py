@@ -46,35 +46,64 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is polled in-process (a reading takes
+    ~0.1 ms, so even a 15 ms timed region holds dozens); `nvidia-smi` (one reading per ~100 ms) is the fallback
+    when the NVML binding is missing."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()     # rows: (t, sm_mhz, reason flags)
+        self.max_mhz, self.source, self.window = None, "nvidia-smi", None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                         pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+            self.source = "nvml"
+        except Exception:
+            self.nv = None
+
+    def _read(self):
+        if self.nv is not None:
+            mhz = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            return mhz, [bool(mask & b) for b in self.bits]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        c = [x.strip() for x in out.split(",")]
+        self.max_mhz = float(c[1])
+        return float(c[0]), [x.lower().startswith("active") for x in c[2:6]]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                mhz, flags = self._read()
+                self.rows.append((time.perf_counter(), mhz, flags))
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.001 if self.nv is not None else 0.2)
 
     def summary(self):
+        """`window` = (t0, t1) host times bracketing the timed region (set by the caller): readings inside it are
+        counted separately; the median and the reasons come from the readings inside the window when there are any."""
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["clock query unavailable"], "samples": 0}
+        inside = [r for r in self.rows if self.window and self.window[0] <= r[0] <= self.window[1]]
+        use = inside or self.rows
+        sm = sorted(r[1] for r in use)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2][i] for r in use)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.rows), "samples_in_timed_region": len(inside), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -231,15 +260,16 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         graphs[i % n_sets][0].replay()
     e1.record()
     barrier()
+    sampler.window = (t_begin, time.perf_counter())
     ms = e0.elapsed_time(e1)
-    # nvidia-smi answers in ~100 ms and the timed region can be shorter than that: keep the SAME load running (untimed)
-    # until the sampler has at least 5 readings, and say how many fell inside the timed region
-    in_timed = len(sampler.rows)
+    # the nvidia-smi fallback answers in ~100 ms and the timed region can be shorter than that: keep the SAME load running
+    # (untimed) until the sampler has at least 5 readings; NVML readings (~0.1 ms each) land inside the timed region
     t_extra = time.perf_counter()
     i = 0
     while len(sampler.rows) < 5 and time.perf_counter() - t_extra < 3.0:
@@ -249,8 +279,8 @@ def run_b200(args):
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.summary()
-    clocks["samples_in_timed_region"] = in_timed
-    clocks["note"] = "readings beyond the timed region were taken under the same graph replays, untimed"
+    if not clocks.get("samples_in_timed_region"):
+        clocks["note"] = "no reading fell inside the timed region; these were taken under the same graph replays, untimed"
     if world > 1:
         t = torch.tensor([ms], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
