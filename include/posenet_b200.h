@@ -81,6 +81,11 @@ int pn_pwconv_gemm(const void *a, const void *w, const float *bias, void *y, int
  * pw_b f32 [cout]; y: NHWC [n,ho,wo,cout].  cin % 8 == 0, cout % 16 == 0, (stride,dilation) in (1,1|2|4), (2,1). */
 int pn_sepconv_block(const void *x, const float *dw_w, const float *dw_b, const void *pw_w, const float *pw_b, void *y,
                      int n, int h, int wd, int cin, int cout, int stride, int dilation, pn_stream_t stream);
+/* Diagnostic for the tensor-pipe depthwise (csrc/dwtc_probe.cu): one 128-position chunk of one 64-channel bf16 image
+ * [h, wd, 64] through shifted-descriptor tcgen05 depthwise (block-diagonal tap tiles `diag` [9*16, 64]) and an
+ * A-from-TMEM pointwise (`pw_w` [64, 64]); out_dw / out_pw: f32 [128, 64].  Not part of the product path. */
+int pn_dwtc_probe(const void *x, int h, int wd, const void *diag, const void *pw_w, const float *dw_bias, float *out_dw,
+                  float *out_pw, int wp, int dil, int qoff, int rows_box, int x_org, int y_org, int flags, pn_stream_t stream);
 /* Tile shape / pipeline depths pn_sepconv_block would pick for a block (host arithmetic only; diagnostics). */
 int pn_sepconv_describe(int n, int h, int wd, int cin, int cout, int stride, int dilation, char *out_host, int capacity);
 
