@@ -171,6 +171,20 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
                    cudaStream_t s);
 void sepwarp_describe(const SepWarpOp *op, char *out, size_t cap);
 
+// fused block with the depthwise on the tensor pipe (septc.cu): stride 1, dilation 1 / 2, cin / cout multiples of 64 (<= 512)
+struct SepTcOp {
+    alignas(64) unsigned char tmap_x[128];
+    alignas(64) unsigned char tmap_w[128];
+    alignas(8) unsigned char geom[256];
+    int smem_bytes;
+};
+bool septc_supported(int k, int nc, int stride, int dil);
+bool septc_enabled();      // PN_SEP_TC=0 falls back to the CUDA-core depthwise of sepconv.cu
+int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil);
+int septc_prepare(SepTcOp *op, const void *x, const void *pw_w, int n, int h, int wd, int k, int nc, int dil);
+int septc_launch(const SepTcOp *op, const float *dw_w, const float *dw_b, const float *pw_b, void *y, cudaStream_t s);
+void septc_describe(const SepTcOp *op, char *out, size_t cap);
+
 // fused SeperableConv block (depthwise -> pointwise in one kernel, sepconv.cu); bf16 only
 struct SepOp {
     alignas(64) unsigned char tmap_x[128];
@@ -183,6 +197,8 @@ struct SepOp {
     // narrow blocks run the warp-autonomous kernel instead (warp_kind): it takes plain pointers, kept here for the launch
     bool warp_kind;
     SepWarpOp warp;
+    bool tc_kind;            // depthwise on the tensor pipe (septc.cu)
+    SepTcOp tc;
     const float *dw_w, *dw_b;
     const void *pw_w;
     void *y;

@@ -632,6 +632,13 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
         op->n = n; op->h = h; op->w = wd; op->k = k; op->nc = nc;
         return PN_OK;
     }
+    if (septc_enabled() && septc_supported(k, nc, stride, dil)) {   // depthwise on the tensor pipe
+        op->tc_kind = true;
+        op->stride = stride; op->dil = dil;
+        op->ho = h; op->wo = wd;
+        op->n = n; op->h = h; op->w = wd; op->k = k; op->nc = nc;
+        return septc_geometry(&op->tc, n, h, wd, k, nc, dil);
+    }
     SepGeom g;
     memset(&g, 0, sizeof(g));
     g.k = k; g.nc = nc;
@@ -821,6 +828,10 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
         op->dw_w = dw_w; op->dw_b = dw_b; op->pw_w = pw_w; op->y = y;
         return sepwarp_prepare(&op->warp, x, n, h, wd, k, nc);
     }
+    if (op->tc_kind) {
+        op->dw_w = dw_w; op->dw_b = dw_b; op->pw_w = pw_w; op->y = y;
+        return septc_prepare(&op->tc, x, pw_w, n, h, wd, k, nc, dil);
+    }
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
     {   // input patches: (C, W, H, N) bf16, box [cb, twi, thi, 1], no swizzle, OOB -> 0
@@ -904,6 +915,7 @@ static int sep_launch_cl(const SepOp *op, const SepGeom &g, const float *pw_bias
 int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t st) {
     PN_CHECK_ARG(op && pw_bias, "pn_sepconv_block: null pointer");
     if (op->warp_kind) return sepwarp_launch(&op->warp, op->dw_w, op->dw_b, op->pw_w, pw_bias, op->y, st);
+    if (op->tc_kind) return septc_launch(&op->tc, op->dw_w, op->dw_b, pw_bias, op->y, st);
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
     if (op->stride == 2) return sep_launch_cl<2, 1>(op, g, pw_bias, st);
@@ -914,6 +926,10 @@ int sep_launch(const SepOp *op, const float *pw_bias, cudaStream_t st) {
 }
 
 void sep_describe(const SepOp *op, char *out, size_t cap) {
+    if (op->tc_kind) {
+        septc_describe(&op->tc, out, cap);
+        return;
+    }
     if (op->warp_kind) {
         SepWarpOp w;
         if (sepwarp_geometry(&w, op->n, op->h, op->w, op->k, op->nc) == PN_OK) sepwarp_describe(&w, out, cap);
