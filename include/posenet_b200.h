@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 3
+#define PN_ABI_VERSION 4
 
 typedef void *pn_stream_t; /* cudaStream_t */
 
@@ -86,6 +86,13 @@ int pn_sepconv_block(const void *x, const float *dw_w, const float *dw_b, const 
  * A-from-TMEM pointwise (`pw_w` [64, 64]); out_dw / out_pw: f32 [128, 64].  Not part of the product path. */
 int pn_dwtc_probe(const void *x, int h, int wd, const void *diag, const void *pw_w, const float *dw_bias, float *out_dw,
                   float *out_pw, int wp, int dil, int qoff, int rows_box, int x_org, int y_org, int flags, pn_stream_t stream);
+/* Diagnostics of the tensor-pipe depthwise path (csrc/septc.cu, PN_SEP_TC=1).  pn_debug_tcs_trace registers a zero-filled
+ * device buffer of 6 roles x cap steps x 4 int64 clock stamps that CTA 0 of the next pn_sepconv_block launches fills
+ * ((NULL, 0) turns it off).  pn_debug_umma_cost times 9 * reps tcgen05.mma (M128 x n x K16, bf16) on one SM; layout
+ * 0 / 1 / 2 = 128 / 32 / 64-byte swizzle issued by one thread, 3 = 128-byte swizzle issued from warp-uniform code;
+ * out_host[0] = cycles until the last issue, out_host[1] = until completion (synchronous, default stream). */
+int pn_debug_tcs_trace(long long *device_buf, int cap);
+int pn_debug_umma_cost(int n, int layout, int reps, int a_step16, long long *out_host);
 /* Tile shape / pipeline depths pn_sepconv_block would pick for a block (host arithmetic only; diagnostics). */
 int pn_sepconv_describe(int n, int h, int wd, int cin, int cout, int stride, int dilation, char *out_host, int capacity);
 

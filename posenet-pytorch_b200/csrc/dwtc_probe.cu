@@ -173,3 +173,122 @@ extern "C" int pn_dwtc_probe(const void *x, int h, int wd, const void *diag, con
     PN_CHECK_LAUNCH();
     return PN_OK;
 }
+
+// ---- UMMA cost microbenchmark (diagnostics): cycles per tcgen05.mma for small N and different operand layouts -----------------
+namespace pn {
+__global__ void __launch_bounds__(128, 1) umma_cost_kernel(int n, int layout, int reps, int a_step16, long long *out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t bars[1];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (uint32_t o = tid * 16; o < 96u * 1024u; o += 128 * 16) st_shared_v4(base + o, 0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        // layout 0: K-major SWIZZLE_128B (128-byte rows, SBO 1024); layout 1: K-major SWIZZLE_32B (32-byte rows, SBO 256);
+        // layout 2: K-major SWIZZLE_64B (64-byte rows, SBO 512)
+        const uint64_t sbo = layout == 0 ? 1024 : layout == 1 ? 256 : 512;
+        const uint64_t lt = layout == 0 ? 2 : layout == 1 ? 6 : 4;
+        const uint64_t hi = (1ull << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (lt << 61);
+        const uint32_t a0 = (base & 0x3FFFF) >> 4, b0 = ((base + 65536u) & 0x3FFFF) >> 4;
+        const uint32_t idesc = probe_idesc(n);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int u = 0; u < 9; ++u) tc_mma_bf16(tmem, hi | (uint64_t)(a0 + u * a_step16), hi | (uint64_t)(b0 + u * 128), idesc, 1);
+        }
+        const long long t1 = clock64();
+        tc_commit(bar0);
+        mbar_wait(bar0, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// Same measurement with the issue loop executed by the WHOLE warp (uniform control flow, operands derived from kernel
+// parameters only) and the MMA itself predicated on elect.sync -- lets ptxas keep the descriptors in uniform registers.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+__global__ void __launch_bounds__(128, 1) umma_cost_uniform_kernel(int n, int reps, int a_step16, long long *out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t bars[1];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (uint32_t o = tid * 16; o < 96u * 1024u; o += 128 * 16) st_shared_v4(base + o, 0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 1) {
+        const uint64_t hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+        const uint32_t a0 = (base & 0x3FFFF) >> 4, b0 = ((base + 65536u) & 0x3FFFF) >> 4;
+        const uint32_t idesc = probe_idesc(n);
+        const uint32_t leader = elect_one();
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int u = 0; u < 9; ++u)
+                if (leader) tc_mma_bf16(tmem, hi | (uint64_t)(a0 + u * a_step16), hi | (uint64_t)(b0 + u * 128), idesc, 1);
+        }
+        const long long t1 = clock64();
+        if (leader) tc_commit(bar0);
+        __syncwarp();
+        mbar_wait(bar0, 0);
+        const long long t2 = clock64();
+        if (leader) {
+            out[0] = t1 - t0;
+            out[1] = t2 - t0;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+}  // namespace pn
+
+// out_host[0] = cycles until the last MMA was issued, out_host[1] = cycles until all completed; 9 * reps MMAs of M128 x N x K16
+extern "C" int pn_debug_umma_cost(int n, int layout, int reps, int a_step16, long long *out_host) {
+    using namespace pn;
+    long long *d = nullptr;
+    PN_CHECK_CUDA(cudaMalloc(&d, 16));
+    const size_t smem = 1024 + 96 * 1024;
+    PN_CHECK_CUDA(cudaFuncSetAttribute(umma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (layout == 3) {
+        PN_CHECK_CUDA(cudaFuncSetAttribute(umma_cost_uniform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        umma_cost_uniform_kernel<<<1, 128, smem>>>(n, reps, a_step16, d);
+    } else
+        umma_cost_kernel<<<1, 128, smem>>>(n, layout, reps, a_step16, d);
+    PN_CHECK_LAUNCH();
+    PN_CHECK_CUDA(cudaMemcpy(out_host, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return PN_OK;
+}

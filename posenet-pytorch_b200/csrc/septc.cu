@@ -11,20 +11,25 @@
 // halo part of the pitch are computed and dropped.  The depthwise accumulator (TMEM, fp32) is read back once per k-block by
 // four converter warps (+ bias, ReLU6 -> bf16) and stored back into TMEM as the A operand of the pointwise MMA
 // (tcgen05.mma with A in tensor memory), so the intermediate never touches shared memory or HBM.
+// What bounds it: every tap MMA re-reads its 4 KB A slice from shared memory (9 x the patch per k-block, ~1150 cycles per
+// 128 positions x 64 channels at 128 B/clk) -- about the CUDA-core kernel's issue time, but the SM's issue slots stay free.
 //
-// Work unit: 128 consecutive flat positions ("chunk") of one column band of one image; per unit, for every tile of n_tile
-// (<= 256) output channels and every 64-channel k-block:
-//   warp 0        TMA producer   patch box [64 ch, wp, rows_box] (OOB zero fill == zero padding) + pointwise weight tile
-//                                [n_tile x 64] (128B swizzle); two mbarrier rings
-//   warp 1        pointwise MMA  the 4 MMAs of a step (A operand in TMEM); tcgen05.commit releases the A buffer and the W stage
-//                                and signals the epilogue after the last k-block
-//   warps 11-14   depthwise MMA  warp 11 + q issues the nine tap MMAs of channel group q (four issuers because one thread cannot
-//                                issue 36 eight-cycle MMAs per step fast enough); their commits release the patch / diag stages
-//   warps 2-5     converters     tcgen05.ld depthwise accumulator -> bias, ReLU6, bf16x2 -> tcgen05.st (A operand)
-//   warps 6-9     epilogue       tcgen05.ld accumulator panel -> bias, ReLU6 -> bf16 -> warp-private swizzled staging ->
-//                                coalesced predicated 16-byte global stores (128 B per pixel)
-//   warp 10       diag writer    the 9 x 4 diagonal weight tiles of the next k-block (576 bf16 values into pre-zeroed tiles)
-// TMEM (512 columns): pointwise accumulator(s) at 0, depthwise accumulators 2 x 64 at 320, A operands 2 x 32 at 448.
+// Work unit: 128 consecutive flat positions ("chunk") of one column band of one image.  Two step sequences per CTA:
+//   depthwise step d = (unit, k-block)            patch stage d % PS, diag / depthwise-accumulator buffer d % 2
+//   pointwise step s = (unit, n-tile, k-block)    W stage s % WS
+// A operands (32 TMEM columns each): cout <= 256 ("ring"): one n-tile, 4 buffers used round-robin, so the depthwise runs up to
+// four k-blocks ahead of the pointwise MMAs (covers the epilogue of a single-buffered accumulator); cout > 256 ("cache"):
+// n-tiles of 128, the A operands of ALL k-blocks of a unit stay in TMEM (<= 8 x 32 columns) and every n-tile re-reads them --
+// the depthwise is computed once per unit, not once per n-tile.
+//   warp 0        patch producer  TMA box [64 ch, wp, rows_box] (OOB zero fill == zero padding), 128B swizzle
+//   warp 15       W producer      pointwise weight tile [n_tile x 64] (128B swizzle)
+//   warps 16-17   depthwise MMA   warp 16 + w issues the 2 x 9 tap MMAs of channel groups 2w, 2w+1; commits release patch / diag stages
+//   warps 2-5     converters      tcgen05.ld depthwise accumulator -> bias, ReLU6, bf16x2 -> tcgen05.st (A operand)
+//   warp 1        pointwise MMA   4 MMAs per step, A from TMEM; commits release the W stage, the A operand, and signal the epilogue
+//   warps 6-13    epilogue        tcgen05.ld 32 accumulator columns -> bias, ReLU6 -> bf16 -> warp-private staging -> coalesced
+//                                 predicated 16-byte global stores
+//   warp 14       diag writer     the 9 x 4 diagonal weight tiles of the next k-block (576 bf16 values into pre-zeroed tiles)
+// TMEM (512 columns): accumulator(s) at 0, A operands from 256 (ring) / 128 (cache) up to 384, depthwise accumulators 2 x 64 at 384.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -34,18 +39,21 @@
 
 namespace pn {
 
-constexpr int TCS_THREADS = 15 * 32;
-constexpr int TCS_MAX_P = 4, TCS_MAX_W = 4;
+constexpr int TCS_WARPS = 18;
+constexpr int TCS_THREADS = TCS_WARPS * 32;
+constexpr int TCS_MAX_P = 4, TCS_MAX_W = 4, TCS_MAX_A = 8;
 constexpr int TCS_DIAG_BYTES = 9 * 16 * 128;          // nine [16 x 64] bf16 tiles
-constexpr int TCS_STG_BYTES = 32 * 128;               // per epilogue warp
-constexpr int TCS_EPI_WARPS = 4;
+constexpr int TCS_STG_BYTES = 32 * 64;                // per epilogue warp: 32 rows x 32 bf16
+constexpr int TCS_EPI_WARPS = 8;
+constexpr int TCS_DW_ISSUERS = 2;
 constexpr int TCS_SMEM_MAX = 232448;
-constexpr uint32_t TCS_DW_COL = 320, TCS_A_COL = 448;
+constexpr uint32_t TCS_DW_COL = 384;
 
 struct TcsGeom {
     int k, nc, h, w, n_img, dil;
     int wp, tw, bands, rows_box, chunks;
     int n_tile, n_tiles, kblocks, acc_bufs;
+    int ring, na, a_col;                                // A operand buffers: ring of 4 (one n-tile) or one per k-block (cache)
     int p_stages, w_stages;
     unsigned patch_bytes, patch_stage_bytes, w_stage_bytes;
     unsigned off_diag, off_patch, off_stg, off_dww, off_dwb, off_pwb, off_bar;
@@ -55,7 +63,8 @@ struct TcsGeom {
 
 struct TcsBars {
     static constexpr int patch_full = 0, patch_empty = 32, w_full = 64, w_empty = 96, diag_full = 128, diag_empty = 144,
-                         dw_full = 160, a_full = 176, a_empty = 192, tfull = 208, tempty = 224, tmem_slot = 240, total = 256;
+                         dw_full = 160, dw_free = 176, a_full = 192, a_empty = 256, tfull = 320, tempty = 336, tmem_slot = 352,
+                         total = 368;
 };
 
 __device__ __forceinline__ uint64_t tcs_desc(uint32_t saddr) {          // K-major SWIZZLE_128B, 8-row groups 1024 B apart
@@ -88,6 +97,11 @@ __device__ __forceinline__ float4 tcs_lds_f4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
     return r;
 }
+__device__ __forceinline__ uint32_t tcs_lds_u16(uint32_t addr) {
+    unsigned short r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(addr));
+    return r;
+}
 __device__ __forceinline__ void tcs_sts_u16(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
 }
@@ -104,39 +118,6 @@ __device__ int g_tcs_trace_cap = 0;
         if (tr && (step) < tr_cap) tr[(((long long)(role)) * tr_cap + (step)) * 4 + (ev)] = clock64();  \
     } while (0)
 
-// Latency-critical waits (MMA issuers, converters, diag writer): plain try_wait polling -- the suspend-time hint of mbar_wait
-// (ptx.cuh) parks the warp and its wake-up costs more than the whole step here.  Bounded like mbar_wait.
-__device__ __forceinline__ void tcs_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spins = 0; !done; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (spins > 200000000u) {
-            printf("posenet_b200: septc mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
-        }
-    }
-}
-
-// (unit, n-tile, k-block) cursor shared by every role: all of them walk the same sequence of steps
-struct TcsCursor {
-    long long unit;
-    int nt, kb;
-    __device__ __forceinline__ bool next(const TcsGeom &g, long long stride) {      // returns true when a new unit starts
-        if (++kb < g.kblocks) return false;
-        kb = 0;
-        if (++nt < g.n_tiles) return false;
-        nt = 0;
-        unit += stride;
-        return true;
-    }
-};
-
 __global__ void __launch_bounds__(TCS_THREADS, 1)
 septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const float *__restrict__ dw_w,
              const float *__restrict__ dw_b, const float *__restrict__ pw_b, __nv_bfloat16 *__restrict__ y, const TcsGeom g) {
@@ -150,26 +131,29 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     auto d_addr = [&](int s) { return base + g.off_diag + (uint32_t)s * TCS_DIAG_BYTES; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ustride = gridDim.x;
-    const long long my_units = (long long)blockIdx.x < g.units ? (g.units - blockIdx.x + ustride - 1) / ustride : 0;
-    const long long total_steps = my_units * g.n_tiles * g.kblocks;
+    const int my_units = (long long)blockIdx.x < g.units ? (int)((g.units - blockIdx.x + ustride - 1) / ustride) : 0;
+    const int per_img = g.bands * g.chunks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_x);
         tma_prefetch_desc(&tmap_w);
         for (int s = 0; s < TCS_MAX_P; ++s) {
             mbar_init(bar(TcsBars::patch_full, s), 1);
-            mbar_init(bar(TcsBars::patch_empty, s), 4);             // one tcgen05.commit per depthwise issuer
+            mbar_init(bar(TcsBars::patch_empty, s), TCS_DW_ISSUERS);      // one tcgen05.commit per depthwise issuer
             mbar_init(bar(TcsBars::w_full, s), 1);
             mbar_init(bar(TcsBars::w_empty, s), 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar(TcsBars::diag_full, s), 1);
-            mbar_init(bar(TcsBars::diag_empty, s), 4);
-            mbar_init(bar(TcsBars::dw_full, s), 4);
-            mbar_init(bar(TcsBars::a_full, s), 128);
-            mbar_init(bar(TcsBars::a_empty, s), 1);
+            mbar_init(bar(TcsBars::diag_empty, s), TCS_DW_ISSUERS);
+            mbar_init(bar(TcsBars::dw_full, s), TCS_DW_ISSUERS);
+            mbar_init(bar(TcsBars::dw_free, s), 128);
             mbar_init(bar(TcsBars::tfull, s), 1);
             mbar_init(bar(TcsBars::tempty, s), TCS_EPI_WARPS * 32);
+        }
+        for (int s = 0; s < TCS_MAX_A; ++s) {
+            mbar_init(bar(TcsBars::a_full, s), 128);
+            mbar_init(bar(TcsBars::a_empty, s), 1);
         }
         mbar_fence_init();
     }
@@ -199,228 +183,263 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(gen + g.off_bar + TcsBars::tmem_slot);
     long long *tr = blockIdx.x == 0 ? g_tcs_trace : nullptr;
     const int tr_cap = g_tcs_trace_cap;
-    const int per_img = g.bands * g.chunks;
+    // A operand of depthwise step (unit i, k-block kb): buffer index and how many times that buffer was used before
+    auto a_slot = [&](int i, int kb, int &ai, uint32_t &use) {
+        if (g.ring) {
+            const int d = i * g.kblocks + kb;
+            ai = d & 3;
+            use = (uint32_t)(d >> 2);
+        } else {
+            ai = kb;
+            use = (uint32_t)i;
+        }
+    };
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== patch producer =====================
         if (lane == 0) {
-            int ps = 0, ws = 0;
-            long long pstep = 0;
-            uint32_t pph = 0, wph = 0;
+            int ps = 0, d = 0;
+            uint32_t pph = 0;
             for (long long u = blockIdx.x; u < g.units; u += ustride) {
                 const int img = (int)(u / per_img), rem = (int)(u - (long long)img * per_img);
                 const int band = rem / g.chunks, chunk = rem - band * g.chunks;
                 const int row0 = (int)__umulhi((uint32_t)(chunk * 128), g.magic_wp);
                 const int x_org = band * g.tw - g.dil, y_org = row0 - g.dil;
+                for (int kb = 0; kb < g.kblocks; ++kb, ++d) {
+                    mbar_wait(bar(TcsBars::patch_empty, ps), pph ^ 1u);
+                    TCS_TR(0, d, 0);
+                    mbar_expect_tx(bar(TcsBars::patch_full, ps), g.patch_bytes);
+                    tma_load_4d(p_addr(ps), &tmap_x, bar(TcsBars::patch_full, ps), kb * 64, x_org, y_org, img);
+                    if (++ps == g.p_stages) { ps = 0; pph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 15) {
+        // ===================== W producer =====================
+        if (lane == 0) {
+            int ws = 0, s = 0;
+            uint32_t wph = 0;
+            for (int i = 0; i < my_units; ++i)
                 for (int nt = 0; nt < g.n_tiles; ++nt)
-                    for (int kb = 0; kb < g.kblocks; ++kb, ++pstep) {
-                        mbar_wait(bar(TcsBars::patch_empty, ps), pph ^ 1u);
-                        TCS_TR(0, pstep, 0);
-                        mbar_expect_tx(bar(TcsBars::patch_full, ps), g.patch_bytes);
-                        tma_load_4d(p_addr(ps), &tmap_x, bar(TcsBars::patch_full, ps), kb * 64, x_org, y_org, img);
-                        if (++ps == g.p_stages) { ps = 0; pph ^= 1u; }
+                    for (int kb = 0; kb < g.kblocks; ++kb, ++s) {
                         mbar_wait(bar(TcsBars::w_empty, ws), wph ^ 1u);
-                        TCS_TR(0, pstep, 1);
+                        TCS_TR(0, s, 1);
                         mbar_expect_tx(bar(TcsBars::w_full, ws), g.w_stage_bytes);
                         tma_load_2d(w_addr(ws), &tmap_w, bar(TcsBars::w_full, ws), kb * 64, nt * g.n_tile);
                         if (++ws == g.w_stages) { ws = 0; wph ^= 1u; }
                     }
-            }
         }
     } else if (warp == 1) {
         // ===================== pointwise MMA issuer (A operand in TMEM) =====================
-        if (lane == 0 && total_steps > 0) {
+        if (lane == 0) {
             const uint32_t idesc_n = tcs_idesc(g.n_tile);
             const uint64_t desc_hi = tcs_desc(0);
-            int pws = 0, kb = 0;
+            int pws = 0, s = 0, item = 0;
             uint32_t pwph = 0;
-            long long item = 0;
-            for (long long s = 0; s < total_steps; ++s) {
-                const int ab = (int)(s & 1);
-                const uint32_t aph = (uint32_t)(s >> 1) & 1u;
-                const int t = g.acc_bufs == 2 ? (int)(item & 1) : 0;
-                TCS_TR(1, s, 0);
-                if (kb == 0) tcs_wait(bar(TcsBars::tempty, t), ((uint32_t)(g.acc_bufs == 2 ? item >> 1 : item) & 1u) ^ 1u);
-                tcs_wait(bar(TcsBars::w_full, pws), pwph);
-                TCS_TR(1, s, 1);
-                tcs_wait(bar(TcsBars::a_full, ab), aph);
-                TCS_TR(1, s, 2);
-                tc_fence_after();
-                const uint32_t w0 = (w_addr(pws) & 0x3FFFF) >> 4;
-                const uint32_t acol = tmem + TCS_A_COL + (uint32_t)ab * 32u, ccol = tmem + (uint32_t)(t * g.n_tile);
+            for (int i = 0; i < my_units; ++i)
+                for (int nt = 0; nt < g.n_tiles; ++nt, ++item) {
+                    const int t = g.acc_bufs == 2 ? (item & 1) : 0;
+                    const uint32_t tuse = (uint32_t)(g.acc_bufs == 2 ? item >> 1 : item);
+                    for (int kb = 0; kb < g.kblocks; ++kb, ++s) {
+                        int ai;
+                        uint32_t use;
+                        a_slot(i, kb, ai, use);
+                        TCS_TR(1, s, 0);
+                        if (kb == 0) mbar_wait(bar(TcsBars::tempty, t), (tuse & 1u) ^ 1u);
+                        mbar_wait(bar(TcsBars::w_full, pws), pwph);
+                        TCS_TR(1, s, 1);
+                        mbar_wait(bar(TcsBars::a_full, ai), use & 1u);
+                        TCS_TR(1, s, 2);
+                        tc_fence_after();
+                        const uint32_t w0 = (w_addr(pws) & 0x3FFFF) >> 4;
+                        const uint32_t acol = tmem + (uint32_t)(g.a_col + ai * 32), ccol = tmem + (uint32_t)(t * g.n_tile);
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) tcs_mma_ts(ccol, acol + k4 * 8, desc_hi | (uint64_t)(w0 + k4 * 2), idesc_n, (kb > 0 || k4 > 0));
-                tc_commit(bar(TcsBars::a_empty, ab));
-                tc_commit(bar(TcsBars::w_empty, pws));
-                TCS_TR(1, s, 3);
-                if (++kb == g.kblocks) {
-                    kb = 0;
-                    tc_commit(bar(TcsBars::tfull, t));
-                    ++item;
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tcs_mma_ts(ccol, acol + k4 * 8, desc_hi | (uint64_t)(w0 + k4 * 2), idesc_n, (kb > 0 || k4 > 0));
+                        tc_commit(bar(TcsBars::w_empty, pws));
+                        if (g.ring || nt == g.n_tiles - 1) tc_commit(bar(TcsBars::a_empty, ai));
+                        if (kb == g.kblocks - 1) tc_commit(bar(TcsBars::tfull, t));
+                        TCS_TR(1, s, 3);
+                        if (++pws == g.w_stages) { pws = 0; pwph ^= 1u; }
+                    }
                 }
-                if (++pws == g.w_stages) { pws = 0; pwph ^= 1u; }
-            }
         }
-    } else if (warp >= 11) {
-        // ===================== depthwise MMA issuers: warp 11 + q owns the 16-channel group q of every k-block ==========
-        // (a single thread cannot issue 36 small MMAs per step fast enough: the tensor pipe needs 8 cycles for each)
-        if (lane == 0 && total_steps > 0) {
-            const int gq = warp - 11;
+    } else if (warp >= 16) {
+        // ===================== depthwise MMA issuers: warp 16 + w owns the 16-channel groups 2w and 2w + 1 =====================
+        if (lane == 0) {
+            const int w2 = warp - 16;
             const uint32_t idesc16 = tcs_idesc(16);
             uint32_t tap[9];                                     // tap shifts in 16-byte descriptor units
 #pragma unroll
-            for (int t = 0; t < 9; ++t) tap[t] = (uint32_t)((t / 3) * g.dil * g.wp + (t % 3) * g.dil) * 8u + (uint32_t)gq * 2u;
+            for (int t = 0; t < 9; ++t) tap[t] = (uint32_t)((t / 3) * g.dil * g.wp + (t % 3) * g.dil) * 8u + (uint32_t)w2 * 4u;
             const uint64_t desc_hi = tcs_desc(0);
-            int dps = 0;
+            int dps = 0, d = 0;
             uint32_t dpph = 0;
-            TcsCursor cd{blockIdx.x, 0, 0};
-            auto qoff_of = [&](long long u) {
-                const int rem = (int)(u % per_img);
-                const int chunk = rem % g.chunks;
+            for (long long u = blockIdx.x; u < g.units; u += ustride) {
+                const int chunk = (int)(u % per_img) % g.chunks;
                 const int row0 = (int)__umulhi((uint32_t)(chunk * 128), g.magic_wp);
-                return (uint32_t)(chunk * 128 - row0 * g.wp) * 8u;
-            };
-            uint32_t qoff = qoff_of(cd.unit);
-            for (long long s = 0; s < total_steps; ++s) {
-                const int db = (int)(s & 1);
-                const uint32_t dph = (uint32_t)(s >> 1) & 1u;
-                if (s >= 2) tcs_wait(bar(TcsBars::a_full, db), dph ^ 1u);     // the converters have read accumulator db (step s - 2)
-                if (gq == 0) TCS_TR(2, s, 0);
-                tcs_wait(bar(TcsBars::patch_full, dps), dpph);
-                if (gq == 0) TCS_TR(2, s, 1);
-                tcs_wait(bar(TcsBars::diag_full, db), dph);
-                if (gq == 0) TCS_TR(2, s, 2);
-                tc_fence_after();
-                const uint32_t a0 = ((p_addr(dps) & 0x3FFFF) >> 4) + qoff, b0 = ((d_addr(db) & 0x3FFFF) >> 4) + (uint32_t)gq * 2u;
-                const uint32_t dcol = tmem + TCS_DW_COL + (uint32_t)db * 64u + (uint32_t)gq * 16u;
+                const uint32_t qoff = (uint32_t)(chunk * 128 - row0 * g.wp) * 8u;
+                for (int kb = 0; kb < g.kblocks; ++kb, ++d) {
+                    const int db = d & 1;
+                    const uint32_t dph = (uint32_t)(d >> 1) & 1u;
+                    mbar_wait(bar(TcsBars::dw_free, db), dph ^ 1u);            // the converters have read accumulator db (step d - 2)
+                    if (w2 == 0) TCS_TR(2, d, 0);
+                    mbar_wait(bar(TcsBars::patch_full, dps), dpph);
+                    if (w2 == 0) TCS_TR(2, d, 1);
+                    mbar_wait(bar(TcsBars::diag_full, db), dph);
+                    if (w2 == 0) TCS_TR(2, d, 2);
+                    tc_fence_after();
+                    const uint32_t a0 = ((p_addr(dps) & 0x3FFFF) >> 4) + qoff, b0 = ((d_addr(db) & 0x3FFFF) >> 4) + (uint32_t)w2 * 4u;
+                    const uint32_t dcol = tmem + TCS_DW_COL + (uint32_t)db * 64u + (uint32_t)w2 * 32u;
 #pragma unroll
-                for (int t = 0; t < 9; ++t)
-                    tc_mma_bf16(dcol, desc_hi | (uint64_t)(a0 + tap[t]), desc_hi | (uint64_t)(b0 + t * 128), idesc16, t > 0);
-                tc_commit(bar(TcsBars::patch_empty, dps));
-                tc_commit(bar(TcsBars::diag_empty, db));
-                tc_commit(bar(TcsBars::dw_full, db));
-                if (gq == 0) TCS_TR(2, s, 3);
-                if (++dps == g.p_stages) { dps = 0; dpph ^= 1u; }
-                if (cd.next(g, ustride) && cd.unit < g.units) qoff = qoff_of(cd.unit);
+                    for (int gq = 0; gq < 2; ++gq)
+#pragma unroll
+                        for (int t = 0; t < 9; ++t)
+                            tc_mma_bf16(dcol + gq * 16, desc_hi | (uint64_t)(a0 + tap[t] + gq * 2), desc_hi | (uint64_t)(b0 + t * 128 + gq * 2),
+                                        idesc16, t > 0);
+                    tc_commit(bar(TcsBars::patch_empty, dps));
+                    tc_commit(bar(TcsBars::diag_empty, db));
+                    tc_commit(bar(TcsBars::dw_full, db));
+                    if (w2 == 0) TCS_TR(2, d, 3);
+                    if (++dps == g.p_stages) { dps = 0; dpph ^= 1u; }
+                }
             }
         }
     } else if (warp < 6) {
         // ===================== converters: depthwise accumulator -> A operand =====================
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t sdwb = base + g.off_dwb;
-        int kb = 0;
-        for (long long s = 0; s < total_steps; ++s) {
-            const int b = (int)(s & 1);
-            const uint32_t ph = (uint32_t)(s >> 1) & 1u;
-            tcs_wait(bar(TcsBars::dw_full, b), ph);
-            if (threadIdx.x == 64) TCS_TR(3, s, 0);
-            tc_fence_after();
-            uint32_t v[64], pk[32];
-            tc_ld32(tmem + lane_off + TCS_DW_COL + (uint32_t)b * 64u, v);
-            tc_ld32(tmem + lane_off + TCS_DW_COL + (uint32_t)b * 64u + 32u, v + 32);
-            tc_ld_wait();
+        int d = 0;
+        for (int i = 0; i < my_units; ++i)
+            for (int kb = 0; kb < g.kblocks; ++kb, ++d) {
+                const int b = d & 1;
+                int ai;
+                uint32_t use;
+                a_slot(i, kb, ai, use);
+                mbar_wait(bar(TcsBars::dw_full, b), (uint32_t)(d >> 1) & 1u);
+                if (threadIdx.x == 64) TCS_TR(3, d, 0);
+                tc_fence_after();
+                uint32_t v[32], pk[32];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float4 bb = tcs_lds_f4(sdwb + (uint32_t)(kb * 64 + j * 4) * 4u);
-                pk[2 * j] = relu6_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
-                pk[2 * j + 1] = relu6_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+                for (int hf = 0; hf < 2; ++hf) {
+                    tc_ld32(tmem + lane_off + TCS_DW_COL + (uint32_t)(b * 64 + hf * 32), v);
+                    tc_ld_wait();
+                    if (hf == 1) {                                  // accumulator b may be overwritten by depthwise step d + 2
+                        tc_fence_before();
+                        mbar_arrive(bar(TcsBars::dw_free, b));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bb = tcs_lds_f4(sdwb + (uint32_t)(kb * 64 + hf * 32 + j * 4) * 4u);
+                        pk[hf * 16 + 2 * j] = relu6_bf16x2(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y);
+                        pk[hf * 16 + 2 * j + 1] = relu6_bf16x2(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+                    }
+                }
+                if (threadIdx.x == 64) TCS_TR(3, d, 1);
+                mbar_wait(bar(TcsBars::a_empty, ai), (use & 1u) ^ 1u);       // the pointwise MMAs have read the previous content
+                if (threadIdx.x == 64) TCS_TR(3, d, 2);
+                tc_fence_after();
+                tcs_st32(tmem + lane_off + (uint32_t)(g.a_col + ai * 32), pk);
+                tcs_st_wait();
+                tc_fence_before();
+                mbar_arrive(bar(TcsBars::a_full, ai));
+                if (threadIdx.x == 64) TCS_TR(3, d, 3);
             }
-            if (threadIdx.x == 64) TCS_TR(3, s, 1);
-            tcs_wait(bar(TcsBars::a_empty, b), ph ^ 1u);
-            if (threadIdx.x == 64) TCS_TR(3, s, 2);
-            tc_fence_after();
-            tcs_st32(tmem + lane_off + TCS_A_COL + (uint32_t)b * 32u, pk);
-            tcs_st_wait();
-            tc_fence_before();
-            mbar_arrive(bar(TcsBars::a_full, b));
-            if (threadIdx.x == 64) TCS_TR(3, s, 3);
-            if (++kb == g.kblocks) kb = 0;
-        }
     } else if (warp < 6 + TCS_EPI_WARPS) {
         // ===================== epilogue =====================
-        const int ew = warp - 6, quad = warp & 3;
+        const int ew = warp - 6, quad = warp & 3, half = ew >> 2;
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const uint32_t stg = base + g.off_stg + (uint32_t)ew * TCS_STG_BYTES;
         const uint32_t spwb = base + g.off_pwb;
-        const int panels = g.n_tile / 64;
-        long long item = 0;
+        const int slabs = g.n_tile / 32;
+        int item = 0;
         for (long long u = blockIdx.x; u < g.units; u += ustride) {
             const int img = (int)(u / per_img), rem = (int)(u - (long long)img * per_img);
             const int band = rem / g.chunks, chunk = rem - band * g.chunks;
-            long long pix[8];                                     // element offset of the pixel this lane stores in pass i, or -1
+            long long pix[4];                                     // element offset of the pixel this lane stores in pass i, or -1
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t q = (uint32_t)(chunk * 128 + quad * 32 + i * 4 + (lane >> 3));
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t q = (uint32_t)(chunk * 128 + quad * 32 + i * 8 + (lane >> 2));
                 const int ty = (int)__umulhi(q, g.magic_wp), tx = (int)q - ty * g.wp;
                 const int gx = band * g.tw + tx;
                 pix[i] = (tx < g.tw && gx < g.w && ty < g.h) ? (((long long)img * g.h + ty) * g.w + gx) * g.nc : -1;
             }
             for (int nt = 0; nt < g.n_tiles; ++nt, ++item) {
-                const int t = g.acc_bufs == 2 ? (int)(item & 1) : 0;
-                const uint32_t ph = (uint32_t)(g.acc_bufs == 2 ? item >> 1 : item) & 1u;
-                mbar_wait(bar(TcsBars::tfull, t), ph);
+                const int t = g.acc_bufs == 2 ? (item & 1) : 0;
+                const uint32_t tuse = (uint32_t)(g.acc_bufs == 2 ? item >> 1 : item);
+                mbar_wait(bar(TcsBars::tfull, t), tuse & 1u);
                 if (threadIdx.x == 192) TCS_TR(5, item, 0);
                 tc_fence_after();
-                for (int p = 0; p < panels; ++p) {
-                    uint32_t v[64];
-                    const uint32_t col = tmem + lane_off + (uint32_t)(t * g.n_tile + p * 64);
-                    tc_ld32(col, v);
-                    tc_ld32(col + 32u, v + 32);
+                for (int sl = half; sl < slabs; sl += 2) {
+                    uint32_t v[32];
+                    tc_ld32(tmem + lane_off + (uint32_t)(t * g.n_tile + sl * 32), v);
                     tc_ld_wait();
-                    if (p + 1 == panels) {                        // this warp's last read of the accumulator
+                    if (sl + 2 >= slabs) {                        // this warp's last read of the accumulator
                         tc_fence_before();
                         mbar_arrive(bar(TcsBars::tempty, t));
                         if (threadIdx.x == 192) TCS_TR(5, item, 1);
                     }
-                    const uint32_t bcol = spwb + (uint32_t)(nt * g.n_tile + p * 64) * 4u;
-                    const uint32_t row = stg + (uint32_t)lane * 128u;
+                    const uint32_t bcol = spwb + (uint32_t)(nt * g.n_tile + sl * 32) * 4u;
+                    const uint32_t row = stg + (uint32_t)lane * 64u;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         const float4 b0 = tcs_lds_f4(bcol + (uint32_t)j * 32u), b1 = tcs_lds_f4(bcol + (uint32_t)j * 32u + 16u);
-                        st_shared_v4(row + (uint32_t)((j ^ (lane & 7)) * 16),
+                        st_shared_v4(row + (uint32_t)((j ^ ((lane >> 1) & 3)) * 16),
                                      relu6_bf16x2(__uint_as_float(v[8 * j]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y),
                                      relu6_bf16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w),
                                      relu6_bf16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y),
                                      relu6_bf16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w));
                     }
                     __syncwarp();
-                    const int ccol = nt * g.n_tile + p * 64 + (lane & 7) * 8;
+                    const int ccol = nt * g.n_tile + sl * 32 + (lane & 3) * 8;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + (lane >> 3);
-                        const uint4 val = ld_shared_v4(stg + (uint32_t)r * 128u + (uint32_t)(((lane & 7) ^ (r & 7)) * 16));
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = i * 8 + (lane >> 2);
+                        const uint4 val = ld_shared_v4(stg + (uint32_t)r * 64u + (uint32_t)(((lane & 3) ^ ((r >> 1) & 3)) * 16));
                         if (pix[i] >= 0) tcs_stg_v4(y + pix[i] + ccol, val);
                     }
                     __syncwarp();
                 }
+                if (threadIdx.x == 192) TCS_TR(5, item, 2);
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == 14) {
         // ===================== diagonal weight tiles =====================
-        const unsigned short *sdww = reinterpret_cast<const unsigned short *>(gen + g.off_dww);
-        int kb = 0;
-        for (long long s = 0; s < total_steps; ++s) {
-            const int db = (int)(s & 1);
-            const uint32_t ph = (uint32_t)(s >> 1) & 1u;
-            tcs_wait(bar(TcsBars::diag_empty, db), ph ^ 1u);
-            if (lane == 0) TCS_TR(4, s, 0);
-            if (g.kblocks > 2 || s < 2) {                         // with <= 2 k-blocks each buffer keeps its k-block for good
-                const uint32_t dst = d_addr(db);
+        // element idx = lane + 32 i (i < 18): tap t = i >> 1, group gq = 2 (i & 1) + (lane >> 4), row n = lane & 15
+        const int n = lane & 15, gq0 = lane >> 4;
+        const uint32_t sdww = base + g.off_dww;
+        const uint32_t dst_e = (uint32_t)(n * 128 + (((gq0 * 2 + (n >> 3)) ^ (n & 7)) * 16) + (n & 7) * 2);
+        const uint32_t dst_o = (uint32_t)(n * 128 + ((((gq0 + 2) * 2 + (n >> 3)) ^ (n & 7)) * 16) + (n & 7) * 2);
+        const uint32_t src_l = (uint32_t)(gq0 * 16 + n) * 2u;
+        int d = 0;
+        for (int i = 0; i < my_units; ++i)
+            for (int kb = 0; kb < g.kblocks; ++kb, ++d) {
+                const int db = d & 1;
+                mbar_wait(bar(TcsBars::diag_empty, db), ((uint32_t)(d >> 1) & 1u) ^ 1u);
+                if (lane == 0) TCS_TR(4, d, 0);
+                if (g.kblocks > 2 || d < 2) {                      // with <= 2 k-blocks each buffer keeps its k-block for good
+                    const uint32_t dst = d_addr(db);
+                    uint32_t src = sdww + src_l + (uint32_t)((g.kblocks == 1 ? 0 : kb) * 64) * 2u;
+                    uint32_t vals[18];
 #pragma unroll
-                for (int i = 0; i < 18; ++i) {
-                    const int idx = lane + 32 * i, t = idx >> 6, gq = (idx >> 4) & 3, n = idx & 15;
-                    const uint32_t val = sdww[t * g.k + (g.kblocks == 1 ? 0 : kb) * 64 + gq * 16 + n];
-                    tcs_sts_u16(dst + (uint32_t)(t * 2048 + n * 128 + (((gq * 2 + (n >> 3)) ^ (n & 7)) * 16) + (n & 7) * 2), val);
+                    for (int t = 0; t < 9; ++t) {
+                        vals[2 * t] = tcs_lds_u16(src);
+                        vals[2 * t + 1] = tcs_lds_u16(src + 64u);
+                        src += (uint32_t)g.k * 2u;
+                    }
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        tcs_sts_u16(dst + (uint32_t)t * 2048u + dst_e, vals[2 * t]);
+                        tcs_sts_u16(dst + (uint32_t)t * 2048u + dst_o, vals[2 * t + 1]);
+                    }
+                    fence_async_smem();
                 }
-                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar(TcsBars::diag_full, db));
+                    TCS_TR(4, d, 1);
+                }
             }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar(TcsBars::diag_full, db));
-                TCS_TR(4, s, 1);
-            }
-            if (++kb == g.kblocks) kb = 0;
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -429,11 +448,15 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
 
 // ---- host side ---------------------------------------------------------------------------------------------
 bool septc_supported(int k, int nc, int stride, int dil) {
-    return stride == 1 && (dil == 1 || dil == 2) && k % 64 == 0 && nc % 64 == 0 && k >= 64 && k <= 512 && nc >= 64 && nc <= 512;
+    if (!(stride == 1 && (dil == 1 || dil == 2) && k % 64 == 0 && nc % 64 == 0 && k >= 64 && k <= 512 && nc >= 64 && nc <= 512)) return false;
+    return nc <= 256 || nc % 128 == 0;                  // wider blocks run n-tiles of 128 over cached A operands (<= 8 k-blocks)
 }
+// Opt-in (PN_SEP_TC=1): measured on B200 the tap MMAs cost 55-70 cycles each (operand fetch: every M128 x N16 x K16 MMA re-reads
+// 4 KB of patch from shared memory), i.e. 2000-2600 cycles per 128 positions x 64 channels against ~1400 for the CUDA-core
+// depthwise of sepconv.cu, and they serialise with the pointwise MMAs on the one tensor pipe.
 bool septc_enabled() {
     const char *e = getenv("PN_SEP_TC");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
 }
 
 int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {
@@ -442,19 +465,17 @@ int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {
     memset(&g, 0, sizeof(g));
     g.k = k; g.nc = nc; g.h = h; g.w = wd; g.n_img = n; g.dil = dil;
     g.kblocks = k / 64;
-    // output-channel tile: the whole width when it fits one UMMA (<= 256), else the largest divisor that is a multiple of 64
-    g.n_tile = nc;
-    if (nc > 256) {
-        g.n_tile = 0;
-        for (int c = 256; c >= 64; c -= 64)
-            if (nc % c == 0) { g.n_tile = c; break; }
-    }
+    g.ring = nc <= 256;
+    g.n_tile = g.ring ? nc : 128;
     g.n_tiles = nc / g.n_tile;
-    g.acc_bufs = 2 * g.n_tile <= (int)TCS_DW_COL ? 2 : 1;
+    g.acc_bufs = (g.ring && g.n_tile <= 128) ? 2 : 1;
+    g.na = g.ring ? 4 : g.kblocks;
+    g.a_col = g.ring ? 256 : 128;
     g.w_stage_bytes = (unsigned)g.n_tile * 128u;
     const unsigned table_bytes = (unsigned)((9 * k * 2 + 15) / 16 * 16 + k * 4 + nc * 4);
     const long long fixed = 1024 + 2LL * TCS_DIAG_BYTES + (long long)TCS_EPI_WARPS * TCS_STG_BYTES + table_bytes + TcsBars::total;
-    // column bands: pitch wp = tw + 2 dil (one band over the whole width shares the zero gap: wp = w + dil)
+    // column bands: pitch wp = tw + 2 dil (one band over the whole width shares the zero gap: wp = w + dil).  Cost per unit in
+    // shared-memory cycles (128 B/clk): 9 tap reads of 128 rows + the patch write per k-block, W write + read per pointwise step.
     double best = 1e30;
     for (int bands = 1; bands <= 16; ++bands) {
         const int tw = ceil_div(wd, bands);
@@ -467,9 +488,8 @@ int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {
         const long long stage = (patch + 1023) / 1024 * 1024;
         if (fixed + 2 * stage + 2LL * g.w_stage_bytes > TCS_SMEM_MAX) continue;
         const int chunks = ceil_div((h - 1) * wp + tw, 128);
-        const double tensor = (double)g.kblocks * g.n_tiles * (288.0 + 2.0 * g.n_tile);
-        const double l2 = ((double)g.kblocks * g.n_tiles * (patch + g.w_stage_bytes) + 128.0 * nc * 2) / 64.0;
-        const double cost = (double)bands * chunks * (tensor > l2 ? tensor : l2);
+        const double per_unit = g.kblocks * (1152.0 + patch / 128.0) + (double)g.n_tiles * g.kblocks * (2.0 * g.w_stage_bytes / 128.0);
+        const double cost = (double)bands * chunks * per_unit;
         if (cost < best) {
             best = cost;
             g.bands = bands; g.tw = tw; g.wp = wp; g.rows_box = rows_box; g.chunks = chunks;
@@ -480,11 +500,11 @@ int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {
     g.magic_wp = (unsigned)((0x100000000ull + (unsigned)g.wp - 1) / (unsigned)g.wp);
     PN_CHECK_ARG((long long)g.chunks * 128 + 128 < (long long)(0x100000000ull / (unsigned)g.wp), "septc: image too large for the pitch division");
     g.units = (long long)n * g.bands * g.chunks;
-    // stages: patches first (the depthwise MMAs run one step ahead), then a third W stage
+    // stages: a third patch stage first (the TMA latency exceeds one depthwise step), then W stages, then a fourth patch stage
     g.p_stages = 2; g.w_stages = 2;
     auto total = [&](int ps, int ws) { return fixed + (long long)ps * g.patch_stage_bytes + (long long)ws * g.w_stage_bytes; };
     if (total(3, 2) <= TCS_SMEM_MAX) g.p_stages = 3;
-    if (total(g.p_stages, 3) <= TCS_SMEM_MAX) g.w_stages = 3;
+    while (g.w_stages < TCS_MAX_W && total(g.p_stages, g.w_stages + 1) <= TCS_SMEM_MAX) ++g.w_stages;
     if (g.p_stages == 3 && total(4, g.w_stages) <= TCS_SMEM_MAX) g.p_stages = 4;
     if (const char *force = getenv("PN_TCS_STAGES")) {
         int fp = 0, fw = 0;
@@ -545,8 +565,8 @@ int septc_launch(const SepTcOp *op, const float *dw_w, const float *dw_b, const 
 void septc_describe(const SepTcOp *op, char *out, size_t cap) {
     TcsGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    snprintf(out, cap, "tensor-pipe depthwise: bands %d x %d cols pitch %d box rows %d chunks %d n_tile %d x%d (acc bufs %d) kblocks %d stages p%d w%d smem %d units %lld",
-             g.bands, g.tw, g.wp, g.rows_box, g.chunks, g.n_tile, g.n_tiles, g.acc_bufs, g.kblocks, g.p_stages, g.w_stages, op->smem_bytes, g.units);
+    snprintf(out, cap, "tensor-pipe depthwise: bands %d x %d cols pitch %d box rows %d chunks %d n_tile %d x%d (acc bufs %d, A %s x%d) kblocks %d stages p%d w%d smem %d units %lld",
+             g.bands, g.tw, g.wp, g.rows_box, g.chunks, g.n_tile, g.n_tiles, g.acc_bufs, g.ring ? "ring" : "cache", g.na, g.kblocks, g.p_stages, g.w_stages, op->smem_bytes, g.units);
 }
 
 }  // namespace pn

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("POSENET_B200_LIB", os.path.join(_PKG_ROOT, "lib", "li
 PN_OK = 0
 PN_F32, PN_BF16 = 0, 1
 NUM_PARTS, NUM_EDGES, HEAD_CHANNELS, HEAD_ROWS = 17, 16, 115, 128
-ABI_VERSION = 3
+ABI_VERSION = 4
 PLAN_UNFUSED = 1
 
 
@@ -62,6 +62,8 @@ _SIGNATURES = {
     "pn_sepconv_describe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "pn_dwtc_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "pn_debug_tcs_trace": (C.c_int, [C.c_void_p, C.c_int]),
+    "pn_debug_umma_cost": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "pn_heads_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pn_candidates": (C.c_int, [C.POINTER(Map), C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p,

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = nat.load()                                       # raises if missing / symbol absent / ABI mismatch
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.pn_abi_version() == nat.ABI_VERSION == 3
+    assert lib.pn_abi_version() == nat.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header():
@@ -46,6 +46,21 @@ def test_sepconv_tile_geometry_is_host_computable():
             pad = ((s - 1) + 2 * d) // 2
             h = w = (h + 2 * pad - 2 * d - 1) // s + 1
     assert lib.pn_sepconv_describe(2, 9, 9, 64, 64, 2, 2, buf, 256) != 0            # never produced by the tables
+
+
+def test_tensor_pipe_depthwise_geometry_is_opt_in(monkeypatch):
+    """PN_SEP_TC=1 routes stride-1 blocks with 64-multiple widths (<= 512) to csrc/septc.cu; band layout is host arithmetic."""
+    import ctypes as C
+    lib, buf = nat.load(), C.create_string_buffer(512)
+    monkeypatch.delenv("PN_SEP_TC", raising=False)
+    assert lib.pn_sepconv_describe(64, 33, 33, 512, 512, 1, 1, buf, 512) == 0 and b"tensor-pipe" not in buf.value
+    monkeypatch.setenv("PN_SEP_TC", "1")
+    for shp, want in (((64, 33, 33, 512, 512, 1, 1), b"bands 1 x 33 cols pitch 34"), ((64, 129, 129, 128, 128, 1, 1), b"A ring x4"),
+                      ((32, 91, 161, 256, 256, 1, 2), b"tensor-pipe"), ((512, 17, 17, 384, 384, 1, 1), b"A cache x6")):
+        assert lib.pn_sepconv_describe(*shp, buf, 512) == 0, lib.pn_last_error_string()
+        assert b"tensor-pipe depthwise" in buf.value and want in buf.value, buf.value
+    for shp in ((64, 65, 65, 256, 512, 2, 1), (64, 257, 257, 32, 64, 1, 1), (2, 33, 33, 1024, 1024, 1, 2), (3, 65, 65, 96, 96, 1, 1)):
+        assert lib.pn_sepconv_describe(*shp, buf, 512) == 0 and b"tensor-pipe" not in buf.value     # stride 2, narrow, wide, ragged
 
 
 @pytest.mark.parametrize("mid", [50, 75, 100, 101])

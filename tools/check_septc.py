@@ -9,6 +9,8 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "posenet-pytorch_b200"), os.path.join(ROOT, "tests"), ROOT]
 import torch
+
+os.environ.setdefault("PN_SEP_TC", "1")          # the path under test is opt-in
 import torch.nn.functional as F
 import abi
 from posenet import _native as nat

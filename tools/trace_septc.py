@@ -6,6 +6,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "posenet-pytorch_b200"), os.path.join(ROOT, "tests"), ROOT]
 import torch
+
+os.environ.setdefault("PN_SEP_TC", "1")          # the path under test is opt-in
 import abi
 from posenet import _native as nat
 
@@ -30,8 +32,8 @@ torch.cuda.synchronize()
 lib.pn_debug_tcs_trace(None, 0)
 t = buf.cpu().numpy()
 t0 = t[t > 0].min()
-names = ["producer: patch_empty ok | w_empty ok", "pw issuer: start | w_full | a_full | issued", "dw issuer0: a_full(s-2) | patch_full | diag_full | issued",
-         "converter: dw_full | math done | a_empty | arrived", "diag writer: diag_empty | done", "epilogue(item): tfull | released"]
+names = ["producers: patch_empty ok (d) | w_empty ok (s)", "pw issuer (s): start | tempty+w_full | a_full | issued", "dw issuer0 (d): dw_free | patch_full | diag_full | issued",
+         "converter (d): dw_full | math done | a_empty | arrived", "diag writer (d): diag_empty | done", "epilogue (item): tfull | released | done"]
 for s in range(lo, hi):
     print("step %d" % s)
     for r in range(6):
