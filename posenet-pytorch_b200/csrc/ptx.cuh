@@ -44,6 +44,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Wait for roles with slack (an epilogue behind a double-buffered accumulator): poll, and on failure sleep `ns` nanoseconds.
+// The suspend-time hint of mbar_wait returns after a few tens of cycles on sm_100, so four idle epilogue warps re-polling
+// cost ~13 % of all issued instructions of an issue-bound fused block (ncu source view); a real sleep makes the wait free at the
+// price of <= `ns` of hand-off latency.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns) {
+    for (uint32_t polls = 0;; ++polls) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+        if (polls > 20000000u) {
+            printf("posenet_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+
 // ---- TMA ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

@@ -53,6 +53,7 @@ struct SepGeom {
     int kblocks;
     int half, cbox;                       // K <= 32: two pixel columns per warp (16 lanes each), 32-channel patch box
     int cl;                               // CTAs per cluster (1, 2, 4): each owns 256 output channels and 1 / cl of the k-blocks
+    unsigned epi_sleep_ns;                // sleep between the epilogue's polls of its accumulator barrier (PN_SEP_EPI_SLEEP, default 200)
     int p_stages, w_stages, a_stages, stg_bufs;
     unsigned patch_stage_bytes, patch_box_bytes, wgt_off, w_stage_bytes;
     unsigned off_a, off_stg, off_patch, off_bias, off_bar;   // from the 1024-aligned base; W stages sit at 0
@@ -387,7 +388,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             const int img = m_tile / m_tiles_per_img;
             const int rem = m_tile - img * m_tiles_per_img;
             const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
-            mbar_wait(bar(SepBars::tfull, acc), acc_phase);
+            mbar_wait_backoff(bar(SepBars::tfull, acc), acc_phase, g.epi_sleep_ns);   // idle epilogue warps must not eat issue slots
             tc_fence_after();
             if (issuer) SEP_TRACE(2, tr_e, 0);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * g.n_tile);
@@ -800,6 +801,8 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
             g.p_stages = fp; g.w_stages = fw; g.a_stages = fa; g.stg_bufs = fs;
         }
     }
+    g.epi_sleep_ns = 200;
+    if (const char *e = getenv("PN_SEP_EPI_SLEEP")) g.epi_sleep_ns = (unsigned)atoi(e);
     static_assert(SepBars::total <= 640, "barrier block exceeds its reserve");
     g.off_a = (unsigned)g.w_stages * g.w_stage_bytes;
     g.off_stg = g.off_a + (unsigned)g.a_stages * SEP_A_BYTES;

@@ -1,8 +1,9 @@
 """``load_model`` with the reference's signature (posenet/models/model_factory.py:11-23).
 
-The reference converts TF.js checkpoints from the network when the ``.pth`` is missing; there is
-no network here, so a missing file is an error that names the helper which writes seeded
-random-init weights (``write_random_checkpoint``) -- the weights every parity test uses.
+The reference downloads and converts TF.js checkpoints when the ``.pth`` is missing; here the conversion
+(``posenet.converter.tfjs2pytorch``) runs when the TF.js files are already on disk, and otherwise a missing
+file is an error that names the helper which writes seeded random-init weights
+(``write_random_checkpoint``) -- the weights every parity test uses.
 """
 import math
 import os
@@ -17,6 +18,12 @@ DEBUG_OUTPUT = False
 
 def load_model(model_id, output_stride=16, model_dir=MODEL_DIR):
     path = os.path.join(model_dir, MOBILENET_V1_CHECKPOINTS[model_id] + '.pth')
+    if not os.path.exists(path):
+        from posenet.converter import tfjs2pytorch
+        manifest = os.path.join(tfjs2pytorch.BASE_DIR, MOBILENET_V1_CHECKPOINTS[model_id], "manifest.json")
+        if os.path.exists(manifest):                               # the reference's fallback (model_factory.py:13-17), minus the download
+            print('Cannot find models file %s, converting from tfjs...' % path)
+            tfjs2pytorch.convert(model_id, model_dir, check=False)
     if not os.path.exists(path):
         raise FileNotFoundError(
             "Cannot find model file %s. TF.js checkpoint conversion needs network access; write seeded "

@@ -118,8 +118,55 @@ def make_decode():
     np.savez_compressed(os.path.join(HERE, "decode.npz"), **out)
 
 
+def make_converter_names():
+    """The reference's TF.js -> torch variable-name mapping (converter/tfjs2pytorch.py:15-43) on every variable name of a
+    PoseNet MobileNetV1 manifest (14 conv layers, 4 heads, plus names the converter must skip) -> converter_names.json.
+    Also runs the reference's load_variables on a synthetic checkpoint and records a checksum of every converted tensor
+    (the layout transposes, tfjs2pytorch.py:46-72) -> converter_tensors.json."""
+    import json
+    import tempfile
+    from posenet.converter import tfjs2pytorch as ref_conv
+    names = ["MobilenetV1/Conv2d_0/weights", "MobilenetV1/Conv2d_0/biases"]
+    for i in range(1, 14):
+        names += ["MobilenetV1/Conv2d_%d_depthwise/depthwise_weights" % i, "MobilenetV1/Conv2d_%d_depthwise/biases" % i,
+                  "MobilenetV1/Conv2d_%d_pointwise/weights" % i, "MobilenetV1/Conv2d_%d_pointwise/biases" % i]
+    for head in ("heatmap", "offset", "displacement_fwd", "displacement_bwd"):
+        names += ["MobilenetV1/%s_2/weights" % head, "MobilenetV1/%s_2/biases" % head]
+    names += ["MobilenetV1/heatmap_1/weights", "MobilenetV1/segment_2/weights", "MobilenetV1/partheat_2/biases",
+              "MobilenetV1/Conv2d_3_pointwise/Relu6", "MobilenetV1/displacement_fwd_1/biases", "MobilenetV1/Logits/weights"]
+    table = {n: ref_conv.to_torch_name(n) for n in names}
+    with open(os.path.join(HERE, "converter_names.json"), "w") as f:
+        json.dump(table, f, indent=0, sort_keys=True)
+    # synthetic checkpoint for model 50: values = a seeded ramp per variable, written in TF layouts
+    rng = np.random.default_rng(7)
+    sd_shapes = {k: tuple(v.shape) for k, v in ref.MobileNetV1(50).state_dict().items()}
+    with tempfile.TemporaryDirectory() as tmp:
+        ck = os.path.join(tmp, "mobilenet_v1_050")
+        os.makedirs(ck)
+        manifest, inv = {}, {v: k for k, v in table.items() if v}
+        for key, shp in sd_shapes.items():
+            tfn = inv[key]
+            if len(shp) == 4:
+                tf_shape = [shp[2], shp[3], shp[0], shp[1]] if "depthwise" in tfn else [shp[2], shp[3], shp[1], shp[0]]
+            else:
+                tf_shape = list(shp)
+            fn = tfn.replace("/", "_")
+            rng.standard_normal(tf_shape).astype("<f4").tofile(os.path.join(ck, fn))
+            manifest[tfn] = {"filename": fn, "shape": tf_shape}
+        json.dump(manifest, open(os.path.join(ck, "manifest.json"), "w"))
+        out = ref_conv.load_variables("mobilenet_v1_050", tmp)
+    sums = {k: [list(v.shape), sha(v.numpy())] for k, v in out.items()}
+    with open(os.path.join(HERE, "converter_tensors.json"), "w") as f:
+        json.dump(sums, f, indent=0, sort_keys=True)
+    print("converter: %d names, %d tensors" % (len(table), len(sums)))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if "--converter-only" in sys.argv:
+        make_converter_names()
+        sys.exit(0)
     make_preprocess()
     make_net()
     make_decode()
+    make_converter_names()
