@@ -33,7 +33,10 @@
 
 namespace pn {
 
-constexpr int SEP_DW_WARPS = 10;
+#ifndef PN_SEP_DW_WARPS
+#define PN_SEP_DW_WARPS 10
+#endif
+constexpr int SEP_DW_WARPS = PN_SEP_DW_WARPS;
 constexpr int SEP_FIRST_DW_WARP = 6;
 constexpr int SEP_THREADS = (SEP_FIRST_DW_WARP + SEP_DW_WARPS) * 32;   // 512
 constexpr int SEP_MAX_A = 6;
