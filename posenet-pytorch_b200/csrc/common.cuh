@@ -179,7 +179,8 @@ struct SepTcOp {
     int smem_bytes;
 };
 bool septc_supported(int k, int nc, int stride, int dil);
-bool septc_enabled();      // PN_SEP_TC=1 opts in (slower than the CUDA-core depthwise of sepconv.cu on B200, see septc.cu)
+bool septc_enabled();      // PN_SEP_TC=0 turns the path off
+bool septc_preferred(int k, int nc, int stride, int dil);   // default: the 256 -> 256 blocks only (measured); PN_SEP_TC=1: every supported block
 int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil);
 int septc_prepare(SepTcOp *op, const void *x, const void *pw_w, int n, int h, int wd, int k, int nc, int dil);
 int septc_launch(const SepTcOp *op, const float *dw_w, const float *dw_b, const float *pw_b, void *y, cudaStream_t s);

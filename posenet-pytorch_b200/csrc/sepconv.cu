@@ -636,7 +636,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
         op->n = n; op->h = h; op->w = wd; op->k = k; op->nc = nc;
         return PN_OK;
     }
-    if (septc_enabled() && septc_supported(k, nc, stride, dil)) {   // depthwise on the tensor pipe
+    if (septc_preferred(k, nc, stride, dil)) {                      // depthwise on the tensor pipe (septc.cu)
         op->tc_kind = true;
         op->stride = stride; op->dil = dil;
         op->ho = h; op->wo = wd;

@@ -451,12 +451,21 @@ bool septc_supported(int k, int nc, int stride, int dil) {
     if (!(stride == 1 && (dil == 1 || dil == 2) && k % 64 == 0 && nc % 64 == 0 && k >= 64 && k <= 512 && nc >= 64 && nc <= 512)) return false;
     return nc <= 256 || nc % 128 == 0;                  // wider blocks run n-tiles of 128 over cached A operands (<= 8 k-blocks)
 }
-// Opt-in (PN_SEP_TC=1): measured on B200 the tap MMAs cost 55-70 cycles each (operand fetch: every M128 x N16 x K16 MMA re-reads
-// 4 KB of patch from shared memory), i.e. 2000-2600 cycles per 128 positions x 64 channels against ~1400 for the CUDA-core
-// depthwise of sepconv.cu, and they serialise with the pointwise MMAs on the one tensor pipe.
+// Which blocks take this path.  Measured on B200 (profiles/r01_v9_septc_experiment.md): a tap MMA costs 32 + N/4 cycles (operand
+// fetch: every M128 x N16 x K16 MMA re-reads 4 KB of patch from shared memory), so the depthwise is no cheaper here than on the
+// CUDA cores and it serialises with the pointwise MMAs on the one tensor pipe.  It wins where the CUDA-core kernel is at its
+// weakest and this one at its best -- 256 -> 256 blocks (one 256-column n-tile, A ring): 0.178 vs 0.203 ms on the dilated blocks of
+// model 50 at OS8 (C3), 0.104 vs 0.107 ms on block 5 of model 101 (C2) -- and loses elsewhere (128 -> 128: 0.199 vs 0.186 ms,
+// 512 -> 512: 0.096 vs 0.073 ms).  PN_SEP_TC=1 forces it for every supported block, PN_SEP_TC=0 turns it off.
 bool septc_enabled() {
     const char *e = getenv("PN_SEP_TC");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
+}
+bool septc_preferred(int k, int nc, int stride, int dil) {
+    if (!septc_enabled() || !septc_supported(k, nc, stride, dil)) return false;
+    const char *e = getenv("PN_SEP_TC");
+    if (e && e[0] == '1') return true;
+    return k == 256 && nc == 256;
 }
 
 int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {

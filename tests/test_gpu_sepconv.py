@@ -49,8 +49,15 @@ def test_sepconv_block(shape):
     n, h, w, cin, cout, stride, dil = shape
     x, wd, bd, wp, bp = make(n, h, w, cin, cout, seed=h * 7 + cin + stride + dil)
     pad = ((stride - 1) + 2 * dil) // 2
+    # 256 -> 256 blocks run the depthwise on the tensor pipe by default (csrc/septc.cu): its depthwise weights are bf16
+    import ctypes as C
+    buf = C.create_string_buffer(512)
+    assert nat.load().pn_sepconv_describe(n, h, w, cin, cout, stride, dil, buf, 512) == 0
+    tensor_pipe = b"tensor-pipe" in buf.value
+    assert tensor_pipe == (cin == 256 and cout == 256 and stride == 1 and dil <= 2)
+    wd_k = wd.to(torch.bfloat16).float() if tensor_pipe else wd
     # torch fp32 reference with the kernel's rounding points
-    t = F.relu6(F.conv2d(x.float().permute(0, 3, 1, 2), wd, bd, stride=stride, padding=pad, dilation=dil, groups=cin))
+    t = F.relu6(F.conv2d(x.float().permute(0, 3, 1, 2), wd_k, bd, stride=stride, padding=pad, dilation=dil, groups=cin))
     t = t.to(torch.bfloat16).float()
     ref = F.relu6(F.conv2d(t, wp.float().reshape(cout, cin, 1, 1), bp)).permute(0, 2, 3, 1)
 
@@ -68,8 +75,11 @@ def test_sepconv_block(shape):
     t2 = abi.dwconv(xd, w9, bdd, stride, dil, nat.PN_BF16)
     y2 = abi.pwconv(t2.reshape(-1, cin), wpd, bpd, nat.PN_BF16).reshape(y.shape)
     diff = (y.float() - y2.float()).abs()
-    assert float(diff.max()) <= 0.0625, float(diff.max())                       # <= 1 bf16 ulp at magnitude <= 6
-    assert float((diff > 0).float().mean()) < 1e-3
+    if tensor_pipe:                                                             # fp32 vs bf16 depthwise weights: a few ulps
+        assert float(diff.max() / y2.float().abs().max()) < 1.5e-2
+    else:
+        assert float(diff.max()) <= 0.0625, float(diff.max())                   # <= 1 bf16 ulp at magnitude <= 6
+        assert float((diff > 0).float().mean()) < 1e-3
 
     y3 = abi.sepconv(xd, w9, bdd, wpd, bpd, stride, dil)
     assert torch.equal(y, y3)
@@ -98,9 +108,12 @@ def test_fused_plan_matches_unfused_plan(mid, os_, H, W, N):
     n_unfused = m.num_launches(N, H, W)
     wide = sum(1 for L in m._layers[1:] if L["outp"] > 512)      # blocks wider than one 512-column tile stay two kernels
     assert (n_fused, n_unfused) == (15 + wide, 28)
+    # blocks with 256 -> 256 channels take the tensor-pipe depthwise, whose depthwise weights are rounded to bf16
+    tc_blocks = sum(1 for L in m._layers[1:] if L["inp"] == 256 and L["outp"] == 256 and L["stride"] == 1 and L["rate"] <= 2)
     for a, b in zip(fused, unfused):
         err = float((a - b).abs().max() / b.abs().max())
-        assert err < 2e-3, err
+        print("fused vs unfused: model %d, %d tensor-pipe blocks, err %.3g" % (mid, tc_blocks, err))
+        assert err < (6e-3 if tc_blocks else 2e-3), err
 
 
 def test_cluster_variant_opt_in():

@@ -1,4 +1,4 @@
-"""Depthwise on the tensor pipe (csrc/septc.cu, opt-in PN_SEP_TC=1) through the C ABI on the B200.
+"""Depthwise on the tensor pipe (csrc/septc.cu; default for 256 -> 256 blocks, PN_SEP_TC=1 forces it for every supported block) through the C ABI on the B200.
 
 (1) pn_dwtc_probe: the hardware behaviours the kernel relies on -- a SWIZZLE_128B UMMA descriptor advanced by whole 128-byte
     rows reads a shifted view of the TMA-written patch (depthwise taps; equal to numpy fp32 up to rare one-ulp flips of the bf16 rounding), and tcgen05.mma takes
@@ -116,8 +116,11 @@ def test_sepconv_block_on_the_tensor_pipe(shape, monkeypatch):
     assert torch.equal(y, y2)                                # deterministic
 
 
-def test_default_path_is_the_cuda_core_depthwise(monkeypatch):
-    monkeypatch.delenv("PN_SEP_TC", raising=False)
+def test_default_policy(monkeypatch):
+    """Unset: only the 256 -> 256 blocks (where it measured faster) take the tensor-pipe depthwise; PN_SEP_TC=0: none."""
     buf = C.create_string_buffer(512)
-    assert nat.load().pn_sepconv_describe(2, 33, 33, 512, 512, 1, 1, buf, 512) == 0
-    assert b"tensor-pipe" not in buf.value
+    monkeypatch.delenv("PN_SEP_TC", raising=False)
+    assert nat.load().pn_sepconv_describe(2, 33, 33, 512, 512, 1, 1, buf, 512) == 0 and b"tensor-pipe" not in buf.value
+    assert nat.load().pn_sepconv_describe(2, 91, 161, 256, 256, 1, 2, buf, 512) == 0 and b"tensor-pipe" in buf.value
+    monkeypatch.setenv("PN_SEP_TC", "0")
+    assert nat.load().pn_sepconv_describe(2, 91, 161, 256, 256, 1, 2, buf, 512) == 0 and b"tensor-pipe" not in buf.value

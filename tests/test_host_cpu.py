@@ -42,18 +42,21 @@ def test_sepconv_tile_geometry_is_host_computable():
             s, d = L["stride"], L["rate"]
             if L["block_id"]:
                 assert lib.pn_sepconv_describe(2, h, w, L["inp"], L["outp"], s, d, buf, 256) == 0, lib.pn_last_error_string()
-                assert b"tile" in buf.value or b"warp-autonomous strips" in buf.value
+                assert b"tile" in buf.value or b"warp-autonomous strips" in buf.value or b"tensor-pipe" in buf.value
             pad = ((s - 1) + 2 * d) // 2
             h = w = (h + 2 * pad - 2 * d - 1) // s + 1
     assert lib.pn_sepconv_describe(2, 9, 9, 64, 64, 2, 2, buf, 256) != 0            # never produced by the tables
 
 
-def test_tensor_pipe_depthwise_geometry_is_opt_in(monkeypatch):
+def test_tensor_pipe_depthwise_policy_and_geometry(monkeypatch):
     """PN_SEP_TC=1 routes stride-1 blocks with 64-multiple widths (<= 512) to csrc/septc.cu; band layout is host arithmetic."""
     import ctypes as C
     lib, buf = nat.load(), C.create_string_buffer(512)
-    monkeypatch.delenv("PN_SEP_TC", raising=False)
+    monkeypatch.delenv("PN_SEP_TC", raising=False)                  # default policy: the 256 -> 256 blocks only
     assert lib.pn_sepconv_describe(64, 33, 33, 512, 512, 1, 1, buf, 512) == 0 and b"tensor-pipe" not in buf.value
+    assert lib.pn_sepconv_describe(32, 91, 161, 256, 256, 1, 2, buf, 512) == 0 and b"tensor-pipe" in buf.value
+    monkeypatch.setenv("PN_SEP_TC", "0")
+    assert lib.pn_sepconv_describe(32, 91, 161, 256, 256, 1, 2, buf, 512) == 0 and b"tensor-pipe" not in buf.value
     monkeypatch.setenv("PN_SEP_TC", "1")
     for shp, want in (((64, 33, 33, 512, 512, 1, 1), b"bands 1 x 33 cols pitch 34"), ((64, 129, 129, 128, 128, 1, 1), b"A ring x4"),
                       ((32, 91, 161, 256, 256, 1, 2), b"tensor-pipe"), ((512, 17, 17, 384, 384, 1, 1), b"A cache x6")):
