@@ -45,6 +45,27 @@ def peaks():
     return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")   # B200_PROFILING.md
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that the pinned host batches of the end-to-end leg are
+    allocated on the GPU's NUMA node and the H2D copies of 8 ranks do not all cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[index]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        before = set(os.sched_getaffinity(0))
+        cpus &= before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "gpu-local cpus (%d of %d)" % (len(cpus), len(before)), before
+    except Exception:
+        pass
+    return "unchanged", None
+
+
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons sampled DURING the timed region.  NVML is polled in-process (a reading takes
     ~0.1 ms, so even a 15 ms timed region holds dozens); `nvidia-smi` (one reading per ~100 ms) is the fallback
@@ -210,6 +231,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity, all_cpus = bind_to_gpu_numa_node(local)            # before any pinned allocation (first touch decides the NUMA node)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -349,6 +371,8 @@ def run_b200(args):
                 "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": traffic,
                 "algorithmic_bytes": next(nb for nm, nb, _ in costs if nm == top["name"]),
                 "peak_source": pk["src"] + (" (sustained)" if top["bound"] == "tensor" else "")}
+    if all_cpus:
+        os.sched_setaffinity(0, all_cpus)                        # the CPU baseline gets every host core again
     cpu = cpu_reference_run("c2" if args.workload == "c2" else args.workload, images_per_step=4, steps=3, warmup=1) \
         if (world == 1 and not args.skip_cpu) else None
     launches = model.num_launches(batch, H, W, True) + 2
@@ -358,7 +382,7 @@ def run_b200(args):
             "config": {"workload": desc, "batch_per_gpu": batch, "decode": DECODE_KW, "weights": "random-init (torch default, seed 0)",
                        "l2": "inputs rotate over %d batches (%d MB > 126 MB L2); per-step activation traffic >> L2" % (
                            n_sets, n_sets * host[0].numel() // 2 ** 20), "cuda_graph": True,
-                       "fused_blocks": bool(model.fused_blocks)},
+                       "fused_blocks": bool(model.fused_blocks), "cpu_affinity": affinity},
             "e2e": e2e, "gpu_launches": launches * args.steps, "clocks": clocks, "roofline": roofline,
             "kernels": kernels, "forward_ms_sum_of_kernels": round(total_ms, 3)}
     if cpu:
