@@ -24,6 +24,9 @@ def short(n):
 idx = [i for i, n in enumerate(names) if "stem" in n]
 start = idx[-2] if len(idx) >= 2 else idx[-1]
 end = idx[-1] if len(idx) >= 2 else len(names)
+dec = [i for i in range(start, end) if "decode_kernel" in names[i]]
+if dec:
+    end = dec[0] + 1                       # what follows the decode kernel belongs to the next phase of bench.py, not to the step
 step = list(zip(names[start:end], vals[start:end]))
 tot = sum(v for _, v in step)
 out += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, tools/gpu_profile.sh)", "",
@@ -41,7 +44,8 @@ hdr, data = rr[0], rr[2:]
 col = lambda n: hdr.index(n)
 M = [("gpu__time_duration.sum", "time us"), ("dram__bytes_read.sum", "dram rd MB"), ("dram__bytes_write.sum", "dram wr MB"),
      ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram %"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
-     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem pipe %"),
+     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem pipe (LSU) %"),
+     ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem pipe (tensor operands) %"),
      ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
      ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"), ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid")]
 out += ["## `ncu --set full --clock-control none --import-source on` (first forward of the process; %d kernels)" % len(data), "",
