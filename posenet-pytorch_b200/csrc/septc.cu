@@ -58,6 +58,7 @@ struct TcsGeom {
     unsigned patch_bytes, patch_stage_bytes, w_stage_bytes;
     unsigned off_diag, off_patch, off_stg, off_dww, off_dwb, off_pwb, off_bar;
     unsigned magic_wp;
+    unsigned sleep_ns[5];                               // poll backoff per role: producers, MMA issuers, converters, epilogue, diag writer
     long long units;
 };
 
@@ -206,7 +207,7 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                 const int row0 = (int)__umulhi((uint32_t)(chunk * 128), g.magic_wp);
                 const int x_org = band * g.tw - g.dil, y_org = row0 - g.dil;
                 for (int kb = 0; kb < g.kblocks; ++kb, ++d) {
-                    mbar_wait(bar(TcsBars::patch_empty, ps), pph ^ 1u);
+                    mbar_wait_backoff(bar(TcsBars::patch_empty, ps), pph ^ 1u, g.sleep_ns[0]);
                     TCS_TR(0, d, 0);
                     mbar_expect_tx(bar(TcsBars::patch_full, ps), g.patch_bytes);
                     tma_load_4d(p_addr(ps), &tmap_x, bar(TcsBars::patch_full, ps), kb * 64, x_org, y_org, img);
@@ -222,7 +223,7 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
             for (int i = 0; i < my_units; ++i)
                 for (int nt = 0; nt < g.n_tiles; ++nt)
                     for (int kb = 0; kb < g.kblocks; ++kb, ++s) {
-                        mbar_wait(bar(TcsBars::w_empty, ws), wph ^ 1u);
+                        mbar_wait_backoff(bar(TcsBars::w_empty, ws), wph ^ 1u, g.sleep_ns[0]);
                         TCS_TR(0, s, 1);
                         mbar_expect_tx(bar(TcsBars::w_full, ws), g.w_stage_bytes);
                         tma_load_2d(w_addr(ws), &tmap_w, bar(TcsBars::w_full, ws), kb * 64, nt * g.n_tile);
@@ -245,10 +246,10 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                         uint32_t use;
                         a_slot(i, kb, ai, use);
                         TCS_TR(1, s, 0);
-                        if (kb == 0) mbar_wait(bar(TcsBars::tempty, t), (tuse & 1u) ^ 1u);
-                        mbar_wait(bar(TcsBars::w_full, pws), pwph);
+                        if (kb == 0) mbar_wait_backoff(bar(TcsBars::tempty, t), (tuse & 1u) ^ 1u, g.sleep_ns[1]);
+                        mbar_wait_backoff(bar(TcsBars::w_full, pws), pwph, g.sleep_ns[1]);
                         TCS_TR(1, s, 1);
-                        mbar_wait(bar(TcsBars::a_full, ai), use & 1u);
+                        mbar_wait_backoff(bar(TcsBars::a_full, ai), use & 1u, g.sleep_ns[1]);
                         TCS_TR(1, s, 2);
                         tc_fence_after();
                         const uint32_t w0 = (w_addr(pws) & 0x3FFFF) >> 4;
@@ -282,11 +283,11 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                 for (int kb = 0; kb < g.kblocks; ++kb, ++d) {
                     const int db = d & 1;
                     const uint32_t dph = (uint32_t)(d >> 1) & 1u;
-                    mbar_wait(bar(TcsBars::dw_free, db), dph ^ 1u);            // the converters have read accumulator db (step d - 2)
+                    mbar_wait_backoff(bar(TcsBars::dw_free, db), dph ^ 1u, g.sleep_ns[1]);            // the converters have read accumulator db (step d - 2)
                     if (w2 == 0) TCS_TR(2, d, 0);
-                    mbar_wait(bar(TcsBars::patch_full, dps), dpph);
+                    mbar_wait_backoff(bar(TcsBars::patch_full, dps), dpph, g.sleep_ns[1]);
                     if (w2 == 0) TCS_TR(2, d, 1);
-                    mbar_wait(bar(TcsBars::diag_full, db), dph);
+                    mbar_wait_backoff(bar(TcsBars::diag_full, db), dph, g.sleep_ns[1]);
                     if (w2 == 0) TCS_TR(2, d, 2);
                     tc_fence_after();
                     const uint32_t a0 = ((p_addr(dps) & 0x3FFFF) >> 4) + qoff, b0 = ((d_addr(db) & 0x3FFFF) >> 4) + (uint32_t)w2 * 4u;
@@ -316,7 +317,7 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                 int ai;
                 uint32_t use;
                 a_slot(i, kb, ai, use);
-                mbar_wait(bar(TcsBars::dw_full, b), (uint32_t)(d >> 1) & 1u);
+                mbar_wait_backoff(bar(TcsBars::dw_full, b), (uint32_t)(d >> 1) & 1u, g.sleep_ns[2]);
                 if (threadIdx.x == 64) TCS_TR(3, d, 0);
                 tc_fence_after();
                 uint32_t v[32], pk[32];
@@ -336,7 +337,7 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                     }
                 }
                 if (threadIdx.x == 64) TCS_TR(3, d, 1);
-                mbar_wait(bar(TcsBars::a_empty, ai), (use & 1u) ^ 1u);       // the pointwise MMAs have read the previous content
+                mbar_wait_backoff(bar(TcsBars::a_empty, ai), (use & 1u) ^ 1u, g.sleep_ns[2]);       // the pointwise MMAs have read the previous content
                 if (threadIdx.x == 64) TCS_TR(3, d, 2);
                 tc_fence_after();
                 tcs_st32(tmem + lane_off + (uint32_t)(g.a_col + ai * 32), pk);
@@ -367,7 +368,7 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
             for (int nt = 0; nt < g.n_tiles; ++nt, ++item) {
                 const int t = g.acc_bufs == 2 ? (item & 1) : 0;
                 const uint32_t tuse = (uint32_t)(g.acc_bufs == 2 ? item >> 1 : item);
-                mbar_wait(bar(TcsBars::tfull, t), tuse & 1u);
+                mbar_wait_backoff(bar(TcsBars::tfull, t), tuse & 1u, g.sleep_ns[3]);
                 if (threadIdx.x == 192) TCS_TR(5, item, 0);
                 tc_fence_after();
                 for (int sl = half; sl < slabs; sl += 2) {
@@ -415,7 +416,7 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         for (int i = 0; i < my_units; ++i)
             for (int kb = 0; kb < g.kblocks; ++kb, ++d) {
                 const int db = d & 1;
-                mbar_wait(bar(TcsBars::diag_empty, db), ((uint32_t)(d >> 1) & 1u) ^ 1u);
+                mbar_wait_backoff(bar(TcsBars::diag_empty, db), ((uint32_t)(d >> 1) & 1u) ^ 1u, g.sleep_ns[4]);
                 if (lane == 0) TCS_TR(4, d, 0);
                 if (g.kblocks > 2 || d < 2) {                      // with <= 2 k-blocks each buffer keeps its k-block for good
                     const uint32_t dst = d_addr(db);
@@ -519,6 +520,17 @@ int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {
         int fp = 0, fw = 0;
         if (sscanf(force, "%d,%d", &fp, &fw) == 2 && fp >= 2 && fp <= TCS_MAX_P && fw >= 2 && fw <= TCS_MAX_W && total(fp, fw) <= TCS_SMEM_MAX) {
             g.p_stages = fp; g.w_stages = fw;
+        }
+    }
+    // Every mbarrier poll is a shared-memory wavefront, and the shared-memory pipe is what bounds this kernel (tensor-operand
+    // fetches): waiting warps sleep between polls instead of re-polling every few tens of cycles (PN_TCS_SLEEP="p,m,c,e,d" in ns).
+    {
+        const unsigned def_ns[5] = {100, 32, 64, 300, 200};
+        for (int i = 0; i < 5; ++i) g.sleep_ns[i] = def_ns[i];
+        if (const char *e = getenv("PN_TCS_SLEEP")) {
+            unsigned v[5];
+            if (sscanf(e, "%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4]) == 5)
+                for (int i = 0; i < 5; ++i) g.sleep_ns[i] = v[i];
         }
     }
     g.off_diag = (unsigned)g.w_stages * g.w_stage_bytes;
