@@ -487,6 +487,7 @@ int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {
     // column bands: pitch wp = tw + 2 dil (one band over the whole width shares the zero gap: wp = w + dil).  Cost per unit in
     // shared-memory cycles (128 B/clk): 9 tap reads of 128 rows + the patch write per k-block, W write + read per pointwise step.
     double best = 1e30;
+    const int force_bands = getenv("PN_TCS_BANDS") ? atoi(getenv("PN_TCS_BANDS")) : 0;      // tuning aid
     for (int bands = 1; bands <= 16; ++bands) {
         const int tw = ceil_div(wd, bands);
         if (bands > 1 && ceil_div(wd, tw) != bands) continue;
@@ -500,6 +501,9 @@ int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {
         const int chunks = ceil_div((h - 1) * wp + tw, 128);
         const double per_unit = g.kblocks * (1152.0 + patch / 128.0) + (double)g.n_tiles * g.kblocks * (2.0 * g.w_stage_bytes / 128.0);
         const double cost = (double)bands * chunks * per_unit;
+        // (measured: fewer, wider bands win even when they leave room for two patch stages only -- C3 0.178 ms with 4 bands / 2
+        // stages against 0.193 ms with 7 bands / 3 stages -- so the stage count is not part of the cost)
+        if (force_bands > 0 && bands != force_bands) continue;
         if (cost < best) {
             best = cost;
             g.bands = bands; g.tw = tw; g.wp = wp; g.rows_box = rows_box; g.chunks = chunks;

@@ -1,0 +1,17 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for wl in c3 c2; do
+  for b in ${BANDS:-0 1 2 3 4 7 9 12}; do
+    if [ "$b" = "0" ]; then unset PN_TCS_BANDS; else export PN_TCS_BANDS=$b; fi
+    timeout 300 python bench.py --workload $wl --skip-cpu --skip-e2e --steps 5 --warmup 3 > gpurun_out/tb.json 2> gpurun_out/tb.err
+    python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/tb.json").read().strip().splitlines()[-1])
+    k = {x["name"]: x["ms"] for x in d["kernels"]}
+    print("bands $b $wl", d["value"], " ".join("%s=%.3f" % (n, k[n]) for n in ("sep5", "sep7", "sep10", "sep13") if n in k))
+except Exception as e:
+    print("bands $b $wl: no line", open("gpurun_out/tb.err").read()[-300:].replace("\n", " "))
+PY
+  done
+done
