@@ -485,7 +485,8 @@ int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {
     const unsigned table_bytes = (unsigned)((9 * k * 2 + 15) / 16 * 16 + k * 4 + nc * 4);
     const long long fixed = 1024 + 2LL * TCS_DIAG_BYTES + (long long)TCS_EPI_WARPS * TCS_STG_BYTES + table_bytes + TcsBars::total;
     // column bands: pitch wp = tw + 2 dil (one band over the whole width shares the zero gap: wp = w + dil).  Cost per unit in
-    // shared-memory cycles (128 B/clk): 9 tap reads of 128 rows + the patch write per k-block, W write + read per pointwise step.
+    // shared-memory cycles (128 B/clk): 9 tap reads of 128 rows + (half) the patch write per k-block, W write + read per pointwise
+    // step, + a per-unit overhead; the weights are fitted to band sweeps (PN_TCS_BANDS) on the C2 / C3 blocks: wide bands win.
     double best = 1e30;
     const int force_bands = getenv("PN_TCS_BANDS") ? atoi(getenv("PN_TCS_BANDS")) : 0;      // tuning aid
     for (int bands = 1; bands <= 16; ++bands) {
@@ -499,7 +500,7 @@ int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {
         const long long stage = (patch + 1023) / 1024 * 1024;
         if (fixed + 2 * stage + 2LL * g.w_stage_bytes > TCS_SMEM_MAX) continue;
         const int chunks = ceil_div((h - 1) * wp + tw, 128);
-        const double per_unit = g.kblocks * (1152.0 + patch / 128.0) + (double)g.n_tiles * g.kblocks * (2.0 * g.w_stage_bytes / 128.0);
+        const double per_unit = g.kblocks * (1152.0 + patch / 256.0) + (double)g.n_tiles * g.kblocks * (2.0 * g.w_stage_bytes / 128.0) + 600.0;
         const double cost = (double)bands * chunks * per_unit;
         // (measured: fewer, wider bands win even when they leave room for two patch stages only -- C3 0.178 ms with 4 bands / 2
         // stages against 0.193 ms with 7 bands / 3 stages -- so the stage count is not part of the cost)
