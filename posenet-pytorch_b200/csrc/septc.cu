@@ -512,6 +512,10 @@ int septc_geometry(SepTcOp *op, int n, int h, int wd, int k, int nc, int dil) {
         }
     }
     PN_CHECK_ARG(best < 1e30, "septc: no band layout fits (h %d w %d cin %d cout %d dilation %d)", h, wd, k, nc, dil);
+    // the last row any tap MMA reads (chunk start at most wp - 1 rows into the box, + the bottom-right tap, + 128 rows) lies
+    // inside the stage, so no descriptor ever points past the patch it belongs to
+    PN_CHECK_ARG((long long)(g.wp - 1 + 2 * dil * g.wp + 2 * dil + 128) * 128 <= (long long)g.patch_stage_bytes,
+                 "septc: internal error, tap view exceeds the patch stage");
     g.magic_wp = (unsigned)((0x100000000ull + (unsigned)g.wp - 1) / (unsigned)g.wp);
     PN_CHECK_ARG((long long)g.chunks * 128 + 128 < (long long)(0x100000000ull / (unsigned)g.wp), "septc: image too large for the pitch division");
     g.units = (long long)n * g.bands * g.chunks;
