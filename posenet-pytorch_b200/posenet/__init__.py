@@ -14,5 +14,6 @@ from posenet.decode_multi import decode_multiple_poses, decode_multiple_poses_ba
 from posenet.models.model_factory import load_model, write_random_checkpoint  # noqa: F401
 from posenet.models import MobileNetV1, MOBILENET_V1_CHECKPOINTS  # noqa: F401
 from posenet.pipeline import BatchPipeline  # noqa: F401  (streaming batches: copies overlap the kernels)
+from posenet.ingest import ImageStream  # noqa: F401  (threaded image-file decode into pinned batches)
 from posenet.utils import *  # noqa: F401,F403
 from posenet.utils import _process_input, process_input_gpu, resize_u8_gpu  # noqa: F401

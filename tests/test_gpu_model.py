@@ -173,3 +173,32 @@ def test_batch_pipeline_resizes_webcam_frames():
         ref = posenet.decode_multiple_poses_batch(*m.forward_u8(x), output_stride=8, **kw)[:4]
         for a, b in zip(rec, ref):
             assert np.array_equal(a, b.cpu().numpy())
+
+
+def test_image_stream_feeds_the_pipeline(tmp_path):
+    """Files -> posenet.ImageStream (thread-pool cv2.imread into pinned batches) -> BatchPipeline: the same records as the
+    reference-shaped per-image path read_imgfile-style (cv2.imread -> forward_u8 -> decode), image by image."""
+    import cv2
+    sd = onet.init_params(50, seed=5, scheme="scaled", gain=0.8)
+    m = build(50, 16, sd, "bf16")
+    H, W, N = 129, 161, 4
+    paths = []
+    for i in range(10):
+        p = str(tmp_path / ("f%02d.png" % i))
+        assert cv2.imwrite(p, synth.smooth_image(H, W, 40 + i))
+        paths.append(p)
+    kw = dict(max_pose_detections=6, min_pose_score=0.1)
+    stream = posenet.ImageStream(paths, batch=N)
+    assert (stream.height, stream.width) == (H, W) and stream.valid_counts() == [4, 4, 2]
+    pipe = posenet.BatchPipeline(m, N, H, W, depth=2, **kw)
+    got = list(pipe.run(b for b, _ in stream.batches()))
+    assert len(got) == 3
+    k = 0
+    for rec, nv in zip(got, stream.valid_counts()):
+        for j in range(nv):
+            img = torch.from_numpy(cv2.imread(paths[k])[None]).to(DEV)
+            ref = posenet.decode_multiple_poses_batch(*m.forward_u8(img), output_stride=16, **kw)[:4]
+            for a, b in zip(rec, ref):
+                assert np.array_equal(a[j], b[0].cpu().numpy())
+            k += 1
+    assert k == 10
