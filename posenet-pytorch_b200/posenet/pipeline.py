@@ -99,24 +99,29 @@ class BatchPipeline:
         self._next = (self._next + 1) % len(self.slots)
         return ticket
 
-    def result(self, ticket, copy=True):
+    def result(self, ticket, copy=True, source_coords=False):
         """Block until the ticket's records are on the host; returns the reference's 4-tuple for the whole batch
-        (numpy float64: [batch,P], [batch,P,17], [batch,P,17,2], [batch,P,17,2])."""
+        (numpy float64: [batch,P], [batch,P,17], [batch,P,17,2], [batch,P,17,2]).  ``source_coords``: keypoint coordinates
+        mapped back to the submitted frames, ``keypoint_coords *= output_scale`` of image_demo.py:50 for the whole batch
+        (implies a copy)."""
         s = self.slots[ticket]
         assert s["busy"], "no batch in flight for this ticket"
         s["out"].synchronize()
         s["busy"] = False
         flat = s["rec_host"].numpy()
-        if copy:
+        if copy or source_coords:
             flat = flat.copy()
-        return split_pose_records(flat, self.batch, self.P)
+        ps, ks, kc, ko = split_pose_records(flat, self.batch, self.P)
+        if source_coords:
+            kc *= self.scale                                     # (y, x) * (src_h / target_h, src_w / target_w), utils.py:19
+        return ps, ks, kc, ko
 
-    def run(self, batches, copy=True):
+    def run(self, batches, copy=True, source_coords=False):
         """Generator: yields the pose records of every batch of ``batches`` in order, keeping ``depth`` batches in flight."""
         pending = []
         for hb in batches:
             if len(pending) == len(self.slots):
-                yield self.result(pending.pop(0), copy=copy)
+                yield self.result(pending.pop(0), copy=copy, source_coords=source_coords)
             pending.append(self.submit(hb))
         while pending:
-            yield self.result(pending.pop(0), copy=copy)
+            yield self.result(pending.pop(0), copy=copy, source_coords=source_coords)

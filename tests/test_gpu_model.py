@@ -173,6 +173,10 @@ def test_batch_pipeline_resizes_webcam_frames():
         ref = posenet.decode_multiple_poses_batch(*m.forward_u8(x), output_stride=8, **kw)[:4]
         for a, b in zip(rec, ref):
             assert np.array_equal(a, b.cpu().numpy())
+    # image_demo.py:50 for a whole batch: coordinates mapped back to the 180 x 320 frames
+    scaled = list(pipe.run(frames, source_coords=True))
+    for a, b in zip(scaled, got):
+        assert np.array_equal(a[2], b[2] * pipe.scale) and np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
 
 
 def test_image_stream_feeds_the_pipeline(tmp_path):
