@@ -83,9 +83,12 @@ __global__ void __launch_bounds__(128) stem_kernel(const void *__restrict__ xin,
 constexpr int STC_THREADS = 128;
 constexpr int STC_NBUF = 2;                          // span ring: the next tile's bytes load while this one is computed
 
-__device__ __forceinline__ uint64_t stc_smem_desc(uint32_t saddr) {      // K-major SWIZZLE_128B (see gemm_tc.cu)
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// K-major SWIZZLE_64B: the stem's K is 32 (27 taps + 5 zero columns) = 64-byte rows, 8-row groups 512 B apart.  Half the shared
+// memory of the 128-byte-row layout for A and W (10 KB instead of 20 KB per CTA), i.e. 7 instead of 5 CTAs per SM.
+__device__ __forceinline__ uint64_t stc_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
+constexpr int STC_A_BYTES = 128 * 64, STC_W_BYTES = 32 * 64;
 
 __device__ __forceinline__ uint32_t lds_u32s(uint32_t addr) {
     uint32_t r;
@@ -106,16 +109,16 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
     extern __shared__ uint8_t stc_raw[];
     const uint32_t base = (smem_u32(stc_raw) + 1023u) & ~1023u;
     uint8_t *gen = stc_raw + (base - smem_u32(stc_raw));
-    const uint32_t sA = base;                         // 128 rows x 128 B (first 64 B of a row = K 0..31)
-    const uint32_t sW = base + 16384;                 // 32 rows x 128 B
-    const uint32_t sSpan = base + 16384 + 4096;       // STC_NBUF x span_cap
-    float *sBias = reinterpret_cast<float *>(gen + 16384 + 4096 + STC_NBUF * a.span_cap);
-    const uint32_t bars = base + 16384 + 4096 + STC_NBUF * (uint32_t)a.span_cap + 128;   // span_full[NBUF], mma_done, tmem slot
+    const uint32_t sA = base;                         // 128 rows x 64 B (K 0..31), 64B swizzle
+    const uint32_t sW = base + STC_A_BYTES;           // 32 rows x 64 B
+    const uint32_t sSpan = base + STC_A_BYTES + STC_W_BYTES;       // STC_NBUF x span_cap
+    float *sBias = reinterpret_cast<float *>(gen + STC_A_BYTES + STC_W_BYTES + STC_NBUF * a.span_cap);
+    const uint32_t bars = base + STC_A_BYTES + STC_W_BYTES + STC_NBUF * (uint32_t)a.span_cap + 128;   // span_full[NBUF], mma_done, tmem slot
     const uint32_t mma_bar = bars + 8u * STC_NBUF, tmem_slot_addr = mma_bar + 8u;
     volatile uint32_t *tmem_slot =
-        reinterpret_cast<volatile uint32_t *>(gen + 16384 + 4096 + STC_NBUF * a.span_cap + 128 + 8 * STC_NBUF + 8);
+        reinterpret_cast<volatile uint32_t *>(gen + STC_A_BYTES + STC_W_BYTES + STC_NBUF * a.span_cap + 128 + 8 * STC_NBUF + 8);
     // span base (byte offset of the ring slot's first byte in the image batch), written by thread 0 when it issues the load
-    volatile long long *span_lo = reinterpret_cast<volatile long long *>(gen + 16384 + 4096 + STC_NBUF * a.span_cap + 128 + 32);
+    volatile long long *span_lo = reinterpret_cast<volatile long long *>(gen + STC_A_BYTES + STC_W_BYTES + STC_NBUF * a.span_cap + 128 + 32);
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long row_bytes = (long long)a.w * 3;
     const long long num_tiles = (a.total_px + 127) / 128;
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
             const __nv_bfloat162 h2 = __floats2bfloat162_rn(w0, w1);
             pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
         }
-        st_shared_v4(sW + (uint32_t)nrow * 128u + (uint32_t)((c ^ (nrow & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+        st_shared_v4(sW + (uint32_t)nrow * 64u + (uint32_t)((c ^ ((nrow >> 1) & 3)) << 4), pk[0], pk[1], pk[2], pk[3]);
     }
     if (tid < 32) {
         float sum = 0.f;
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
                 const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[c * 8 + 2 * j], f[c * 8 + 2 * j + 1]);
                 pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
             }
-            st_shared_v4(sA + (uint32_t)tid * 128u + (uint32_t)((c ^ (tid & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(sA + (uint32_t)tid * 64u + (uint32_t)((c ^ ((tid >> 1) & 3)) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
         fence_async_smem();
         tc_fence_before();
@@ -321,7 +324,7 @@ static int launch_stem_tc(const uint8_t *img, const float *w, const float *b, vo
     const long long rows_out = 128 / wo + 2;
     long long span = (rows_out * stride + 2) * (long long)wd * 3 + 32;
     span = (span + 127) & ~127ll;
-    const long long smem = 16384 + 4096 + STC_NBUF * span + 128 + 128 + 1024;
+    const long long smem = STC_A_BYTES + STC_W_BYTES + STC_NBUF * span + 128 + 128 + 1024;
     if (smem > 200 * 1024) return 1;                              // does not fit: caller falls back to the SIMT kernel
     a.span_cap = (int)span;
     static int configured = 0;
