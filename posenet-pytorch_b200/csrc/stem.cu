@@ -320,9 +320,10 @@ static int launch_stem_tc(const uint8_t *img, const float *w, const float *b, vo
     a.total_px = (long long)n * ho * wo;
     if (a.total_px >= (1ll << 31) - 256) return 1;                // 32-bit pixel indexing inside the kernel
     a.total_bytes16 = ((long long)n * h * wd * 3 + 15) & ~15ll;
-    // rows a 128-pixel tile can touch: its output rows (at most 128/wo + 2, across an image boundary too) x stride + 2
+    // input rows a 128-pixel tile can touch: it covers at most 128/wo + 2 output rows (across an image boundary too), i.e.
+    // (rows_out - 1) * stride + 3 contiguous input rows (tight: checked by brute force over every tile of 28 geometries)
     const long long rows_out = 128 / wo + 2;
-    long long span = (rows_out * stride + 2) * (long long)wd * 3 + 32;
+    long long span = ((rows_out - 1) * stride + 3) * (long long)wd * 3 + 32;
     span = (span + 127) & ~127ll;
     const long long smem = STC_A_BYTES + STC_W_BYTES + STC_NBUF * span + 128 + 128 + 1024;
     if (smem > 200 * 1024) return 1;                              // does not fit: caller falls back to the SIMT kernel
