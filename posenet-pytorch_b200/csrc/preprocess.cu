@@ -2,6 +2,8 @@
 // Replaces posenet/utils.py:13-26 (_process_input) of the reference, i.e. cv2.resize(INTER_LINEAR) on
 // uint8 + cvtColor + two rounded fp32 ops.  Integer/fixed-point work: bit-exact with OpenCV.
 // HBM-bound: reads 3 B and writes 12 B per output pixel; one thread per output pixel, x fastest.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pn {
@@ -79,6 +81,65 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t *__restri
     o[2 * plane] = normalise(bgr[0]);
 }
 
+// MODE_LINEAR with the coefficient arithmetic hoisted: a block covers 256 output columns x PRE_RB output rows; the row
+// coefficients (float64 -> fixed point, the expensive part of a pixel) are computed once per block row into shared memory and
+// the column coefficients once per thread, then reused down the rows.  Same operations per coefficient as above -> same bits.
+constexpr int PRE_RB = 8;
+template <bool OUT_U8>
+__global__ void __launch_bounds__(256) resize_linear_kernel(const uint8_t *__restrict__ src, void *__restrict__ dst_, int sh, int sw,
+                                                             int dh, int dw, double scale_x, double scale_y) {
+    __shared__ int s_y0[PRE_RB], s_y1[PRE_RB], s_b0[PRE_RB], s_b1[PRE_RB];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ybase = blockIdx.y * PRE_RB;
+    const int img = blockIdx.z;
+    if (threadIdx.x < PRE_RB && ybase + threadIdx.x < dh) {
+        int sy;
+        float fy;
+        axis_coeff(ybase + threadIdx.x, scale_y, sy, fy);              // rows: index clipped, weights kept
+        s_y0[threadIdx.x] = min(max(sy, 0), sh - 1);
+        s_y1[threadIdx.x] = min(max(sy + 1, 0), sh - 1);
+        s_b1[threadIdx.x] = __float2int_rn(__fmul_rn(fy, 2048.f));
+        s_b0[threadIdx.x] = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fy), 2048.f));
+    }
+    __syncthreads();
+    if (x >= dw) return;
+    int sx;
+    float fx;
+    axis_coeff(x, scale_x, sx, fx);
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= sw - 1) { sx = sw - 1; fx = 0.f; }
+    const int x1 = min(sx + 1, sw - 1);
+    const int a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
+    const int a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f));
+    const uint8_t *s = src + (size_t)img * sh * sw * 3;
+    const int rows = min(PRE_RB, dh - ybase);
+    const size_t plane = (size_t)dh * dw;
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r) {
+        const uint8_t *r0 = s + (size_t)s_y0[r] * sw * 3;
+        const uint8_t *r1 = s + (size_t)s_y1[r] * sw * 3;
+        const int b0 = s_b0[r], b1 = s_b1[r];
+        int bgr[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int h0 = r0[sx * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
+            const int h1 = r1[sx * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
+            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            bgr[c] = min(max(v, 0), 255);
+        }
+        const int y = ybase + r;
+        if (OUT_U8) {
+            uint8_t *o8 = reinterpret_cast<uint8_t *>(dst_) + (((size_t)img * dh + y) * dw + x) * 3;
+            o8[0] = (uint8_t)bgr[0]; o8[1] = (uint8_t)bgr[1]; o8[2] = (uint8_t)bgr[2];
+        } else {
+            float *o = reinterpret_cast<float *>(dst_) + (size_t)img * 3 * plane + (size_t)y * dw + x;
+            o[0] = normalise(bgr[2]);          // utils.py:22 BGR -> RGB
+            o[plane] = normalise(bgr[1]);
+            o[2 * plane] = normalise(bgr[0]);
+        }
+    }
+}
+
 template <bool OUT_U8>
 static int launch_preprocess_t(const uint8_t *src, int n, int sh, int sw, int dh, int dw, void *dst, cudaStream_t st, const char *who) {
     PN_CHECK_ARG(src && dst && n > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0, "%s: bad argument", who);
@@ -91,8 +152,11 @@ static int launch_preprocess_t(const uint8_t *src, int n, int sh, int sw, int dh
         preprocess_kernel<MODE_COPY, OUT_U8><<<grid, block, 0, st>>>(src, dst, sh, sw, dh, dw, scale_x, scale_y);
     else if (sh == 2 * dh && sw == 2 * dw)
         preprocess_kernel<MODE_AREA2, OUT_U8><<<grid, block, 0, st>>>(src, dst, sh, sw, dh, dw, scale_x, scale_y);
-    else
+    else if (getenv("PN_RESIZE_PER_PIXEL"))          // the one-thread-per-pixel form (A/B)
         preprocess_kernel<MODE_LINEAR, OUT_U8><<<grid, block, 0, st>>>(src, dst, sh, sw, dh, dw, scale_x, scale_y);
+    else
+        resize_linear_kernel<OUT_U8><<<dim3(ceil_div(dw, 256), ceil_div(dh, PRE_RB), n), block, 0, st>>>(src, dst, sh, sw, dh, dw, scale_x,
+                                                                                                     scale_y);
     PN_CHECK_LAUNCH();
     return PN_OK;
 }
