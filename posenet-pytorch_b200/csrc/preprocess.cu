@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t *__restri
 // MODE_LINEAR with the coefficient arithmetic hoisted: a block covers 256 output columns x PRE_RB output rows; the row
 // coefficients (float64 -> fixed point, the expensive part of a pixel) are computed once per block row into shared memory and
 // the column coefficients once per thread, then reused down the rows.  Same operations per coefficient as above -> same bits.
-constexpr int PRE_RB = 8;
+constexpr int PRE_RB = 16;
 template <bool OUT_U8>
 __global__ void __launch_bounds__(256) resize_linear_kernel(const uint8_t *__restrict__ src, void *__restrict__ dst_, int sh, int sw,
                                                              int dh, int dw, double scale_x, double scale_y) {
@@ -114,17 +114,26 @@ __global__ void __launch_bounds__(256) resize_linear_kernel(const uint8_t *__res
     const uint8_t *s = src + (size_t)img * sh * sw * 3;
     const int rows = min(PRE_RB, dh - ybase);
     const size_t plane = (size_t)dh * dw;
+    // horizontal pass of a source row (cv2's int32 row sums); when the scale is near 1 the lower row of one output row is the
+    // upper row of the next, so its sums are carried over instead of being recomputed from memory
+    int carried_row = -1, hc[3] = {0, 0, 0};
+    auto hpass = [&](int row, int (&h)[3]) {
+        const uint8_t *rp = s + (size_t)row * sw * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) h[c] = rp[sx * 3 + c] * a0 + rp[x1 * 3 + c] * a1;
+    };
 #pragma unroll 2
     for (int r = 0; r < rows; ++r) {
-        const uint8_t *r0 = s + (size_t)s_y0[r] * sw * 3;
-        const uint8_t *r1 = s + (size_t)s_y1[r] * sw * 3;
+        const int y0 = s_y0[r], y1 = s_y1[r];
         const int b0 = s_b0[r], b1 = s_b1[r];
+        int h0[3], h1[3];
+        if (y0 == carried_row) { h0[0] = hc[0]; h0[1] = hc[1]; h0[2] = hc[2]; } else hpass(y0, h0);
+        if (y1 == y0) { h1[0] = h0[0]; h1[1] = h0[1]; h1[2] = h0[2]; } else hpass(y1, h1);
+        carried_row = y1; hc[0] = h1[0]; hc[1] = h1[1]; hc[2] = h1[2];
         int bgr[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const int h0 = r0[sx * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
-            const int h1 = r1[sx * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
-            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            const int v = (((b0 * (h0[c] >> 4)) >> 16) + ((b1 * (h1[c] >> 4)) >> 16) + 2) >> 2;
             bgr[c] = min(max(v, 0), 255);
         }
         const int y = ybase + r;
