@@ -283,18 +283,29 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         tc_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
         tc_ld_wait();
         if (live) {
-            uint4 *dst = reinterpret_cast<uint4 *>(a.y + (size_t)m * a.cout);
+            // a pixel's cout bf16 values are contiguous (32 / 48 / 64 bytes): 256-bit stores where the row is 32-byte aligned
+            // (cout 16, 32) -- a warp store then fills whole 32-byte sectors instead of half of 32 of them per request, which is
+            // what kept the LSU data pipe 75 % busy -- 128-bit stores otherwise (cout 24)
+            __nv_bfloat16 *dst = a.y + (size_t)m * a.cout;
+            const bool wide = (a.cout & 15) == 0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c * 8 < a.cout) {
-                    uint32_t o[4];
+            for (int c2 = 0; c2 < 2; ++c2) {
+                if (c2 * 16 < a.cout) {
+                    uint32_t o[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int col = c * 8 + 2 * j;
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = c2 * 16 + 2 * j;
                         o[j] = relu6_bf16x2(fadd2(make_float2(__uint_as_float(v[col]), __uint_as_float(v[col + 1])),
                                                   *reinterpret_cast<const float2 *>(sBias + col)));
                     }
-                    dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
+                    if (wide) {
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c2 * 16), "r"(o[0]), "r"(o[1]),
+                                     "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                                     : "memory");
+                    } else {
+                        *reinterpret_cast<uint4 *>(dst + c2 * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                        if (c2 * 16 + 8 < a.cout) *reinterpret_cast<uint4 *>(dst + c2 * 16 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
                 }
             }
         }
