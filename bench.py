@@ -89,6 +89,7 @@ class ClockSampler(threading.Thread):
             self.bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
                          pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
             self.source = "nvml"
+            self._read()                                         # first NVML query is slow (~10 ms): pay for it here
         except Exception:
             self.nv = None
 
@@ -103,14 +104,19 @@ class ClockSampler(threading.Thread):
         self.max_mhz = float(c[1])
         return float(c[0]), [x.lower().startswith("active") for x in c[2:6]]
 
+    def sample_now(self):
+        """One reading from the calling thread (the main thread calls this right after enqueueing the timed steps, while
+        the GPU is still executing them, so that even a few-millisecond region holds a reading)."""
+        try:
+            mhz, flags = self._read()
+            self.rows.append((time.perf_counter(), mhz, flags))
+        except Exception:
+            pass
+
     def run(self):
         while not self.stop_flag.is_set():
-            try:
-                mhz, flags = self._read()
-                self.rows.append((time.perf_counter(), mhz, flags))
-            except Exception:
-                pass
-            self.stop_flag.wait(0.001 if self.nv is not None else 0.2)
+            self.sample_now()
+            self.stop_flag.wait(0.0005 if self.nv is not None else 0.2)
 
     def summary(self):
         """`window` = (t0, t1) host times bracketing the timed region (set by the caller): readings inside it are
@@ -287,6 +293,8 @@ def run_b200(args):
     for i in range(args.steps):
         graphs[i % n_sets][0].replay()
     e1.record()
+    if sampler.nv is not None:
+        sampler.sample_now()                                     # the replays above are still executing
     barrier()
     sampler.window = (t_begin, time.perf_counter())
     ms = e0.elapsed_time(e1)
