@@ -383,7 +383,7 @@ def run_b200(args):
         os.sched_setaffinity(0, all_cpus)                        # the CPU baseline gets every host core again
     cpu = cpu_reference_run("c2" if args.workload == "c2" else args.workload, images_per_step=4, steps=3, warmup=1) \
         if (world == 1 and not args.skip_cpu) else None
-    launches = model.num_launches(batch, H, W, True) + 2
+    launches = model.num_launches(batch, H, W, True) + 2 + (1 if resized is not None else 0)   # + candidates, decode (+ resize)
     line = {"metric": METRIC, "value": round(value, 1), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",

@@ -124,8 +124,9 @@ typedef struct pn_decode_params {
 
 /* ---- D1-D4: decode_multi.py:61-148 + decode.py:9-63,131-182 (greedy multi-pose decode, float64).
  * One thread block per image; candidates are consumed in (score desc, flat index asc) order.
- * Outputs (float64, caller zero-fills): pose_scores [n_img,P], kp_scores [n_img,P,17],
- * kp_coords [n_img,P,17,2] (y,x), kp_offsets [n_img,P,17,2]; pose_counts int32 [n_img]. */
+ * Outputs (float64): pose_scores [n_img,P], kp_scores [n_img,P,17], kp_coords [n_img,P,17,2] (y,x),
+ * kp_offsets [n_img,P,17,2]; pose_counts int32 [n_img].  The buffers need not be initialised: the rows
+ * past pose_counts[i] are zero-padded by the kernel (the reference's np.zeros, decode_multi.py:94-100). */
 int pn_decode_greedy(const pn_map *heat, const pn_map *off, const pn_map *fwd, const pn_map *bwd,
                      int n_img, int h, int wd, const uint64_t *keys, int capacity, const int *counts,
                      const pn_decode_params *params, double *pose_scores, double *kp_scores,

@@ -411,6 +411,11 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
         __syncthreads();
     }
     if (tid == 0) a.pose_counts[img] = npose;
+    // decode_multi.py:94-100: the outputs are np.zeros; rows past the last accepted pose are zero-padded here, so the
+    // caller hands over uninitialised buffers and the step needs no separate fill launch
+    for (int i = npose + tid; i < P; i += DEC_THREADS) out_ps[i] = 0.0;
+    for (int i = npose * PN_NUM_PARTS + tid; i < P * PN_NUM_PARTS; i += DEC_THREADS) out_ks[i] = 0.0;
+    for (int i = npose * PN_NUM_PARTS * 2 + tid; i < P * PN_NUM_PARTS * 2; i += DEC_THREADS) { out_kc[i] = 0.0; out_ko[i] = 0.0; }
 #ifdef PN_DEC_TRACE
     if (tid == 0 && (img == 0 || img == 7))
         printf("decode img %d: n %d poses %d rounds %d slots %d | cycles: pivot %lld gather %lld sort %lld screen %lld spec %lld commit %lld\n", img, n,

@@ -46,7 +46,7 @@ def decode_multiple_poses_batch(scores, offsets, displacements_fwd, displacement
     Inputs are [N,17|34|32|32,h,w] fp32 CUDA tensors with any strides.  Returns
     ``(pose_scores [N,P], keypoint_scores [N,P,17], keypoint_coords [N,P,17,2], pose_offsets [N,P,17,2],
     pose_counts [N] int32)`` as CUDA tensors (float64 like the reference's numpy outputs); the first four
-    are views of one packed buffer (``out``: optional preallocated float64 [N*P*86], zeroed here).
+    are views of one packed buffer (``out``: optional preallocated float64 [N*P*86], fully overwritten).
     """
     nat.require_device()
     lib = nat.load()
@@ -66,11 +66,10 @@ def decode_multiple_poses_batch(scores, offsets, displacements_fwd, displacement
     if ws is None:
         ws = workspace[key] = dict(keys=torch.empty((n, cap), dtype=torch.int64, device=dev),
                                    counts=torch.empty(n, dtype=torch.int32, device=dev))
-    if out is None:
-        out = torch.zeros(n * P * (1 + NUM_KEYPOINTS * 5), dtype=torch.float64, device=dev)
+    if out is None:                                    # pn_decode_greedy zero-pads the rows it does not fill
+        out = torch.empty(n * P * (1 + NUM_KEYPOINTS * 5), dtype=torch.float64, device=dev)
     else:
         assert out.dtype == torch.float64 and out.numel() == n * P * (1 + NUM_KEYPOINTS * 5) and out.is_contiguous()
-        out.zero_()
     ps, ks, kc, ko = split_pose_records(out, n, P)
     pose_counts = torch.empty(n, dtype=torch.int32, device=dev)
     maps = [nat.make_map(t) for t in (heat, off, fwd, bwd)]

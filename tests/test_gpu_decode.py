@@ -100,3 +100,20 @@ def test_decode_accepts_cpu_tensors_and_image_demo_usage():
     assert len(res) == 4                                  # this fork returns a 4-tuple
     res[2][...] *= np.array([1.5, 0.5])                   # image_demo.py:50 scales the coords in place
     assert_same(res[:2], odec.decode_multiple_poses(*heads, 16, max_pose_detections=10, min_pose_score=0.25)[:2])
+
+
+def test_decode_zero_pads_an_uninitialised_record_buffer():
+    # decode_multi.py:94-100: the reference's outputs are np.zeros; pn_decode_greedy pads the rows it does not fill itself,
+    # whatever the buffer held before -- including images with no candidate at all (threshold above every score)
+    sets = [synth.people_heads(33, 33, 16, p, seed=10 + p)[:4] for p in (1, 2, 5)]
+    batched = [torch.from_numpy(np.stack([s[j] for s in sets])).to(DEV) for j in range(4)]
+    P = 7
+    for thr in (0.5, 2.0):
+        out = torch.full((3 * P * 86,), float("nan"), dtype=torch.float64, device=DEV)
+        ps, ks, kc, ko, cnt = posenet.decode_multiple_poses_batch(*batched, output_stride=16, max_pose_detections=P,
+                                                                  score_threshold=thr, min_pose_score=0.25, out=out)
+        assert not torch.isnan(out).any()
+        for b in range(3):
+            ref = odec.decode_multiple_poses(*sets[b], 16, max_pose_detections=P, score_threshold=thr, min_pose_score=0.25)
+            assert_same([ps[b].cpu().numpy(), ks[b].cpu().numpy(), kc[b].cpu().numpy(), ko[b].cpu().numpy()], ref)
+            assert int(cnt[b]) == int((ref[0] != 0).sum())

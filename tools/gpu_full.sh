@@ -22,4 +22,4 @@ for wl in ("c2", "c3", "c4"):
 print(open("gpurun_out/bench_c5_decode.jsonl").read())
 print(open("gpurun_out/bench_ref.json").read()[:600])
 PY
-tail -3 gpurun_out/bench_c2.err gpurun_out/bench_c5.err
+tail -n 3 gpurun_out/bench_c2.err gpurun_out/bench_c5.err; true
