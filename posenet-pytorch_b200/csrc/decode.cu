@@ -75,14 +75,23 @@ __global__ void __launch_bounds__(256) candidates_kernel(pn_map heat, int h, int
 // (2 dependent gathers each), which is pure latency.  decode_pose (decode.py:131-182) does not depend on the poses
 // accepted so far -- only the root NMS test and the instance score do -- so a block decodes in ROUNDS:
 //   (a) screen: all threads test the next candidates against the accepted poses and compact the survivors, in
-//       order, into up to DEC_BATCH slots (candidates suppressed now stay suppressed: poses are only ever added);
-//   (b) speculate: one thread per slot runs the full 32-step decode_pose, all slots in parallel;
+//       order, into up to DEC_SLOTS slots (candidates suppressed now stay suppressed: poses are only ever added);
+//   (b) speculate: 17 threads per slot, one per part.  decode_pose reaches every part along the unique tree path from the
+//       root part (child -> parent hops of the backward pass first, then parent -> child hops of the forward pass), and a hop
+//       is a pure function of its source coordinates, so the thread of part k walks the path root -> k on its own: at most 8
+//       dependent hops instead of the 16 a single thread pays, prefixes shared with other parts are recomputed (same
+//       addresses, same warp-level requests), and a path stops where the reference's `score[source] > 0.0` gate stops it;
 //   (c) commit: warp 0 replays the reference's greedy loop over the slots in order -- root NMS against every accepted
 //       pose (including those of this round), instance score, acceptance -- from shared memory only.
 // The sequence of accepted poses and every float64 operation is the reference's; only the latency is shared.
-constexpr int DEC_THREADS = 256;
-constexpr int DEC_KBUF = 4096;          // candidate keys sorted per chunk in shared memory (32 KB)
-constexpr int DEC_BATCH = 128;          // slots decoded speculatively per round
+#ifndef PN_DEC_THREADS
+#define PN_DEC_THREADS 512
+#endif
+constexpr int DEC_THREADS = PN_DEC_THREADS;
+constexpr int DEC_KBUF = 4096;          // capacity of the sorted chunk in shared memory (32 KB)
+constexpr int DEC_CHUNK = 1024;         // keys taken per chunk when an image has more: the greedy loop rarely needs more
+constexpr int DEC_BATCH = 128;          // slot capacity of the speculative pose records
+constexpr int DEC_SLOTS = DEC_THREADS / PN_NUM_PARTS < DEC_BATCH ? DEC_THREADS / PN_NUM_PARTS : DEC_BATCH;   // slots per round
 constexpr int DEC_ACC = 64;             // accepted poses whose coordinates are cached in shared memory
 
 struct DecodeArgs {
@@ -103,6 +112,9 @@ struct DecodeShared {
     float ks[PN_NUM_PARTS][DEC_BATCH];
     float ko[PN_NUM_PARTS][2][DEC_BATCH];
     uint32_t cand[DEC_BATCH];           // flat (part, y, x) index of each slot's root
+    double full[DEC_BATCH];             // instance score of a slot when no part is masked: np.sum(all 17 scores) / 17
+    int up[PN_NUM_PARTS], up_edge[PN_NUM_PARTS];
+    unsigned anc[PN_NUM_PARTS];         // bit a set: part a is part k's ancestor or k itself
     double acc[DEC_ACC][PN_NUM_PARTS][2];   // keypoint coordinates of the accepted poses (the first DEC_ACC)
     double vals[PN_NUM_PARTS];
     unsigned hist[256];
@@ -138,23 +150,21 @@ __device__ double np_sum(const double *a, int n) {
     return res;
 }
 
-// decode.py:9-63: one displacement hop source -> target along edge e, on the pose record in slot `s`.
-__device__ __forceinline__ void hop(const DecodeArgs &a, DecodeShared &S, int s, int img, const pn_map &disp, int e, int src,
-                                    int tgt) {
+// decode.py:9-63: one displacement hop along edge e from the source at (cy, cx) to part `tgt`; on return (cy, cx) are the
+// target's coordinates, sc its score and (oy, ox) its offset vector.
+__device__ __forceinline__ void hop(const DecodeArgs &a, int img, const pn_map &disp, int e, int tgt, double &cy, double &cx,
+                                    float &sc, float &oy, float &ox) {
     const int os = a.prm.output_stride;
     const double stride = (double)os, inv = (os & (os - 1)) == 0 ? 1.0 / stride : 0.0;
-    const double sy = S.kc[src][0][s], sx = S.kc[src][1][s];
-    const int iy = to_cell(sy, stride, inv, a.h - 1), ix = to_cell(sx, stride, inv, a.w - 1);
-    const double py = __dadd_rn(sy, (double)map_at(disp, img, e, iy, ix));                    // decode.py:39-40
-    const double px = __dadd_rn(sx, (double)map_at(disp, img, PN_NUM_EDGES + e, iy, ix));
+    const int iy = to_cell(cy, stride, inv, a.h - 1), ix = to_cell(cx, stride, inv, a.w - 1);
+    const double py = __dadd_rn(cy, (double)map_at(disp, img, e, iy, ix));                    // decode.py:39-40
+    const double px = __dadd_rn(cx, (double)map_at(disp, img, PN_NUM_EDGES + e, iy, ix));
     const int ty = to_cell(py, stride, inv, a.h - 1), tx = to_cell(px, stride, inv, a.w - 1);
-    const float sc = map_at(a.heat, img, tgt, ty, tx);                                        // decode.py:53
-    const float oy = map_at(a.off, img, tgt, ty, tx), ox = map_at(a.off, img, PN_NUM_PARTS + tgt, ty, tx);
-    S.ks[tgt][s] = sc;
-    S.kc[tgt][0][s] = __dadd_rn((double)(ty * a.prm.output_stride), (double)oy);              // decode.py:55-56
-    S.kc[tgt][1][s] = __dadd_rn((double)(tx * a.prm.output_stride), (double)ox);
-    S.ko[tgt][0][s] = oy;
-    S.ko[tgt][1][s] = ox;
+    sc = map_at(a.heat, img, tgt, ty, tx);                                                    // decode.py:53
+    oy = map_at(a.off, img, tgt, ty, tx);
+    ox = map_at(a.off, img, PN_NUM_PARTS + tgt, ty, tx);
+    cy = __dadd_rn((double)(ty * os), (double)oy);                                            // decode.py:55-56
+    cx = __dadd_rn((double)(tx * os), (double)ox);
 }
 
 __device__ __forceinline__ double sqdist(double ay, double ax, double by, double bx) {
@@ -167,7 +177,7 @@ __device__ __forceinline__ double acc_coord(const DecodeShared &S, const double 
     return p < DEC_ACC ? S.acc[p][part][c] : __ldcg(out_kc + ((size_t)p * PN_NUM_PARTS + part) * 2 + c);
 }
 
-__global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
+__global__ void __launch_bounds__(DEC_THREADS, DEC_THREADS <= 512 ? 2 : 1) decode_kernel(DecodeArgs a) {
     extern __shared__ __align__(16) unsigned char dec_smem_raw[];
     DecodeShared &S = *reinterpret_cast<DecodeShared *>(dec_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -191,14 +201,29 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
 #else
 #define DEC_STAMP(i) do { } while (0)
 #endif
+    // the skeleton as a tree rooted at the nose (part 0): parent part, the edge whose child a part is, ancestors-or-self
+    if (tid < PN_NUM_PARTS) {
+        int up = 0, up_edge = -1;
+        for (int e = 0; e < PN_NUM_EDGES; ++e)
+            if (c_child[e] == tid) { up = c_parent[e]; up_edge = e; }
+        S.up[tid] = up;
+        S.up_edge[tid] = up_edge;
+    }
+    __syncthreads();
+    if (tid < PN_NUM_PARTS) {
+        unsigned m = 1u << tid;
+        for (int k = tid; k != 0; k = S.up[k]) m |= 1u << S.up[k];
+        S.anc[tid] = m;
+    }
+    __syncthreads();
     uint64_t lo = 0;            // every key consumed so far is <= lo (real keys are never 0)
     int remaining = n;
     int npose = 0;
 
     while (remaining > 0 && npose < P) {
-        // ---- 1. pick a pivot so that (lo, pivot] holds between 1 and DEC_KBUF of the best keys
+        // ---- 1. pick a pivot so that (lo, pivot] holds between 1 and DEC_CHUNK of the best keys
         uint64_t pivot = ~0ull;
-        if (remaining > DEC_KBUF) {
+        if (remaining > DEC_CHUNK) {
             // MSB-first radix descent, 8 bits per level, among keys > lo.  Keys are unique (low word is
             // the cell index), so the descent always terminates with a non-empty prefix set.
             uint64_t prefix = 0;
@@ -207,9 +232,16 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
                 for (int i = tid; i < 256; i += DEC_THREADS) S.hist[i] = 0;
                 __syncthreads();
                 const int shift = 56 - bits;
-                for (int i = tid; i < n; i += DEC_THREADS) {
-                    const uint64_t k = keys[i];
-                    if (k > lo && (bits == 0 || (k >> (64 - bits)) == prefix)) atomicAdd(&S.hist[(k >> shift) & 255], 1u);
+                // four keys in flight per thread: the pass is bound by the latency of the key loads, not by the atomics
+                for (int i0 = tid; i0 < n; i0 += 4 * DEC_THREADS) {
+                    uint64_t k4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) k4[j] = i0 + j * DEC_THREADS < n ? __ldg(keys + i0 + j * DEC_THREADS) : 0ull;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t k = k4[j];                       // 0 is never a key and never > lo
+                        if (k > lo && (bits == 0 || (k >> (64 - bits)) == prefix)) atomicAdd(&S.hist[(k >> shift) & 255], 1u);
+                    }
                 }
                 __syncthreads();
                 if (tid == 0) {
@@ -218,7 +250,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
                     for (int d = 0; d < 256; ++d) {
                         const unsigned c = S.hist[d];
                         if (c && first < 0) first = d;
-                        if (cum + c > (unsigned)DEC_KBUF) break;
+                        if (cum + c > (unsigned)DEC_CHUNK) break;
                         cum += c;
                         if (c) sel = d;
                     }
@@ -244,17 +276,21 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
         // ---- 2. gather (lo, pivot] into shared memory and sort ascending (bitonic)
         if (tid == 0) S.cnt = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += DEC_THREADS) {
-            const uint64_t k = keys[i];
-            if (k > lo && k <= pivot) S.keys[atomicAdd(&S.cnt, 1)] = k;
+        for (int i0 = tid; i0 < n; i0 += 4 * DEC_THREADS) {
+            uint64_t k4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) k4[j] = i0 + j * DEC_THREADS < n ? __ldg(keys + i0 + j * DEC_THREADS) : 0ull;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k4[j] > lo && k4[j] <= pivot) S.keys[atomicAdd(&S.cnt, 1)] = k4[j];
         }
         __syncthreads();
         const int cnt = S.cnt;
         DEC_STAMP(1);
-        if (cnt <= DEC_KBUF / 2 && cnt <= 1024) {
-            // Small chunk (the usual case: a few hundred candidates): rank sort.  Keys are unique, so the number of smaller
-            // keys IS the sorted position; every thread reads the same key at a time (a shared-memory broadcast), and the
-            // whole sort is two barriers instead of ~50 bitonic passes.
+        if (cnt <= DEC_THREADS) {
+            // Small chunk (the usual case: a few hundred candidates, one per thread): rank sort.  Keys are unique, so the
+            // number of smaller keys IS the sorted position; every thread reads the same key at a time (a shared-memory
+            // broadcast), and the whole sort is two barriers instead of ~50 bitonic passes.
             uint64_t *scratch = S.keys + DEC_KBUF / 2;
             for (int i = tid; i < cnt; i += DEC_THREADS) {
                 const uint64_t k = S.keys[i];
@@ -285,12 +321,13 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
             }
         }
         DEC_STAMP(2);
-        // ---- 3. greedy pass over this chunk, in rounds of up to DEC_BATCH speculatively decoded candidates
+        // ---- 3. greedy pass over this chunk, in rounds of up to DEC_SLOTS speculatively decoded candidates
         int ci = 0;
         while (ci < cnt && npose < P) {
             // (a) screen candidates ci.. against the npose accepted poses; survivors -> slots, in order
+            constexpr int slots = DEC_SLOTS;
             int nb = 0, next = ci;
-            while (next < cnt && nb < DEC_BATCH) {
+            while (next < cnt && nb < slots) {
                 const int base = next, i = base + tid;
                 if (tid == 0) S.next_ci = 0x7fffffff;
                 bool keep = false;
@@ -320,39 +357,52 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
                 }
                 pos += __popc(bal & ((1u << lane) - 1));
                 if (keep) {
-                    if (pos < DEC_BATCH) S.cand[pos] = flat;
+                    if (pos < slots) S.cand[pos] = flat;
                     else atomicMin(&S.next_ci, i);                  // first survivor that did not fit: resume there
                 }
                 __syncthreads();
-                next = total > DEC_BATCH ? S.next_ci : min(base + DEC_THREADS, cnt);
-                nb = min(total, DEC_BATCH);
+                next = total > slots ? S.next_ci : min(base + DEC_THREADS, cnt);
+                nb = min(total, slots);
                 __syncthreads();
             }
             DEC_STAMP(3);
-            // (b) one thread per slot: decode.py:131-182 on its own record
-            if (tid < nb) {
-                const int s = tid;
+            // (b) one thread per (slot, part): decode.py:131-182, the part's own path from the root
+            if (tid < nb * PN_NUM_PARTS) {
+                const int s = tid / PN_NUM_PARTS, k = tid - s * PN_NUM_PARTS;
                 const uint32_t flat = S.cand[s];
-                const int part = flat / hw;
-                const int rem = flat - part * hw;
+                const int root = flat / hw;
+                const int rem = flat - root * hw;
                 const int y = rem / a.w, x = rem - y * a.w;
+                float sc = map_at(a.heat, img, root, y, x), oy = 0.f, ox = 0.f;       // the root's offset row stays 0 (decode.py:150)
+                double cy = __dadd_rn((double)(y * os), (double)map_at(a.off, img, root, y, x));
+                double cx = __dadd_rn((double)(x * os), (double)map_at(a.off, img, PN_NUM_PARTS + root, y, x));
+                const unsigned anc_k = S.anc[k];
+                int cur = root;
+                bool reached = true;
+                while (cur != k) {
+                    // decode.py:152-153,169-170: a hop needs `score[source] > 0.0`; its target is still 0.0 (every part has
+                    // exactly one path from the root), so a non-positive score on the path leaves the rest of it undecoded
+                    if (!(sc > 0.f)) { reached = false; break; }
+                    const bool climb = ((anc_k >> cur) & 1u) == 0;                      // cur is not above k yet: child -> parent
+                    int nxt;
+                    if (climb) nxt = S.up[cur];
+                    else { nxt = k; while (S.up[nxt] != cur) nxt = S.up[nxt]; }         // the child of cur on the way down to k
+                    const int e = climb ? S.up_edge[cur] : S.up_edge[nxt];
+                    hop(a, img, climb ? a.bwd : a.fwd, e, nxt, cy, cx, sc, oy, ox);
+                    cur = nxt;
+                }
+                if (!reached) { sc = 0.f; oy = ox = 0.f; cy = cx = 0.0; }
+                S.ks[k][s] = sc;
+                S.kc[k][0][s] = cy; S.kc[k][1][s] = cx;
+                S.ko[k][0][s] = oy; S.ko[k][1][s] = ox;
+            }
+            __syncthreads();
+            // the instance score of a slot none of whose parts is masked (decode_multi.py:14-24 with an all-true mask)
+            if (tid < nb) {
+                double v[PN_NUM_PARTS];
 #pragma unroll
-                for (int k = 0; k < PN_NUM_PARTS; ++k) {
-                    S.ks[k][s] = 0.f;
-                    S.kc[k][0][s] = 0.0; S.kc[k][1][s] = 0.0;
-                    S.ko[k][0][s] = 0.f; S.ko[k][1][s] = 0.f;
-                }
-                S.ks[part][s] = map_at(a.heat, img, part, y, x);
-                S.kc[part][0][s] = __dadd_rn((double)(y * os), (double)map_at(a.off, img, part, y, x));
-                S.kc[part][1][s] = __dadd_rn((double)(x * os), (double)map_at(a.off, img, PN_NUM_PARTS + part, y, x));
-                for (int e = PN_NUM_EDGES - 1; e >= 0; --e) {               // backward: child -> parent
-                    const int tgt = c_parent[e], src = c_child[e];
-                    if (S.ks[src][s] > 0.f && S.ks[tgt][s] == 0.f) hop(a, S, s, img, a.bwd, e, src, tgt);
-                }
-                for (int e = 0; e < PN_NUM_EDGES; ++e) {                    // forward: parent -> child
-                    const int src = c_parent[e], tgt = c_child[e];
-                    if (S.ks[src][s] > 0.f && S.ks[tgt][s] == 0.f) hop(a, S, s, img, a.fwd, e, src, tgt);
-                }
+                for (int k = 0; k < PN_NUM_PARTS; ++k) v[k] = (double)S.ks[k][tid];
+                S.full[tid] = __ddiv_rn(np_sum(v, PN_NUM_PARTS), (double)PN_NUM_PARTS);
             }
             __syncthreads();
             DEC_STAMP(4);
@@ -363,26 +413,31 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(DecodeArgs a) {
             if (warp == 0) {
                 for (int s = 0; s < nb && npose < P; ++s) {
                     const int part = S.cand[s] / hw;
-                    const double ry = S.kc[part][0][s], rx = S.kc[part][1][s];
-                    bool hit = false;
-                    for (int p = lane; p < npose; p += 32)
-                        if (sqdist(acc_coord(S, out_kc, p, part, 0), acc_coord(S, out_kc, p, part, 1), ry, rx) <= r2) hit = true;
-                    if (__any_sync(0xFFFFFFFFu, hit)) continue;
-                    // decode_multi.py:14-24: keep the parts that are strictly farther than the radius from
-                    // that part of EVERY accepted pose; sum in numpy's order; always divide by 17.
-                    bool far = lane < PN_NUM_PARTS;
+                    // one pass over the accepted poses per part: `near` of the root part is the NMS test of
+                    // decode_multi.py:8-11,111-113 (<=), `far` the mask of decode_multi.py:14-24 (strictly farther from EVERY pose)
+                    bool far = lane < PN_NUM_PARTS, near = false;
                     double ky = 0.0, kx = 0.0;
                     if (lane < PN_NUM_PARTS) {
                         ky = S.kc[lane][0][s]; kx = S.kc[lane][1][s];
-                        for (int p = 0; p < npose; ++p)
-                            if (!(sqdist(acc_coord(S, out_kc, p, lane, 0), acc_coord(S, out_kc, p, lane, 1), ky, kx) > r2)) far = false;
+                        for (int p = 0; p < npose; ++p) {
+                            const double d = sqdist(acc_coord(S, out_kc, p, lane, 0), acc_coord(S, out_kc, p, lane, 1), ky, kx);
+                            if (d <= r2) near = true;
+                            if (!(d > r2)) far = false;
+                        }
                     }
+                    if (__shfl_sync(0xFFFFFFFFu, near ? 1 : 0, part)) continue;
                     const unsigned fmask = __ballot_sync(0xFFFFFFFFu, far);
-                    if (far) S.vals[__popc(fmask & ((1u << lane) - 1))] = (double)S.ks[lane][s];
-                    __syncwarp();
-                    double score = 0.0;
-                    if (lane == 0) score = __ddiv_rn(np_sum(S.vals, __popc(fmask)), (double)PN_NUM_PARTS);
-                    score = __shfl_sync(0xFFFFFFFFu, score, 0);
+                    double score;
+                    if (fmask == (1u << PN_NUM_PARTS) - 1u) {
+                        score = S.full[s];                       // nothing masked: computed with the slot, in parallel
+                    } else {
+                        // sum the kept scores in numpy's order; always divide by 17
+                        if (far) S.vals[__popc(fmask & ((1u << lane) - 1))] = (double)S.ks[lane][s];
+                        __syncwarp();
+                        score = 0.0;
+                        if (lane == 0) score = __ddiv_rn(np_sum(S.vals, __popc(fmask)), (double)PN_NUM_PARTS);
+                        score = __shfl_sync(0xFFFFFFFFu, score, 0);
+                    }
                     if (a.prm.min_pose_score == 0.0 || score >= a.prm.min_pose_score) {    // decode_multi.py:128
                         if (lane == 0) out_ps[npose] = score;
                         if (lane < PN_NUM_PARTS) {
