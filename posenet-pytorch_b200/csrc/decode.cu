@@ -291,11 +291,22 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_THREADS <= 512 ? 2 : 1) decod
             // Small chunk (the usual case: a few hundred candidates, one per thread): rank sort.  Keys are unique, so the
             // number of smaller keys IS the sorted position; every thread reads the same key at a time (a shared-memory
             // broadcast), and the whole sort is two barriers instead of ~50 bitonic passes.
+            // The list is padded to a multiple of 8 with all-ones keys (never smaller than a key), so the count runs over
+            // 128-bit shared-memory loads, eight independent comparisons at a time.
             uint64_t *scratch = S.keys + DEC_KBUF / 2;
+            const int cnt8 = (cnt + 7) & ~7;
+            if (tid < cnt8 - cnt) S.keys[cnt + tid] = ~0ull;
+            __syncthreads();
             for (int i = tid; i < cnt; i += DEC_THREADS) {
                 const uint64_t k = S.keys[i];
                 int rank = 0;
-                for (int j = 0; j < cnt; ++j) rank += (S.keys[j] < k) ? 1 : 0;
+                for (int j = 0; j < cnt8; j += 8) {
+                    ulonglong2 q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const ulonglong2 *>(&S.keys[j + 2 * u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) rank += (q[u].x < k ? 1 : 0) + (q[u].y < k ? 1 : 0);
+                }
                 scratch[rank] = k;
             }
             __syncthreads();
