@@ -420,23 +420,30 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_THREADS <= 512 ? 2 : 1) decod
 #ifdef PN_DEC_TRACE
             ++tr_rounds; tr_slots += nb;
 #endif
-            // (c) warp 0: the reference's greedy loop over the slots, in candidate order
+            // (c) warp 0: the reference's greedy loop over the slots, in candidate order.  The screen left no slot within the
+            // radius of a pose accepted in an EARLIER round, so the root NMS test (decode_multi.py:8-11,111-113) only has to look
+            // at the poses accepted in THIS round: lane l owns slot l, and after every acceptance each lane tests its own pending
+            // slot against the new pose -- a suppressed slot costs nothing instead of a pass over all accepted poses.
+            static_assert(DEC_SLOTS <= 32, "one lane per slot in the commit loop");
             if (warp == 0) {
-                for (int s = 0; s < nb && npose < P; ++s) {
-                    const int part = S.cand[s] / hw;
-                    // one pass over the accepted poses per part: `near` of the root part is the NMS test of
-                    // decode_multi.py:8-11,111-113 (<=), `far` the mask of decode_multi.py:14-24 (strictly farther from EVERY pose)
-                    bool far = lane < PN_NUM_PARTS, near = false;
+                int my_part = 0;
+                double my_ry = 0.0, my_rx = 0.0;
+                if (lane < nb) {
+                    my_part = S.cand[lane] / hw;
+                    my_ry = S.kc[my_part][0][lane]; my_rx = S.kc[my_part][1][lane];
+                }
+                unsigned pending = nb >= 32 ? 0xFFFFFFFFu : (1u << nb) - 1u;     // slots neither visited nor suppressed yet
+                while (pending && npose < P) {
+                    const int s = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    // the mask of decode_multi.py:14-24: parts strictly farther than the radius from that part of EVERY accepted pose
+                    bool far = lane < PN_NUM_PARTS;
                     double ky = 0.0, kx = 0.0;
                     if (lane < PN_NUM_PARTS) {
                         ky = S.kc[lane][0][s]; kx = S.kc[lane][1][s];
-                        for (int p = 0; p < npose; ++p) {
-                            const double d = sqdist(acc_coord(S, out_kc, p, lane, 0), acc_coord(S, out_kc, p, lane, 1), ky, kx);
-                            if (d <= r2) near = true;
-                            if (!(d > r2)) far = false;
-                        }
+                        for (int p = 0; p < npose; ++p)
+                            if (!(sqdist(acc_coord(S, out_kc, p, lane, 0), acc_coord(S, out_kc, p, lane, 1), ky, kx) > r2)) far = false;
                     }
-                    if (__shfl_sync(0xFFFFFFFFu, near ? 1 : 0, part)) continue;
                     const unsigned fmask = __ballot_sync(0xFFFFFFFFu, far);
                     double score;
                     if (fmask == (1u << PN_NUM_PARTS) - 1u) {
@@ -462,6 +469,10 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_THREADS <= 512 ? 2 : 1) decod
                         }
                         ++npose;
                         if (npose > DEC_ACC) __threadfence_block();   // poses beyond the shared-memory cache are re-read from global
+                        // pending slots whose root lies within the radius (<=) of the same part of the new pose are suppressed
+                        bool hit = false;
+                        if ((pending >> lane) & 1u) hit = sqdist(S.kc[my_part][0][s], S.kc[my_part][1][s], my_ry, my_rx) <= r2;
+                        pending &= ~__ballot_sync(0xFFFFFFFFu, hit);
                     }
                     __syncwarp();
                 }
