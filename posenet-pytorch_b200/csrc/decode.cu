@@ -119,7 +119,7 @@ struct DecodeShared {
     double vals[PN_NUM_PARTS];
     unsigned hist[256];
     int warp_cnt[DEC_THREADS / 32];
-    uint64_t pivot;
+    uint64_t pivot, kmax;
     int cnt, npose, done, next_ci;
 };
 
@@ -225,13 +225,41 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_THREADS <= 512 ? 2 : 1) decod
         uint64_t pivot = ~0ull;
         if (remaining > DEC_CHUNK) {
             // MSB-first radix descent, 8 bits per level, among keys > lo.  Keys are unique (low word is
-            // the cell index), so the descent always terminates with a non-empty prefix set.
-            uint64_t prefix = 0;
-            int bits = 0;
+            // the cell index), so the descent always terminates with a non-empty prefix set.  The descent starts below the
+            // bits all remaining keys share (one min / max pass): scores of one image often agree in their top 2-3 bytes,
+            // and every such byte would cost a histogram pass that ends in a single bucket.
+            if (tid == 0) { S.pivot = ~0ull; S.kmax = 0ull; }
+            __syncthreads();
+            {
+                uint64_t mn = ~0ull, mx = 0ull;
+                for (int i0 = tid; i0 < n; i0 += 4 * DEC_THREADS) {
+                    uint64_t k4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) k4[j] = i0 + j * DEC_THREADS < n ? __ldg(keys + i0 + j * DEC_THREADS) : 0ull;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (k4[j] > lo) { mn = k4[j] < mn ? k4[j] : mn; mx = k4[j] > mx ? k4[j] : mx; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const uint64_t a_ = __shfl_xor_sync(0xFFFFFFFFu, mn, o), b_ = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
+                    mn = a_ < mn ? a_ : mn;
+                    mx = b_ > mx ? b_ : mx;
+                }
+                if (lane == 0) {
+                    atomicMin(reinterpret_cast<unsigned long long *>(&S.pivot), (unsigned long long)mn);
+                    atomicMax(reinterpret_cast<unsigned long long *>(&S.kmax), (unsigned long long)mx);
+                }
+            }
+            __syncthreads();
+            int bits = __clzll((long long)(S.pivot ^ S.kmax));           // > DEC_CHUNK distinct keys remain, so min != max
+            uint64_t prefix = bits ? S.pivot >> (64 - bits) : 0ull;
+            __syncthreads();
             for (;;) {
                 for (int i = tid; i < 256; i += DEC_THREADS) S.hist[i] = 0;
                 __syncthreads();
-                const int shift = 56 - bits;
+                const int width = 64 - bits < 8 ? 64 - bits : 8;
+                const int shift = 64 - bits - width;
                 // four keys in flight per thread: the pass is bound by the latency of the key loads, not by the atomics
                 for (int i0 = tid; i0 < n; i0 += 4 * DEC_THREADS) {
                     uint64_t k4[4];
@@ -240,7 +268,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_THREADS <= 512 ? 2 : 1) decod
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint64_t k = k4[j];                       // 0 is never a key and never > lo
-                        if (k > lo && (bits == 0 || (k >> (64 - bits)) == prefix)) atomicAdd(&S.hist[(k >> shift) & 255], 1u);
+                        if (k > lo && (bits == 0 || (k >> (64 - bits)) == prefix)) atomicAdd(&S.hist[(k >> shift) & ((1u << width) - 1u)], 1u);
                     }
                 }
                 __syncthreads();
@@ -256,10 +284,10 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_THREADS <= 512 ? 2 : 1) decod
                     }
                     if (sel >= 0) {
                         const uint64_t low_ones = shift ? ((1ull << shift) - 1) : 0ull;
-                        S.pivot = (((prefix << 8) | (uint64_t)sel) << shift) | low_ones;
+                        S.pivot = (((prefix << width) | (uint64_t)sel) << shift) | low_ones;
                         S.done = 1;
                     } else {
-                        S.pivot = (prefix << 8) | (uint64_t)first;   // descend into the first non-empty bucket
+                        S.pivot = (prefix << width) | (uint64_t)first;   // descend into the first non-empty bucket
                         S.done = 0;
                     }
                 }
@@ -269,7 +297,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_THREADS <= 512 ? 2 : 1) decod
                 __syncthreads();
                 if (done) { pivot = pv; break; }
                 prefix = pv;
-                bits += 8;
+                bits += width;
             }
         }
         DEC_STAMP(0);
