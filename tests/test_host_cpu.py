@@ -123,3 +123,72 @@ def test_product_package_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(d, f)).read()), os.path.join(d, f)
+
+
+def _path_walk_decode_pose(root_score, root_id, root_xy, scores, offsets, stride, fwd, bwd):
+    """The scheme of csrc/decode.cu's speculative phase, restated on the host: the thread of part k walks the unique tree
+    path root -> k (child -> parent hops with ``bwd`` first, then parent -> child hops with ``fwd``) and stops where the
+    reference's ``score[source] > 0.0`` gate would; parts that are not reached keep zeros."""
+    up, up_edge = [0] * odec.PARTS, [-1] * odec.PARTS
+    for e, (parent, child) in enumerate(odec.EDGES):
+        up[child], up_edge[child] = parent, e
+    anc = []
+    for k in range(odec.PARTS):
+        chain, c = {k}, k
+        while c != 0:
+            c = up[c]
+            chain.add(c)
+        anc.append(chain)
+    ks, kc, ko = np.zeros(odec.PARTS), np.zeros((odec.PARTS, 2)), np.zeros((odec.PARTS, 2))
+    hops = 0
+    for k in range(odec.PARTS):
+        cur, sc, xy, off, reached, n = root_id, root_score, np.asarray(root_xy, dtype=np.float64), np.zeros(2), True, 0
+        while cur != k:
+            if not (sc > 0.0):
+                reached = False
+                break
+            if cur not in anc[k]:                                   # climb: child -> parent
+                nxt, e, disp = up[cur], up_edge[cur], bwd
+            else:                                                   # descend towards k: parent -> child
+                nxt = k
+                while up[nxt] != cur:
+                    nxt = up[nxt]
+                e, disp = up_edge[nxt], fwd
+            sc, xy, off = odec._hop(e, xy, nxt, scores, offsets, stride, disp)
+            cur = nxt
+            n += 1
+        hops = max(hops, n)
+        if reached:
+            ks[k], kc[k], ko[k] = sc, xy, off
+    return ks, kc, ko, hops
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_per_part_path_walk_equals_the_two_pass_decode_pose(seed):
+    # decode.py:131-182 reaches every part along its tree path from the root, and a hop only depends on its source coordinates:
+    # the equivalence the CUDA decoder's 17-threads-per-pose phase rests on, checked for every root part, with zero, negative
+    # and NaN scores on the paths (the `> 0.0` / `== 0.0` gates), bit for bit
+    from oracle import synth
+    rng = np.random.default_rng(seed)
+    h, w, stride = int(rng.integers(5, 30)), int(rng.integers(5, 30)), int(rng.choice([8, 16, 32]))
+    heat, off, fwd, bwd = synth.random_heads(h, w, seed=seed, disp_scale=float(rng.uniform(5, 90)), off_scale=float(rng.uniform(1, 20)),
+                                             zero_frac=float(rng.choice([0.0, 0.2, 0.5])))[:4]
+    heat = heat.copy()
+    if seed % 2:
+        mask = rng.random(heat.shape)
+        heat[mask < 0.05] = -0.25
+        heat[mask > 0.97] = np.nan
+    split = lambda a: np.asarray(a, dtype=np.float32).reshape(2, -1, h, w).transpose(1, 2, 3, 0)
+    offs, f, b = split(off), split(fwd), split(bwd)
+    longest = 0
+    for root_id in range(odec.PARTS):
+        for _ in range(4):
+            y, x = int(rng.integers(0, h)), int(rng.integers(0, w))
+            root_score = float(rng.choice([heat[root_id, y, x], 0.7]))
+            root = np.array([y, x]) * stride + offs[root_id, y, x]
+            ref = odec.decode_pose(root_score, root_id, root, heat, offs, stride, f, b)
+            got = _path_walk_decode_pose(root_score, root_id, root, heat, offs, stride, f, b)
+            for a_, b_ in zip(got[:3], ref):
+                assert np.array_equal(a_, b_, equal_nan=True)
+            longest = max(longest, got[3])
+    assert longest <= 8                                              # ankle -> nose -> other ankle
