@@ -192,3 +192,28 @@ def test_per_part_path_walk_equals_the_two_pass_decode_pose(seed):
                 assert np.array_equal(a_, b_, equal_nan=True)
             longest = max(longest, got[3])
     assert longest <= 8                                              # ankle -> nose -> other ankle
+
+
+@pytest.mark.parametrize("mid,H,W,os_,fmap,total,gemm,dw,stem", [
+    (101, 513, 513, 16, (33, 33), 9.066, 8.742, 0.210, 0.114),       # C1 / C2
+    (50, 721, 1281, 8, (91, 161), 17.860, 16.936, None, None),      # C3
+    (75, 257, 257, 32, (17, 17), 1.001, 0.940, None, None),         # C4 ("OS32" is really 16)
+])
+def test_bench_algorithmic_work_matches_the_survey(mid, H, W, os_, fmap, total, gemm, dw, stem):
+    # the per-image flops bench.py's roofline entries are built from (2 * MACs), per config
+    import bench
+    rows, hw = bench.layer_costs(posenet.MobileNetV1(mid, output_stride=os_), 1, H, W)
+    assert hw == fmap
+    f = {name: flops for name, _, flops in rows}
+    s_stem = f["stem"]
+    s_dw = sum(v for k, v in f.items() if k.startswith("dw"))
+    s_gemm = sum(v for k, v in f.items() if k.startswith("pw")) + f["heads"]
+    assert round((s_stem + s_dw + s_gemm) / 1e9, 3) == total
+    assert round(s_gemm / 1e9, 3) == gemm
+    if dw is not None:
+        assert round(s_dw / 1e9, 3) == dw and round(s_stem / 1e9, 3) == stem
+    # a fused block moves its input and its output once: strictly less than depthwise + pointwise apart
+    b = {name: nbytes for name, nbytes, _ in rows}
+    for k in [k for k in b if k.startswith("sep")]:
+        i = k[3:]
+        assert b[k] < b["dw" + i] + b["pw" + i]
