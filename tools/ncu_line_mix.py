@@ -8,7 +8,7 @@ import collections, csv, sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 24
-cur, hdr = None, None
+cur, hdr, line = None, None, None
 agg = collections.defaultdict(lambda: [0.0, 0.0, ""])
 for r in rows:
     if not r:
@@ -17,14 +17,21 @@ for r in rows:
         cur = r[1].split("/")[-1]
         continue
     if r[0] == "Line No":
-        hdr = r
+        hdr, line = r, None
         continue
     if hdr is None or len(r) < 10:
         continue
-    if not r[0]:
-        continue                                   # the SASS rows under a source line; the line's own row already sums them
+    if r[0]:                                       # a source line's own row: remember it, count only the SASS rows under it
+        try:
+            line = int(r[0])
+        except ValueError:
+            line = None
+        if line is not None and r[1] and not agg[(cur, line)][2]:
+            agg[(cur, line)][2] = " ".join(r[1].split())[:100]
+        continue
+    if line is None:
+        continue
     try:
-        line = int(r[0])
         ex, sm = float(r[hdr.index("Instructions Executed")]), float(r[hdr.index("# Samples")])
     except ValueError:
         continue
