@@ -124,6 +124,8 @@ typedef struct pn_decode_params {
 
 /* ---- D1-D4: decode_multi.py:61-148 + decode.py:9-63,131-182 (greedy multi-pose decode, float64).
  * One thread block per image; candidates are consumed in (score desc, flat index asc) order.
+ * keys / counts are pn_candidates' outputs: the keys of an image must be pairwise distinct (they are -- the
+ * low word is the cell index) and non-zero; the in-kernel radix selection relies on it.
  * Outputs (float64): pose_scores [n_img,P], kp_scores [n_img,P,17], kp_coords [n_img,P,17,2] (y,x),
  * kp_offsets [n_img,P,17,2]; pose_counts int32 [n_img].  The buffers need not be initialised: the rows
  * past pose_counts[i] are zero-padded by the kernel (the reference's np.zeros, decode_multi.py:94-100). */
