@@ -217,3 +217,65 @@ def test_bench_algorithmic_work_matches_the_survey(mid, H, W, os_, fmap, total, 
     for k in [k for k in b if k.startswith("sep")]:
         i = k[3:]
         assert b[k] < b["dw" + i] + b["pw" + i]
+
+
+def _radix_chunks(keys, chunk=1024):
+    """Host model of the candidate selection in csrc/decode.cu (decode_kernel, step 1): the best <= `chunk` keys greater than
+    `lo` are cut off by an MSB-first radix descent (8 bits per level) that starts below the bits all remaining keys share."""
+    keys = [int(k) for k in keys]
+    lo, remaining, out = 0, len(keys), []
+    while remaining > 0:
+        pivot = (1 << 64) - 1
+        if remaining > chunk:
+            live = [k for k in keys if k > lo]
+            mn, mx = min(live), max(live)
+            bits = 64 - (mn ^ mx).bit_length()                      # __clzll(min ^ max)
+            prefix = mn >> (64 - bits) if bits else 0
+            while True:
+                width = min(8, 64 - bits)
+                shift = 64 - bits - width
+                hist = [0] * 256
+                for k in live:
+                    if bits == 0 or (k >> (64 - bits)) == prefix:
+                        hist[(k >> shift) & ((1 << width) - 1)] += 1
+                cum, sel, first = 0, -1, -1
+                for d in range(256):
+                    c = hist[d]
+                    if c and first < 0:
+                        first = d
+                    if cum + c > chunk:
+                        break
+                    cum += c
+                    if c:
+                        sel = d
+                if sel >= 0:
+                    pivot = (((prefix << width) | sel) << shift) | ((1 << shift) - 1)
+                    break
+                prefix, bits = (prefix << width) | first, bits + width
+                assert bits <= 64
+        got = sorted(k for k in keys if lo < k <= pivot)
+        assert 1 <= len(got) <= max(chunk, 1) or remaining <= chunk
+        out.append(got)
+        lo, remaining = pivot, remaining - len(got)
+    return out
+
+
+@pytest.mark.parametrize("kind", ["random", "near_half", "plateaus", "two_levels"])
+def test_radix_selection_model_partitions_the_sorted_candidates(kind):
+    # keys as pn_candidates builds them: high word = inverted orderable score bits, low word = flat cell index (unique)
+    rng = np.random.default_rng(5)
+    n = 6000
+    if kind == "random":
+        score = rng.random(n, dtype=np.float32)
+    elif kind == "near_half":                                        # random-init heatmaps: everything within 1e-3 of 0.5
+        score = (0.5 + 1e-3 * rng.random(n)).astype(np.float32)
+    elif kind == "plateaus":                                         # six distinct values only: the index word must separate
+        score = rng.choice(np.linspace(0.3, 0.9, 6), n).astype(np.float32)
+    else:
+        score = np.where(rng.random(n) < 0.5, np.float32(0.75), rng.random(n, dtype=np.float32)).astype(np.float32)
+    u = score.view(np.uint32).astype(np.uint64) ^ np.uint64(0x80000000)                  # positive floats: set the sign bit
+    keys = ((~u & np.uint64(0xFFFFFFFF)) << np.uint64(32)) | rng.permutation(n).astype(np.uint64)
+    chunks = _radix_chunks(keys)
+    assert all(1 <= len(c) <= 1024 for c in chunks)
+    flat = [k for c in chunks for k in c]
+    assert flat == sorted(int(k) for k in keys)                      # ascending key == descending score, index ascending
