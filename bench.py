@@ -5,8 +5,10 @@
 One "step" = one pass of  uint8 images -> (fused preprocess) stem -> 13 separable blocks -> heads ->
 part candidates -> greedy decode  over one batch.  Default workload = BASELINE.json configs[1]:
 MobileNetV1 model 101, 513x513, output stride 16, batch 64 per GPU, bf16, random-init weights, synthetic images.
-Rank 0 prints ONE JSON line (see the keys below).  ``--impl reference`` times the CPU oracle port
-(the reference's algorithm: torch-CPU fp32 convs + numpy float64 decode) on the host cores instead.
+Rank 0 prints ONE JSON line (see the keys below).  ``--impl reference`` times the reference's own CPU code on the host
+cores instead: the unmodified reference package byte-compiled into ``oracle/_ref`` by ``oracle/make_ref.py``
+(``cpu_baseline.kind`` "reference"), or, when that build is absent, the oracle port (``kind`` "port": torch-CPU fp32
+convs + numpy float64 decode).  Both arms print the same ``config`` dict; how each arm batches the workload is in ``run``.
 """
 import argparse
 import json
@@ -17,9 +19,10 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (os.path.join(ROOT, "posenet-pytorch_b200"), ROOT):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+PKG = os.path.join(ROOT, "posenet-pytorch_b200")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)          # `oracle` (checker / CPU arm).  The product arm adds PKG; the reference arm adds oracle/_ref:
+                                      # both packages are called `posenet`, so a process imports exactly one of them.
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -34,6 +37,17 @@ WORKLOADS = {
 SOURCE_SIZE = {"c3": (720, 1280)}          # frames arrive at webcam resolution (utils.py:51-55) and are resized on the GPU
 METRIC = "images/sec (backbone+decode)"
 DECODE_KW = dict(max_pose_detections=10, score_threshold=0.5, nms_radius=20, min_pose_score=0.25)  # benchmark.py:37-44
+
+
+def workload_config(name):
+    """The `config` object of the JSON line -- identical for the product arm and the reference arm (what is computed);
+    how an arm batches it (64 images per launch chain on the GPU, one image at a time on the host like benchmark.py:32-44)
+    is reported separately under `run`."""
+    mid, H, W, os_, batch, desc = WORKLOADS[name]
+    sh, sw = SOURCE_SIZE.get(name, (H, W))
+    return {"workload": desc, "model": "mobilenet_v1_%03d" % mid, "network_input": "%dx%d" % (H, W), "source_frames": "%dx%d" % (sh, sw),
+            "output_stride": os_, "decode": DECODE_KW, "weights": "random-init (torch default init, seed 0)",
+            "images": "synthetic uint8 noise, seeded"}
 
 
 def peaks():
@@ -135,19 +149,43 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------ reference arm
 def cpu_reference_run(workload, images_per_step, steps, warmup):
-    """The reference's algorithm on the host cores: batch 1 per image like benchmark.py:32-44 --
-    preprocess (utils.py:13-26), forward (mobilenet_v1.py:156-162, torch CPU fp32), decode (decode_multi.py:61-148)."""
-    from oracle import decode as odec, net as onet, preprocess as opre, synth
+    """The reference's path on the host cores, one image at a time like benchmark.py:32-44 (plus the pre-processing of :29):
+    utils._process_input (utils.py:13-26) -> MobileNetV1.forward (mobilenet_v1.py:156-162, torch CPU fp32) ->
+    decode_multiple_poses (decode_multi.py:61-148).  Runs the reference's OWN code from oracle/_ref when that build exists
+    (kind "reference"), the oracle port otherwise (kind "port").  Must be called in a process that has not imported the
+    product package (both are named `posenet`)."""
+    from oracle import make_ref, synth
     mid, H, W, os_, _, _ = WORKLOADS[workload]
+    sh, sw = SOURCE_SIZE.get(workload, (H, W))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = onet.init_params(mid, seed=0)
-    imgs = [synth.noise_image(H, W, s) for s in range(4)]
+    imgs = [synth.noise_image(sh, sw, s) for s in range(4)]
+    if make_ref.available():
+        assert "posenet" not in sys.modules, "the reference arm needs a process that has not imported the product package"
+        sys.path.insert(0, make_ref.REF_DIR)
+        import posenet as ref
+        import posenet.decode_multi as ref_dm
+        assert os.path.realpath(ref.__file__).startswith(os.path.realpath(make_ref.REF_DIR)), ref.__file__
+        torch.manual_seed(0)
+        model = ref.MobileNetV1(mid, output_stride=os_)          # load_model minus the checkpoint file: default init, seeded
+        kind, how = "reference", "unmodified reference package (oracle/_ref, byte-compiled by oracle/make_ref.py)"
 
-    def one(i):
-        x, _, _ = opre.process_input(imgs[i % len(imgs)], 1.0, os_)
-        heads = onet.forward(sd, mid, os_, torch.from_numpy(x))
-        return odec.decode_multiple_poses(*[t.squeeze(0).numpy() for t in heads], os_, **DECODE_KW)
+        def one(i):
+            x, _, _ = ref.utils._process_input(imgs[i % len(imgs)], 1.0, os_)                     # benchmark.py:29
+            with torch.no_grad():
+                heat, off, fwd, bwd = model(torch.Tensor(x))                                       # benchmark.py:33-36
+                return ref_dm.decode_multiple_poses(heat.squeeze(0), off.squeeze(0), fwd.squeeze(0), bwd.squeeze(0),
+                                                    output_stride=os_, max_pose_detections=DECODE_KW["max_pose_detections"],
+                                                    min_pose_score=DECODE_KW["min_pose_score"])   # benchmark.py:37-44
+    else:
+        from oracle import decode as odec, net as onet, preprocess as opre
+        sd = onet.init_params(mid, seed=0)
+        kind, how = "port", "oracle port (oracle/_ref not built here)"
+
+        def one(i):
+            x, _, _ = opre.process_input(imgs[i % len(imgs)], 1.0, os_)
+            heads = onet.forward(sd, mid, os_, torch.from_numpy(x))
+            return odec.decode_multiple_poses(*[t.squeeze(0).numpy() for t in heads], os_, **DECODE_KW)
 
     for i in range(warmup):
         one(i)
@@ -156,23 +194,39 @@ def cpu_reference_run(workload, images_per_step, steps, warmup):
         for i in range(images_per_step):
             one(s * images_per_step + i)
     dt = time.perf_counter() - t0
-    return dict(value=steps * images_per_step / dt, ms_per_step=dt / steps * 1e3, cores=cores,
-                sample="%d steps x %d images, batch 1, torch-CPU fp32 forward + numpy f64 decode" % (steps, images_per_step))
+    return dict(value=steps * images_per_step / dt, ms_per_step=dt / steps * 1e3, cores=cores, kind=kind,
+                sample="%d steps x %d images, one image per call (benchmark.py:32-44), %s: cv2 preprocess + torch-CPU fp32 forward + "
+                       "numpy f64 decode, %d torch threads" % (steps, images_per_step, how, cores))
+
+
+REF_IMAGES_PER_STEP = 4
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    mid, H, W, os_, batch, desc = WORKLOADS[args.workload]
-    r = cpu_reference_run(args.workload, images_per_step=4, steps=args.steps, warmup=args.warmup)
+    r = cpu_reference_run(args.workload, images_per_step=REF_IMAGES_PER_STEP, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "images/sec", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "images_per_step": 4, "batch": 1},
-            "cpu_baseline": {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "config": workload_config(args.workload),
+            "run": {"images_per_step": REF_IMAGES_PER_STEP, "batch": 1, "device": "host cpu", "threads": r["cores"]},
+            "cpu_baseline": {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(workload, steps=3, warmup=1):
+    """cpu_baseline of the product line: the reference arm in a fresh process (this one has imported the product `posenet`)."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", str(steps),
+                              "--warmup", str(warmup)], capture_output=True, text=True, timeout=900,
+                             env={k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")})
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        return line["cpu_baseline"]
+    except Exception as e:                                           # the product line must not die with its baseline leg
+        return {"value": None, "unit": "images/sec", "cores": os.cpu_count(), "kind": "unavailable", "sample": "failed: %r" % (e,)}
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
@@ -236,7 +290,38 @@ def per_kernel_times(model, imgs_list, reps=5):
     return times
 
 
+def h2d_ceiling(host_batches, dev, world, reps=6):
+    """What the host can feed: plain pinned-host -> device copies of the SAME buffers the end-to-end leg submits, nothing else
+    running, every rank at once (barrier, CUDA events, max over ranks).  Returns aggregate GB/s over all ranks."""
+    dst = [torch.empty_like(h, device=dev) for h in host_batches[:2]]
+    st = torch.cuda.Stream(dev)
+
+    def burst(n):
+        with torch.cuda.stream(st):
+            for i in range(n):
+                dst[i % 2].copy_(host_batches[i % len(host_batches)], non_blocking=True)
+    burst(2)
+    st.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        e0.record(st)
+    burst(reps)
+    with torch.cuda.stream(st):
+        e1.record(st)
+    st.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t)
+    return world * reps * host_batches[0].numel() / (ms * 1e-3) / 1e9
+
+
 def run_b200(args):
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
     import posenet
     from posenet import _native as nat
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -324,11 +409,43 @@ def run_b200(args):
         ms = float(t)
     value = world * batch * args.steps / (ms / 1e3)
 
+    # ---- sustained leg: the SAME graph replays for >= `--sustain` seconds (the timed region above is a 0.03 s burst at the boost
+    # clock; MEASURED_PEAKS.json shows this pool settling to a lower SM clock under a seconds-long load).  Device-timed, max over
+    # ranks, with its own clock / throttle-reason samples.
+    sustained = None
+    if args.sustain > 0:
+        barrier()
+        s_sampler = ClockSampler(local)
+        s_sampler.start()
+        chunk = max(8, int(0.25 / (ms / args.steps / 1e3)))           # ~0.25 s of replays between host synchronisations
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_s = time.perf_counter()
+        s0.record()
+        n_rep = 0
+        while time.perf_counter() - t_s < args.sustain:
+            for _ in range(chunk):
+                graphs[n_rep % n_sets][0].replay()
+                n_rep += 1
+            torch.cuda.current_stream().synchronize()
+        s1.record()
+        torch.cuda.synchronize()
+        s_sampler.window = (t_s, time.perf_counter())
+        s_ms = s0.elapsed_time(s1)
+        s_clk = s_sampler.summary()
+        rate = batch * n_rep / (s_ms / 1e3)                            # this rank's images/s over its own window
+        if world > 1:
+            t = torch.tensor([rate], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+            rate = float(t)                                           # slowest rank x world: ranks run the same load independently
+        sustained = {"value": round(world * rate, 1), "unit": "images/sec", "seconds": round(s_ms / 1e3, 2), "steps": n_rep,
+                     "ms_per_step": round(s_ms / n_rep, 4), "vs_burst": round(world * rate / value, 4),
+                     "clocks": {k: s_clk.get(k) for k in ("sm_mhz", "sm_min_mhz", "sm_max_mhz", "reasons", "samples_in_timed_region")}}
+
     # ---- end to end through the public API (posenet.BatchPipeline): every step copies ITS pinned host uint8 batch to the
     # device, runs model + decode, and copies ITS pose records back to pinned host memory; the copies of neighbouring
     # steps overlap the kernels (2 slots in flight), nothing is cached across steps.
     e2e_steps = 1 if args.skip_e2e else args.steps
-    pipe = posenet.BatchPipeline(model, batch, sh, sw, depth=2, output_stride=os_, **DECODE_KW)
+    pipe = posenet.BatchPipeline(model, batch, sh, sw, depth=args.depth, output_stride=os_, gather=world > 1, **DECODE_KW)
     for rec in pipe.run(host[i % n_sets] for i in range(1 if args.skip_e2e else max(3, args.warmup))):
         pass
     barrier()
@@ -342,13 +459,24 @@ def run_b200(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_s = float(t)
     e2e = {"value": world * batch * e2e_steps / e2e_s, "unit": "images/sec", "h2d_bytes_per_step": int(pipe.h2d_bytes_per_batch),
-           "d2h_bytes_per_step": int(pipe.d2h_bytes_per_batch), "api": "posenet.BatchPipeline.run (depth 2)"}
+           "d2h_bytes_per_step": int(pipe.d2h_bytes_per_batch), "api": "posenet.BatchPipeline.run (depth %d)" % args.depth}
+    if world > 1:
+        # every step's pose records were all-gathered over NCCL inside the timed loop above (BatchPipeline(gather=True): each rank
+        # ends the step holding the records of all `world` shards); its device time alone, for the record:
+        e2e["gather"] = "all_gather_into_tensor of %d B per rank per step (NCCL), inside the timed loop" % (pipe.d2h_bytes_per_batch // world)
+        e2e["gather_ms"] = round(pipe.time_gather(reps=20), 4)
     # the same step without overlap (one batch at a time, synchronous), for reference
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         rec = pipe.result(pipe.submit(host[i % n_sets]), copy=False)
     e2e["value_serial"] = world * batch * e2e_steps / (time.perf_counter() - t0)
     del pipe
+    if not args.skip_e2e:
+        # the ceiling the host can feed: the same pinned batches, copies only, all ranks at once
+        gbs = h2d_ceiling(host, dev, world)
+        e2e["h2d_ceiling_gbs"] = round(gbs, 1)
+        e2e["h2d_gbs"] = round(e2e["value"] * (host[0].numel() / batch) / 1e9, 1)
+        e2e["frac_of_h2d_ceiling"] = round(e2e["h2d_gbs"] / gbs, 4)
 
     if rank != 0:
         return
@@ -366,11 +494,13 @@ def run_b200(args):
             continue                                             # fused plans have sepN, unfused dwN + pwN
         t = times[name] * 1e-3
         ai = flops / nbytes
-        tensor_bound = name.startswith(("pw", "sep", "heads")) and ai > pk["bf16_sustained"] * 1e3 / pk["hbm"]
+        # each kernel is timed alone inside a 1.6 ms step at the boost clock: the burst bf16 peak is its denominator (and sets
+        # the ridge); the sustained peak belongs to the sustained leg only
+        tensor_bound = name.startswith(("pw", "sep", "heads")) and ai > pk["bf16_burst"] * 1e3 / pk["hbm"]
         kernels.append({"name": name, "ms": round(times[name], 4), "share": round(times[name] / total_ms, 4),
                         "gbs": round(nbytes / t / 1e9, 1), "tflops": round(flops / t / 1e12, 2),
                         "bound": "tensor" if tensor_bound else "hbm",
-                        "frac": round((flops / t / 1e12) / pk["bf16_sustained"] if tensor_bound else (nbytes / t / 1e9) / pk["hbm"], 4)})
+                        "frac": round((flops / t / 1e12) / pk["bf16_burst"] if tensor_bound else (nbytes / t / 1e9) / pk["hbm"], 4)})
     top = max(kernels, key=lambda k: k["ms"])
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of the same workload
     # (profiles/ncu_traffic.json: launch name -> dram__bytes_read.sum + dram__bytes_write.sum), null if not captured
@@ -382,27 +512,29 @@ def run_b200(args):
             traffic = t.get("dram_bytes", {}).get(top["name"])
     roofline = {"kernel": top["name"], "bound": top["bound"],
                 "achieved": top["tflops"] if top["bound"] == "tensor" else top["gbs"],
-                "peak": pk["bf16_sustained"] if top["bound"] == "tensor" else pk["hbm"],
+                "peak": pk["bf16_burst"] if top["bound"] == "tensor" else pk["hbm"],
                 "unit": "TFLOP/s" if top["bound"] == "tensor" else "GB/s", "frac": top["frac"], "traffic": traffic,
                 "algorithmic_bytes": next(nb for nm, nb, _ in costs if nm == top["name"]),
-                "peak_source": pk["src"] + (" (sustained)" if top["bound"] == "tensor" else "")}
+                "peak_source": pk["src"] + (" (burst: the kernel is timed alone)" if top["bound"] == "tensor" else "")}
     if all_cpus:
         os.sched_setaffinity(0, all_cpus)                        # the CPU baseline gets every host core again
-    cpu = cpu_reference_run("c2" if args.workload == "c2" else args.workload, images_per_step=4, steps=3, warmup=1) \
-        if (world == 1 and not args.skip_cpu) else None
+    cpu = cpu_baseline_subprocess(args.workload) if (world == 1 and not args.skip_cpu) else None
     launches = model.num_launches(batch, H, W, True) + 2 + (1 if resized is not None else 0)   # + candidates, decode (+ resize)
     line = {"metric": METRIC, "value": round(value, 1), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": batch, "decode": DECODE_KW, "weights": "random-init (torch default, seed 0)",
-                       "l2": "inputs rotate over %d batches (%d MB > 126 MB L2); per-step activation traffic >> L2" % (
-                           n_sets, n_sets * host[0].numel() // 2 ** 20), "cuda_graph": True,
-                       "fused_blocks": bool(model.fused_blocks), "cpu_affinity": affinity},
+            "config": workload_config(args.workload),
+            "run": {"batch_per_gpu": batch, "images_per_step": world * batch, "device": "B200 x %d" % world, "compute": "bf16 activations / fp32 accumulate",
+                    "l2": "inputs rotate over %d batches (%d MB > 126 MB L2); per-step activation traffic >> L2" % (
+                        n_sets, n_sets * host[0].numel() // 2 ** 20), "cuda_graph": True,
+                    "fused_blocks": bool(model.fused_blocks), "cpu_affinity": affinity},
             "e2e": e2e, "gpu_launches": launches * args.steps, "clocks": clocks, "roofline": roofline,
             "kernels": kernels, "forward_ms_sum_of_kernels": round(total_ms, 3)}
+    if sustained:
+        line["sustained"] = sustained
+        line["value_sustained"] = sustained["value"]
     if cpu:
-        line["cpu_baseline"] = {"value": round(cpu["value"], 2), "unit": "images/sec", "cores": cpu["cores"], "kind": "port",
-                                "sample": cpu["sample"]}
+        line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -418,6 +550,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: skip the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
+    ap.add_argument("--sustain", type=float, default=3.0, help="seconds of back-to-back replays for the sustained leg (0: skip)")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight in the end-to-end leg (BatchPipeline depth)")
     ap.add_argument("--unfused", action="store_true", help="run every block as depthwise + pointwise kernels (A/B against the fused blocks)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 4
+#define PN_ABI_VERSION 5
 
 typedef void *pn_stream_t; /* cudaStream_t */
 
@@ -81,18 +81,6 @@ int pn_pwconv_gemm(const void *a, const void *w, const float *bias, void *y, int
  * pw_b f32 [cout]; y: NHWC [n,ho,wo,cout].  cin % 8 == 0, cout % 16 == 0, (stride,dilation) in (1,1|2|4), (2,1). */
 int pn_sepconv_block(const void *x, const float *dw_w, const float *dw_b, const void *pw_w, const float *pw_b, void *y,
                      int n, int h, int wd, int cin, int cout, int stride, int dilation, pn_stream_t stream);
-/* Diagnostic for the tensor-pipe depthwise (csrc/dwtc_probe.cu): one 128-position chunk of one 64-channel bf16 image
- * [h, wd, 64] through shifted-descriptor tcgen05 depthwise (block-diagonal tap tiles `diag` [9*16, 64]) and an
- * A-from-TMEM pointwise (`pw_w` [64, 64]); out_dw / out_pw: f32 [128, 64].  Not part of the product path. */
-int pn_dwtc_probe(const void *x, int h, int wd, const void *diag, const void *pw_w, const float *dw_bias, float *out_dw,
-                  float *out_pw, int wp, int dil, int qoff, int rows_box, int x_org, int y_org, int flags, pn_stream_t stream);
-/* Diagnostics of the tensor-pipe depthwise path (csrc/septc.cu, PN_SEP_TC=1).  pn_debug_tcs_trace registers a zero-filled
- * device buffer of 6 roles x cap steps x 4 int64 clock stamps that CTA 0 of the next pn_sepconv_block launches fills
- * ((NULL, 0) turns it off).  pn_debug_umma_cost times 9 * reps tcgen05.mma (M128 x n x K16, bf16) on one SM; layout
- * 0 / 1 / 2 = 128 / 32 / 64-byte swizzle issued by one thread, 3 = 128-byte swizzle issued from warp-uniform code;
- * out_host[0] = cycles until the last issue, out_host[1] = until completion (synchronous, default stream). */
-int pn_debug_tcs_trace(long long *device_buf, int cap);
-int pn_debug_umma_cost(int n, int layout, int reps, int a_step16, long long *out_host);
 /* Tile shape / pipeline depths pn_sepconv_block would pick for a block (host arithmetic only; diagnostics). */
 int pn_sepconv_describe(int n, int h, int wd, int cin, int cout, int stride, int dilation, char *out_host, int capacity);
 
@@ -133,6 +121,29 @@ int pn_decode_greedy(const pn_map *heat, const pn_map *off, const pn_map *fwd, c
                      int n_img, int h, int wd, const uint64_t *keys, int capacity, const int *counts,
                      const pn_decode_params *params, double *pose_scores, double *kp_scores,
                      double *kp_coords, double *kp_offsets, int *pose_counts, pn_stream_t stream);
+
+/* ---- D3: posenet/decode.py:9-63 (traverse_to_targ_keypoint) as a stand-alone call: ONE displacement hop along edge
+ * `edge_id` from `source_keypoint_host` (float64 (y, x) image coordinates, HOST pointer) to part `target_keypoint_id`.
+ * heat [1,17,h,w], off [1,34,h,w], disp [1,32,h,w] (channels 0..15 dy, 16..31 dx), any strides.
+ * out7 (device, float64): score, image_coord y, x, displacement_vector y, x, offset y, x -- the fp32 values widened exactly. */
+int pn_traverse_to_targ_keypoint(int edge_id, const double *source_keypoint_host, int target_keypoint_id,
+                                 const pn_map *heat, const pn_map *off, const pn_map *disp, int h, int wd,
+                                 int output_stride, double *out7, pn_stream_t stream);
+
+/* ---- D2: posenet/decode.py:131-182 (decode_pose) as a stand-alone call for ONE root: backward edges 15..0 through `bwd`, then
+ * forward edges 0..15 through `fwd`; a hop needs score[source] > 0.0 and an undecoded (== 0.0) target.
+ * root_image_coord_host: float64 (y, x), HOST pointer.  out85 (device, float64): instance_keypoint_scores [17],
+ * instance_keypoint_coords [17,2], instance_offsets [17,2] (the root's offset row stays 0, decode.py:150). */
+int pn_decode_pose(double root_score, int root_id, const double *root_image_coord_host, const pn_map *heat,
+                   const pn_map *off, const pn_map *fwd, const pn_map *bwd, int h, int wd, int output_stride,
+                   double *out85, pn_stream_t stream);
+
+/* ---- N4: image_demo.py:50 (`keypoint_coords *= output_scale`, output_scale = (src_h / target_h, src_w / target_w) of
+ * utils.py:19) for a batch of pose records ON THE DEVICE: kp_coords float64 [n_img, points_per_img, 2] (y, x), multiplied in
+ * place (IEEE float64 multiply, what numpy does).  scales: device float64 [n_img, 2] with one (y, x) factor per image (frames
+ * of different sizes), or NULL for the uniform (scale_y, scale_x). */
+int pn_scale_keypoint_coords(double *kp_coords, int n_img, int points_per_img, const double *scales, double scale_y,
+                             double scale_x, pn_stream_t stream);
 
 /* ---- Whole-network plan: mobilenet_v1.py:130-162 (MobileNetV1.__init__/forward) --------------------
  * The layer table is computed by the caller (posenet/models/mobilenet_v1.py mirrors

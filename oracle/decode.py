@@ -39,8 +39,9 @@ def _cell(p, stride, h, w):
     return np.clip(np.round(p / stride), a_min=0, a_max=[h - 1, w - 1]).astype(np.int32)
 
 
-def _hop(edge, src_xy, target, scores, offsets, stride, disp):
-    """decode.py:9-63 ``traverse_to_targ_keypoint`` (single step, no refinement)."""
+def traverse_to_targ_keypoint(edge, src_xy, target, scores, offsets, stride, disp):
+    """decode.py:9-63 (single step, no refinement).  ``offsets`` [17,h,w,2], ``disp`` [16,h,w,2] (decode_multi.py:89-97).
+    Returns the reference's 4-tuple ``(score, image_coord, displacement_vector, offset)``."""
     h, w = scores.shape[1], scores.shape[2]
     si = _cell(src_xy, stride, h, w)
     d = disp[edge, si[0], si[1]]                  # f32[2] (dy, dx)
@@ -48,7 +49,12 @@ def _hop(edge, src_xy, target, scores, offsets, stride, disp):
     ti = _cell(p, stride, h, w)
     sc = scores[target, ti[0], ti[1]]
     off = offsets[target, ti[0], ti[1]]           # f32[2]
-    return sc, ti * stride + off, off
+    return sc, ti * stride + off, d, off
+
+
+def _hop(edge, src_xy, target, scores, offsets, stride, disp):
+    sc, xy, _, off = traverse_to_targ_keypoint(edge, src_xy, target, scores, offsets, stride, disp)
+    return sc, xy, off
 
 
 def decode_pose(root_score, root_id, root_xy, scores, offsets, stride, fwd, bwd):

@@ -26,12 +26,19 @@ bool pdl_enabled() {
     return on == 1;
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+    return dev;
+}
+
 int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;
+    static DeviceOnce cache;                      // per device: a mixed box must not size grids by device 0's SM count
+    const int dev = current_device();
+    int sms = cache.get(dev);
+    if (sms <= 0) {
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cache.set(dev, sms);
     }
     return sms;
 }

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/posenet_b200.h"
 
 namespace pn {
@@ -51,7 +53,20 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
-int num_sms();
+int current_device();   // cudaGetDevice (0 when the query fails)
+int num_sms();          // SM count of the CURRENT device
+
+// One-time setup per DEVICE: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and occupancy queries apply to the current
+// device only, so a process that drives several GPUs must repeat them on each.  Usage:
+//     static DeviceOnce once;  const int dev = current_device();
+//     if (once.get(dev) < wanted) { ...setup on the current device...;  once.set(dev, wanted); }
+// Racing threads at worst both run the (idempotent) setup.
+constexpr int PN_MAX_DEVICES = 64;
+struct DeviceOnce {
+    std::atomic<int> v[PN_MAX_DEVICES];
+    int get(int dev) const { return dev >= 0 && dev < PN_MAX_DEVICES ? v[dev].load(std::memory_order_acquire) : 0; }
+    void set(int dev, int value) { if (dev >= 0 && dev < PN_MAX_DEVICES) v[dev].store(value, std::memory_order_release); }
+};
 
 // ---- shared epilogue description for both GEMM paths -------------------------------------------
 // EPI_RELU6: y[m, n] = clamp(acc + bias[n], 0, 6) stored row-major [M, N] in the activation dtype.

@@ -151,20 +151,27 @@ __device__ double np_sum(const double *a, int n) {
 }
 
 // decode.py:9-63: one displacement hop along edge e from the source at (cy, cx) to part `tgt`; on return (cy, cx) are the
-// target's coordinates, sc its score and (oy, ox) its offset vector.
-__device__ __forceinline__ void hop(const DecodeArgs &a, int img, const pn_map &disp, int e, int tgt, double &cy, double &cx,
-                                    float &sc, float &oy, float &ox) {
+// target's coordinates, sc its score, (oy, ox) its offset vector and (dy, dx) the displacement vector that was followed.
+__device__ __forceinline__ void hop_full(const DecodeArgs &a, int img, const pn_map &disp, int e, int tgt, double &cy, double &cx,
+                                         float &sc, float &oy, float &ox, float &dy, float &dx) {
     const int os = a.prm.output_stride;
     const double stride = (double)os, inv = (os & (os - 1)) == 0 ? 1.0 / stride : 0.0;
     const int iy = to_cell(cy, stride, inv, a.h - 1), ix = to_cell(cx, stride, inv, a.w - 1);
-    const double py = __dadd_rn(cy, (double)map_at(disp, img, e, iy, ix));                    // decode.py:39-40
-    const double px = __dadd_rn(cx, (double)map_at(disp, img, PN_NUM_EDGES + e, iy, ix));
+    dy = map_at(disp, img, e, iy, ix);                                                        // decode.py:39
+    dx = map_at(disp, img, PN_NUM_EDGES + e, iy, ix);
+    const double py = __dadd_rn(cy, (double)dy);                                              // decode.py:40
+    const double px = __dadd_rn(cx, (double)dx);
     const int ty = to_cell(py, stride, inv, a.h - 1), tx = to_cell(px, stride, inv, a.w - 1);
     sc = map_at(a.heat, img, tgt, ty, tx);                                                    // decode.py:53
     oy = map_at(a.off, img, tgt, ty, tx);
     ox = map_at(a.off, img, PN_NUM_PARTS + tgt, ty, tx);
     cy = __dadd_rn((double)(ty * os), (double)oy);                                            // decode.py:55-56
     cx = __dadd_rn((double)(tx * os), (double)ox);
+}
+__device__ __forceinline__ void hop(const DecodeArgs &a, int img, const pn_map &disp, int e, int tgt, double &cy, double &cx,
+                                    float &sc, float &oy, float &ox) {
+    float dy, dx;
+    hop_full(a, img, disp, e, tgt, cy, cx, sc, oy, ox, dy, dx);
 }
 
 __device__ __forceinline__ double sqdist(double ay, double ax, double by, double bx) {
@@ -528,6 +535,77 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_THREADS <= 512 ? 2 : 1) decod
 #endif
 }
 
+// ---------------------------------------------------------------------------------- D2 / D3 as stand-alone calls
+// posenet/decode.py:9-63 -- traverse_to_targ_keypoint: one hop, one thread.  out[7] = score, image_coord (y, x),
+// displacement_vector (y, x), offset (y, x); the fp32 values are stored as doubles (exact).
+__global__ void traverse_kernel(DecodeArgs a, pn_map disp, int edge, int target, double sy, double sx, double *__restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float sc, oy, ox, dy, dx;
+    double cy = sy, cx = sx;
+    hop_full(a, 0, disp, edge, target, cy, cx, sc, oy, ox, dy, dx);
+    out[0] = (double)sc; out[1] = cy; out[2] = cx; out[3] = (double)dy; out[4] = (double)dx; out[5] = (double)oy; out[6] = (double)ox;
+}
+
+// posenet/decode.py:131-182 -- decode_pose for ONE root: the thread of part k walks the tree path root -> k exactly like a slot of
+// decode_kernel's speculation phase (climbing hops use displacements_bwd, descending hops displacements_fwd; a hop needs
+// `score[source] > 0.0`).  out = keypoint_scores[17] | keypoint_coords[17][2] | offsets[17][2], float64.
+__global__ void decode_pose_kernel(DecodeArgs a, double root_score, int root, double ry, double rx, double *__restrict__ out) {
+    const int k = threadIdx.x;
+    if (k >= PN_NUM_PARTS) return;
+    int up[PN_NUM_PARTS], up_edge[PN_NUM_PARTS];
+#pragma unroll
+    for (int p = 0; p < PN_NUM_PARTS; ++p) { up[p] = 0; up_edge[p] = -1; }
+#pragma unroll
+    for (int e = 0; e < PN_NUM_EDGES; ++e) { up[c_child[e]] = c_parent[e]; up_edge[c_child[e]] = e; }
+    unsigned anc_k = 1u << k;
+    for (int p = k; p != 0; p = up[p]) anc_k |= 1u << up[p];
+    double ks = 0.0, cy = 0.0, cx = 0.0;
+    float oy = 0.f, ox = 0.f;
+    if (k == root) {                                   // decode.py:142-143: the root keeps the caller's score and coordinates
+        ks = root_score; cy = ry; cx = rx;
+    } else if (root_score > 0.0) {
+        float sc = 1.f;                                // the root passed the `> 0.0` gate; every hop overwrites sc
+        cy = ry; cx = rx;
+        int cur = root;
+        bool reached = true;
+        while (cur != k) {
+            if (!(sc > 0.f)) { reached = false; break; }
+            const bool climb = ((anc_k >> cur) & 1u) == 0;
+            int nxt;
+            if (climb) nxt = up[cur];
+            else { nxt = k; while (up[nxt] != cur) nxt = up[nxt]; }
+            const int e = climb ? up_edge[cur] : up_edge[nxt];
+            hop(a, 0, climb ? a.bwd : a.fwd, e, nxt, cy, cx, sc, oy, ox);
+            cur = nxt;
+        }
+        if (reached) ks = (double)sc;
+        else { cy = cx = 0.0; oy = ox = 0.f; }
+    }
+    out[k] = ks;
+    out[PN_NUM_PARTS + 2 * k] = cy;
+    out[PN_NUM_PARTS + 2 * k + 1] = cx;
+    out[3 * PN_NUM_PARTS + 2 * k] = (double)oy;
+    out[3 * PN_NUM_PARTS + 2 * k + 1] = (double)ox;
+}
+
+// ---------------------------------------------------------------------------------- N4: coordinates back to the source frame
+// image_demo.py:50 -- `keypoint_coords *= output_scale` (float64 multiply by (src_h / target_h, src_w / target_w), utils.py:19)
+// for a whole batch of pose records on the device, so the scaled records leave with the same single D2H copy.
+__global__ void scale_coords_kernel(double *__restrict__ kc, long long pairs, int pairs_per_img, const double *__restrict__ scales,
+                                    double sy, double sx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pairs) return;
+    double fy = sy, fx = sx;
+    if (scales) {
+        const long long img = i / pairs_per_img;
+        fy = scales[2 * img]; fx = scales[2 * img + 1];
+    }
+    double2 v = reinterpret_cast<double2 *>(kc)[i];
+    v.x = __dmul_rn(v.x, fy);
+    v.y = __dmul_rn(v.y, fx);
+    reinterpret_cast<double2 *>(kc)[i] = v;
+}
+
 }  // namespace pn
 
 // ---- C ABI ---------------------------------------------------------------------------------------
@@ -561,12 +639,55 @@ extern "C" int pn_decode_greedy(const pn_map *heat, const pn_map *off, const pn_
     a.h = h; a.w = wd; a.keys = keys; a.capacity = capacity; a.counts = counts; a.prm = *params;
     a.pose_scores = pose_scores; a.kp_scores = kp_scores; a.kp_coords = kp_coords; a.kp_offsets = kp_offsets;
     a.pose_counts = pose_counts;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    const int dev = current_device();
+    if (!once.get(dev)) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeShared)));
-        configured = true;
+        once.set(dev, 1);
     }
     decode_kernel<<<n_img, DEC_THREADS, sizeof(DecodeShared), as_stream(stream)>>>(a);
+    PN_CHECK_LAUNCH();
+    return PN_OK;
+}
+
+extern "C" int pn_traverse_to_targ_keypoint(int edge_id, const double *source_keypoint_host, int target_keypoint_id,
+                                            const pn_map *heat, const pn_map *off, const pn_map *disp, int h, int wd,
+                                            int output_stride, double *out7, pn_stream_t stream) {
+    PN_CHECK_ARG(source_keypoint_host && heat && off && disp && heat->ptr && off->ptr && disp->ptr && out7,
+                 "pn_traverse_to_targ_keypoint: null pointer");
+    PN_CHECK_ARG(edge_id >= 0 && edge_id < PN_NUM_EDGES && target_keypoint_id >= 0 && target_keypoint_id < PN_NUM_PARTS,
+                 "pn_traverse_to_targ_keypoint: edge %d / part %d out of range", edge_id, target_keypoint_id);
+    PN_CHECK_ARG(h > 0 && wd > 0 && output_stride > 0, "pn_traverse_to_targ_keypoint: bad shape");
+    DecodeArgs a = {};
+    a.heat = *heat; a.off = *off; a.h = h; a.w = wd; a.prm.output_stride = output_stride;
+    traverse_kernel<<<1, 32, 0, as_stream(stream)>>>(a, *disp, edge_id, target_keypoint_id, source_keypoint_host[0],
+                                                     source_keypoint_host[1], out7);
+    PN_CHECK_LAUNCH();
+    return PN_OK;
+}
+
+extern "C" int pn_decode_pose(double root_score, int root_id, const double *root_image_coord_host, const pn_map *heat,
+                              const pn_map *off, const pn_map *fwd, const pn_map *bwd, int h, int wd, int output_stride,
+                              double *out85, pn_stream_t stream) {
+    PN_CHECK_ARG(root_image_coord_host && heat && off && fwd && bwd && heat->ptr && off->ptr && fwd->ptr && bwd->ptr && out85,
+                 "pn_decode_pose: null pointer");
+    PN_CHECK_ARG(root_id >= 0 && root_id < PN_NUM_PARTS, "pn_decode_pose: root part %d out of range", root_id);
+    PN_CHECK_ARG(h > 0 && wd > 0 && output_stride > 0, "pn_decode_pose: bad shape");
+    DecodeArgs a = {};
+    a.heat = *heat; a.off = *off; a.fwd = *fwd; a.bwd = *bwd; a.h = h; a.w = wd; a.prm.output_stride = output_stride;
+    decode_pose_kernel<<<1, 32, 0, as_stream(stream)>>>(a, root_score, root_id, root_image_coord_host[0], root_image_coord_host[1],
+                                                        out85);
+    PN_CHECK_LAUNCH();
+    return PN_OK;
+}
+
+extern "C" int pn_scale_keypoint_coords(double *kp_coords, int n_img, int points_per_img, const double *scales, double scale_y,
+                                        double scale_x, pn_stream_t stream) {
+    PN_CHECK_ARG(kp_coords && n_img > 0 && points_per_img > 0, "pn_scale_keypoint_coords: bad argument");
+    PN_CHECK_ARG(((uintptr_t)kp_coords & 15) == 0, "pn_scale_keypoint_coords: kp_coords must be 16-byte aligned");
+    const long long pairs = (long long)n_img * points_per_img;
+    scale_coords_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, as_stream(stream)>>>(kp_coords, pairs, points_per_img, scales, scale_y,
+                                                                                        scale_x);
     PN_CHECK_LAUNCH();
     return PN_OK;
 }

@@ -7,8 +7,9 @@
 //   (3) tcgen05.st of packed bf16 pairs + tcgen05.mma with the A operand in TMEM (the pointwise conv on the depthwise result).
 #include <cuda.h>
 
-#include "common.cuh"
-#include "ptx.cuh"
+#include "../common.cuh"
+#include "../ptx.cuh"
+#include "../../../include/posenet_b200_diag.h"
 
 namespace pn {
 

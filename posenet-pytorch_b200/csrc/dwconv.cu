@@ -324,11 +324,12 @@ int dw_prepare(DwOp *op, const void *x, int n, int h, int wd, int c, int stride,
 
 template <typename T, int S, int D>
 static int launch_tma(const DwOp *op, const DwGeom &g, const float *w, const float *b, void *y, cudaStream_t st) {
-    static bool configured = false;
+    static DeviceOnce once;
+    const int dev = current_device();
     auto kern = dwconv_tma_kernel<T, S, D>;
-    if (!configured) {
+    if (!once.get(dev)) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_PER_CTA));
-        configured = true;
+        once.set(dev, 1);
     }
     const int smem = 256 + g.stages * (int)g.stage_bytes;
     const long long max_ctas = num_sms();

@@ -212,11 +212,12 @@ int dwwarp_prepare(DwWarpOp *op, const void *x, int n, int h, int wd, int c, int
 
 template <int D>
 static int dwwarp_launch_t(const DwWarpOp *op, const DwwGeom &g, const float *w, const float *b, void *y, cudaStream_t st) {
-    static bool configured = false;
+    static DeviceOnce once;
+    const int dev = current_device();
     auto kern = dwwarp_kernel<D>;
-    if (!configured) {
+    if (!once.get(dev)) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dww_smem(D)));
-        configured = true;
+        once.set(dev, 1);
     }
     const long long ctas = ((long long)g.items + dww_warps(D) - 1) / dww_warps(D);
     const int grid = (int)(ctas < num_sms() ? ctas : num_sms());

@@ -119,10 +119,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (EPI == EPI_HEADS && threadIdx.x < 128) {                             // head bias (128 padded entries) -> the staging area
         reinterpret_cast<float *>(smem_gen + STAGES * STAGE_BYTES)[threadIdx.x] = threadIdx.x < (unsigned)N ? __ldg(ep.bias + threadIdx.x) : 0.f;
     }
-    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_launch_dependents();                                  // after the TMEM allocation is made (see stem.cu): a dependent CTA must not allocate first
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_wait();                                                              // (ptx.cuh) the previous layer has completed
 
@@ -336,12 +336,13 @@ int gemm_tc_prepare(GemmTc *g, const void *a, const void *w, void *y, int m, int
 
 template <int BLOCK_N, int EPI>
 static int launch_tc(const GemmTc *g, const EpiParams &ep, cudaStream_t st) {
-    static bool configured = false;
+    static DeviceOnce once;
+    const int dev = current_device();
     auto kern = gemm_tc_kernel<BLOCK_N, EPI>;
     constexpr int smem = tc_smem_bytes(BLOCK_N);
-    if (!configured) {
+    if (!once.get(dev)) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        once.set(dev, 1);
     }
     const int tiles = ceil_div(g->m, TC_BLOCK_M) * (g->n / BLOCK_N);
     const int grid = tiles < num_sms() ? tiles : num_sms();

@@ -25,6 +25,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Bounded wait: a pipeline protocol error traps instead of hanging the GPU.  The suspend-time hint lets the hardware park the
 // warp until the phase completes (or ~1 ms passes), so a waiting warp does not burn issue slots re-polling.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    {   // fast path: a phase that has already completed costs one non-blocking probe (the parking try_wait below takes a few
+        // hundred cycles to return even then -- measured ~300 cycles per wait in the fused blocks' timeline)
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
     const long long t0 = clock64();
     for (;;) {
         uint32_t done;

@@ -42,7 +42,7 @@ constexpr int SEP_THREADS = (SEP_FIRST_DW_WARP + SEP_DW_WARPS) * 32;   // 512
 constexpr int SEP_MAX_A = 6;
 constexpr int SEP_A_BYTES = 128 * 128;                                 // 128 rows x 64 bf16
 constexpr int SEP_STG_BYTES = 128 * 128;                               // one 128 x 64 bf16 output panel
-constexpr int SEP_MAX_P = 6, SEP_MAX_W = 4;
+constexpr int SEP_MAX_P = 6, SEP_MAX_W = 6;
 constexpr int SEP_WGT_BYTES = 9 * 64 * 4 + 64 * 4;                     // dw weights [9][64] + bias [64] fp32
 constexpr int SEP_SMEM_MAX = 232448;
 
@@ -56,6 +56,7 @@ struct SepGeom {
     int kblocks;
     int half, cbox;                       // K <= 32: two pixel columns per warp (16 lanes each), 32-channel patch box
     int cl;                               // CTAs per cluster (1, 2, 4): each owns 256 output channels and 1 / cl of the k-blocks
+    int exp;                              // PN_SEP_EXP build only: experiment flags (1 no dw math, 2 no epilogue work, 4 no MMA, 8 no W loads)
     unsigned epi_sleep_ns;                // sleep between the epilogue's polls of its accumulator barrier (PN_SEP_EPI_SLEEP, default 200)
     int p_stages, w_stages, a_stages, stg_bufs;
     unsigned patch_stage_bytes, patch_box_bytes, wgt_off, w_stage_bytes;
@@ -166,7 +167,8 @@ template <int S, int D, bool HALF, int CL>
 __global__ void __launch_bounds__(SEP_THREADS, 1)
 sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dww,
                const __grid_constant__ CUtensorMap tmap_dwb, const __grid_constant__ CUtensorMap tmap_w,
-               const __grid_constant__ CUtensorMap tmap_y, const float *__restrict__ pw_bias, const SepGeom g) {
+               const __grid_constant__ CUtensorMap tmap_y, const float *__restrict__ pw_bias, __nv_bfloat16 *__restrict__ y,
+               const SepGeom g) {
     constexpr int CB = 64;                                  // channels per k-block (ragged K is zero-filled by TMA)
     // CL > 1: a cluster of CL CTAs shares every 128-pixel tile.  CTA `rank` owns output channels [rank * 256, +256) --
     // its own pointwise weights, accumulators (double-buffered) and epilogue -- and computes the depthwise result of the
@@ -231,11 +233,11 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const int ncp = g.n_tiles * g.panels * 64;                // padded so that ragged panels read zeros
         for (int i = threadIdx.x; i < ncp; i += SEP_THREADS) sbias[i] = col_base + i < g.nc ? __ldg(pw_bias + col_base + i) : 0.f;
     }
-    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     if (CLUSTER) cluster_sync_all();                          // the peers' barriers exist before anything remote targets them
     tc_fence_after();
+    pdl_launch_dependents();                                  // after the TMEM allocation is made (see stem.cu): a dependent CTA must not allocate first
     pdl_wait();                                               // everything above overlapped the previous layer's tail
     const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -306,8 +308,14 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 if (w_tile < g.tiles) {
                     if (w_new) { w_col = col_base + (int)(w_tile % g.n_tiles) * g.n_tile; w_new = false; }
                     if (mbar_test(bar(SepBars::w_empty, ws), wph ^ 1)) {
+#ifdef PN_SEP_EXP
+                        if (g.exp & 8) mbar_arrive(bar(SepBars::w_full, ws)); else {
+#endif
                         mbar_expect_tx(bar(SepBars::w_full, ws), g.w_stage_bytes);
                         tma_load_2d(w_addr(ws), &tmap_w, bar(SepBars::w_full, ws), w_kb * CB, w_col + w_hf * g.n_half);
+#ifdef PN_SEP_EXP
+                        }
+#endif
                         if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
                         if (++w_hf == g.n_halves) {
                             w_hf = 0;
@@ -350,7 +358,11 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         const uint32_t sb = w_addr(ws);
 #pragma unroll
                         for (int k = 0; k < CB / 16; ++k)
-                            if (k < ksteps)
+                            if (k < ksteps
+#ifdef PN_SEP_EXP
+                                && !(g.exp & 4)
+#endif
+                                )
                                 tc_mma_bf16(d_tmem + (uint32_t)(hf * g.n_half), sep_smem_desc(sa + k * 32), sep_smem_desc(sb + k * 32), idesc,
                                             (uint32_t)((kb | k) != 0));
                         tc_commit(bar(SepBars::w_empty, ws));
@@ -385,6 +397,67 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         int acc = 0, buf = 0, tr_e = 0;
         uint32_t acc_phase = 0;
         (void)tr_e;
+        if (g.stg_bufs == 0) {
+            // ---- direct epilogue: TMEM -> registers -> global, no staging panel, no CTA-level barrier.  A thread owns one tile row
+            // (= one output pixel): 32 accumulator columns are 64 contiguous bytes of its NHWC pixel, written as two 32-byte
+            // stores (whole sectors).  The tcgen05.ld of chunk c + 1 is in flight while chunk c is converted and stored.
+            const int r_ty = row_in_tile / g.tw, r_tx = row_in_tile - r_ty * g.tw;
+            const int chunks = (g.n_tile + 31) >> 5;
+            auto emit = [&](const uint32_t (&v)[32], int c, __nv_bfloat16 *yrow, bool row_ok, int col_lim, uint32_t bias_base) {
+                const int col0 = c * 32;                                  // column inside this tile's n_tile block
+#pragma unroll
+                for (int piece = 0; piece < 2; ++piece) {
+                    uint32_t o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const float4 b0 = lds_f4(bias_base + (uint32_t)(col0 + piece * 16 + j * 2) * 4u);
+                        const int i0 = piece * 16 + j * 2;
+                        const float2 s0 = fadd2(make_float2(__uint_as_float(v[i0 + 0]), __uint_as_float(v[i0 + 1])), make_float2(b0.x, b0.y));
+                        const float2 s1 = fadd2(make_float2(__uint_as_float(v[i0 + 2]), __uint_as_float(v[i0 + 3])), make_float2(b0.z, b0.w));
+                        o[j] = relu6_bf16x2(s0);
+                        o[j + 1] = relu6_bf16x2(s1);
+                    }
+                    if (row_ok && col0 + piece * 16 < col_lim)
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + col0 + piece * 16), "r"(o[0]),
+                                     "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                                     : "memory");
+                }
+            };
+            for (long long tile = tile_first; tile < g.tiles; tile += tile_step) {
+                const int n_tile = (int)(tile % g.n_tiles);
+                const int m_tile = (int)(tile / g.n_tiles);
+                const int img = m_tile / m_tiles_per_img;
+                const int rem = m_tile - img * m_tiles_per_img;
+                const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+                const int oy = ty * g.th + r_ty, ox = tx * g.tw + r_tx;
+                const bool row_ok = r_ty < g.th && oy < g.ho && ox < g.wo;
+                const int colg = col_base + n_tile * g.n_tile;            // first global output channel of this accumulator
+                __nv_bfloat16 *yrow = y + (((size_t)img * g.ho + oy) * g.wo + ox) * (size_t)g.nc + colg;
+                const int col_lim = g.nc - colg;                          // columns of this block that exist (ragged N)
+                mbar_wait_backoff(bar(SepBars::tfull, acc), acc_phase, g.epi_sleep_ns);
+                tc_fence_after();
+                if (issuer) SEP_TRACE(2, tr_e, 0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * g.n_tile);
+                const uint32_t bias_base = base + g.off_bias + (uint32_t)(n_tile * g.n_tile) * 4u;   // this block's bias in shared memory
+                uint32_t va[32], vb[32];
+                tc_ld32(taddr, va);
+#pragma unroll 1
+                for (int c = 0; c < chunks; c += 2) {
+                    tc_ld_wait();
+                    if (c + 1 < chunks) tc_ld32(taddr + (uint32_t)((c + 1) * 32), vb);
+                    else { tc_fence_before(); mbar_arrive(bar(SepBars::tempty, acc)); }
+                    emit(va, c, yrow, row_ok, col_lim, bias_base);
+                    if (c + 1 < chunks) {
+                        tc_ld_wait();
+                        if (c + 2 < chunks) tc_ld32(taddr + (uint32_t)((c + 2) * 32), va);
+                        else { tc_fence_before(); mbar_arrive(bar(SepBars::tempty, acc)); }
+                        emit(vb, c + 1, yrow, row_ok, col_lim, bias_base);
+                    }
+                }
+                if (issuer) { SEP_TRACE(2, tr_e, 1); ++tr_e; }
+                if (++acc == g.acc_bufs) { acc = 0; acc_phase ^= 1; }
+            }
+        } else
         for (long long tile = tile_first; tile < g.tiles; tile += tile_step) {
             const int n_tile = (int)(tile % g.n_tiles);
             const int m_tile = (int)(tile / g.n_tiles);
@@ -395,6 +468,14 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             tc_fence_after();
             if (issuer) SEP_TRACE(2, tr_e, 0);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * g.n_tile);
+#ifdef PN_SEP_EXP
+            if (g.exp & 2) {
+                tc_fence_before();
+                mbar_arrive(bar(SepBars::tempty, acc));
+                if (++acc == g.acc_bufs) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
+#endif
 #pragma unroll 1
             for (int p = 0; p < g.panels; ++p) {
                 const int col0 = n_tile * g.n_tile + p * 64;
@@ -498,7 +579,11 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 const int s_col = (int)(tab & 0xffu), s_r0 = (int)((tab >> 8) & 0xffu), s_n = (int)(tab >> 16);
                 const int orow0 = sub * g.ths + s_r0;
                 const int nrows = min(s_n, (g.th - orow0 + RSTEP - 1) / RSTEP);     // rows of this segment inside the tile
-                if (nrows > 0) {
+                if (nrows > 0
+#ifdef PN_SEP_EXP
+                    && !(g.exp & 1)
+#endif
+                    ) {
                     const uint32_t src = stage + (uint32_t)(s_r0 * S) * rowb1 + (uint32_t)(s_col * S) * PIX + lane_off;
                     const int ncol_ok = g.tw - s_col;                               // strip pixels px < ncol_ok exist
                     int arow = orow0 * g.tw + s_col;                                // A-tile row == TMEM lane == staging row
@@ -536,11 +621,13 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                         const int slot = (PRE + j * S + n) % NR;
                                         if (UNPACKED) ringf[slot][c] = unpack(nxt[n][c]); else ringp[slot][c] = nxt[n][c];
                                     }
-                                // ... and the next step's rows are requested before this step's math
-                                if (t + 1 < nrows) {
+                                // ... and the next step's rows are requested before this step's math.  After the last row the
+                                // request repeats the last one (a predicated load would cost a register copy per element)
+                                {
+                                    const int tn = t + 1 < nrows ? t + 1 : t;
     #pragma unroll
                                     for (int n = 0; n < NNEW; ++n) {
-                                        const uint32_t rp = src + (uint32_t)(PRE + (t + 1) * S + n) * rowb;
+                                        const uint32_t rp = src + (uint32_t)(PRE + tn * S + n) * rowb;
     #pragma unroll
                                         for (int c = 0; c < NCOLS; ++c) nxt[n][c] = lds_u32(rp + (uint32_t)c * PIX);
                                     }
@@ -675,17 +762,23 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
         g.n_tile = 256;
     }
     g.n_halves = g.n_tile > 256 ? 2 : 1;
+    // W ring granularity: UMMA column blocks of n_tile / n_halves columns.  PN_SEP_NBLK=128 splits wide tiles into 128-column
+    // blocks (16 KB W stages instead of 24-32 KB: a finer ring leaves shared memory for deeper patch / A rings)
+    if (const char *e = getenv("PN_SEP_NBLK")) {
+        const int want = atoi(e);
+        if (want >= 64 && want % 16 == 0 && g.n_tile > want && g.n_tile % want == 0 && g.n_tile / want <= 4) g.n_halves = g.n_tile / want;
+    }
     g.n_half = g.n_tile / g.n_halves;
     PN_CHECK_ARG(g.n_tile * g.n_tiles * g.cl == nc && g.n_half * g.n_halves == g.n_tile && g.n_half % 16 == 0,
                  "pn_sepconv_block: cout %d does not split into tiles", nc);
     g.panels = ceil_div(g.n_tile, 64);
-    g.acc_bufs = g.n_halves == 2 ? 1 : 2;
-    g.tmem_cols = g.n_halves == 2 ? 512 : next_pow2_cols(g.n_tile + g.panels * 64);
+    g.acc_bufs = g.n_tile > 256 ? 1 : 2;
+    g.tmem_cols = g.n_tile > 256 ? 512 : next_pow2_cols(g.n_tile + g.panels * 64);
     PN_CHECK_ARG(g.tmem_cols <= 512 && g.panels * 64 <= 512, "pn_sepconv_block: TMEM budget exceeded");
     g.w_stage_bytes = (unsigned)g.n_half * 128u;
 
     // ---- tile search: fewest (tiles x per-tile cost); one strip per depthwise thread group per sub-tile
-    const int min_w = g.n_halves == 2 ? 3 : 2;                     // W ring entries (one per UMMA column block)
+    const int min_w = g.n_halves >= 2 ? 3 : 2;                     // default W ring entries (column blocks of a k-block, plus one ahead)
     const int min_a = g.cl > 2 ? g.cl : 2;                         // cluster: the A ring is a multiple of the cluster size
     const int fixed = min_a * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 640 + 4224;   // minimum non-patch smem
     double best = 1e300;
@@ -774,9 +867,12 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
                    (long long)pst * g.patch_stage_bytes <= avail;
     };
     int bestp = -1;
-    for (int stg = 2; stg >= 1; --stg)
+    // PN_SEP_DIRECT=1: the epilogue stores straight from registers (no staging panel, stg = 0); the 16-32 KB go to the rings
+    const bool direct = getenv("PN_SEP_DIRECT") != nullptr && atoi(getenv("PN_SEP_DIRECT")) != 0;
+    const int max_a1 = direct ? 5 : 3;
+    for (int stg = direct ? 0 : 2; stg >= (direct ? 0 : 1); --stg)
         for (int ast = SEP_MAX_A; ast >= 2; --ast) {
-            if (g.cl == 1 && ast > 3) continue;
+            if (g.cl == 1 && ast > max_a1) continue;
             if (g.cl > 1 && ast % g.cl != 0) continue;
             for (int wst = SEP_MAX_W; wst >= min_w; --wst)
                 for (int pst = SEP_MAX_P; pst >= 2 && pst >= g.subs + 1; --pst) {
@@ -796,14 +892,17 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     // 512-column tiles have a single accumulator: the epilogue cannot overlap the next tile's MMAs, so what pays is a
     // short epilogue (two staging panels keep the TMA stores in flight) and a third A stage for the depthwise warps to
     // run ahead into -- worth more than a third patch stage (measured: 84 -> 77 us on the 512 -> 512 blocks)
-    if (g.n_halves == 2 && g.subs == 1 && fits(2, min_w, 3, 2)) { g.p_stages = 2; g.w_stages = min_w; g.a_stages = 3; g.stg_bufs = 2; }
+    if (!direct && g.n_halves == 2 && g.subs == 1 && fits(2, min_w, 3, 2)) { g.p_stages = 2; g.w_stages = min_w; g.a_stages = 3; g.stg_bufs = 2; }
     if (const char *force = getenv("PN_SEP_STAGES")) {              // tuning aid: "p,w,a,stg"
         int fp = 0, fw = 0, fa = 0, fs = 0;
-        if (sscanf(force, "%d,%d,%d,%d", &fp, &fw, &fa, &fs) == 4 && fp >= g.subs + 1 && fp <= SEP_MAX_P && fw >= min_w &&
-            fw <= SEP_MAX_W && fa >= 2 && fa <= SEP_MAX_A && fa % g.cl == 0 && fs >= 1 && fs <= 2 && fits(fp, fw, fa, fs)) {
+        if (sscanf(force, "%d,%d,%d,%d", &fp, &fw, &fa, &fs) == 4 && fp >= g.subs + 1 && fp <= SEP_MAX_P && fw >= 2 &&
+            fw <= SEP_MAX_W && fa >= 2 && fa <= SEP_MAX_A && fa % g.cl == 0 && fs >= 0 && fs <= 2 && fits(fp, fw, fa, fs)) {
             g.p_stages = fp; g.w_stages = fw; g.a_stages = fa; g.stg_bufs = fs;
         }
     }
+#ifdef PN_SEP_EXP
+    if (const char *e = getenv("PN_SEP_EXP")) g.exp = atoi(e);
+#endif
     g.epi_sleep_ns = 200;
     if (const char *e = getenv("PN_SEP_EPI_SLEEP")) g.epi_sleep_ns = (unsigned)atoi(e);
     static_assert(SepBars::total <= 640, "barrier block exceeds its reserve");
@@ -838,6 +937,7 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
         op->dw_w = dw_w; op->dw_b = dw_b; op->pw_w = pw_w; op->y = y;
         return septc_prepare(&op->tc, x, pw_w, n, h, wd, k, nc, dil);
     }
+    op->y = y;                                                       // the direct-store epilogue writes through the plain pointer
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
     {   // input patches: (C, W, H, N) bf16, box [cb, twi, thi, 1], no swizzle, OOB -> 0
@@ -872,8 +972,8 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
 
 template <int S, int D, bool HALF, int CL>
 static int sep_launch_t(const SepOp *op, const SepGeom &g, const float *pw_bias, cudaStream_t st) {
-    static bool configured = false;
-    static int max_clusters = 0;
+    static DeviceOnce once, clusters;                             // per device: attribute set / clusters that fit at once
+    const int dev = current_device();
     auto kern = sepconv_kernel<S, D, HALF, CL>;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -890,24 +990,26 @@ static int sep_launch_t(const SepOp *op, const SepGeom &g, const float *pw_bias,
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = (CL > 1 || pdl_enabled()) ? 1 : 0;
-    if (!configured) {
+    if (!once.get(dev)) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SEP_SMEM_MAX));
         if (CL > 1) {                                             // how many clusters fit at once (GPC boundaries cost a few SMs)
+            int max_clusters = 0;
             cfg.gridDim = dim3((unsigned)(num_sms() / CL * CL), 1, 1);
             cfg.dynamicSmemBytes = SEP_SMEM_MAX;
             PN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
             PN_CHECK_ARG(max_clusters > 0, "pn_sepconv_block: no %d-CTA cluster fits on this device", CL);
             cfg.dynamicSmemBytes = (size_t)op->smem_bytes;
+            clusters.set(dev, max_clusters);
         }
-        configured = true;
+        once.set(dev, 1);
     }
-    const long long units = CL > 1 ? max_clusters : num_sms();     // persistent: one CTA (cluster) per SM (SM group)
+    const long long units = CL > 1 ? clusters.get(dev) : num_sms();     // persistent: one CTA (cluster) per SM (SM group)
     const int grid = (int)(g.tiles < units ? g.tiles : units) * CL;
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
     PN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *reinterpret_cast<const CUtensorMap *>(op->tmap_x),
                                      *reinterpret_cast<const CUtensorMap *>(op->tmap_dww), *reinterpret_cast<const CUtensorMap *>(op->tmap_dwb),
                                      *reinterpret_cast<const CUtensorMap *>(op->tmap_w), *reinterpret_cast<const CUtensorMap *>(op->tmap_y),
-                                     pw_bias, g));
+                                     pw_bias, reinterpret_cast<__nv_bfloat16 *>(op->y), g));
     return PN_OK;
 }
 

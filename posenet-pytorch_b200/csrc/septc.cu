@@ -110,14 +110,18 @@ __device__ __forceinline__ void tcs_stg_v4(void *p, const uint4 &v) {
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// Timeline trace (diagnostics; tools/trace_septc.py): CTA 0 stamps clock64 at the hand-offs of its first `cap` steps into
-// [role][step][4] when a buffer has been registered with pn_debug_tcs_trace; a null check per event otherwise.
+// Timeline trace (diagnostics build only: -DPN_TCS_TRACE, tools/trace_septc.py): CTA 0 stamps clock64 at the hand-offs of its
+// first `cap` steps into [role][step][4] once a buffer has been registered with pn_debug_tcs_trace.
+#ifdef PN_TCS_TRACE
 __device__ long long *g_tcs_trace = nullptr;
 __device__ int g_tcs_trace_cap = 0;
 #define TCS_TR(role, step, ev)                                                                         \
     do {                                                                                                \
         if (tr && (step) < tr_cap) tr[(((long long)(role)) * tr_cap + (step)) * 4 + (ev)] = clock64();  \
     } while (0)
+#else
+#define TCS_TR(role, step, ev) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(TCS_THREADS, 1)
 septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const float *__restrict__ dw_w,
@@ -176,14 +180,16 @@ septc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         for (int i = threadIdx.x; i < g.nc; i += TCS_THREADS) spwb[i] = __ldg(pw_b + i);
     }
     fence_async_smem();
-    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_launch_dependents();                                  // after the TMEM allocation is made (see stem.cu): a dependent CTA must not allocate first
     pdl_wait();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(gen + g.off_bar + TcsBars::tmem_slot);
+#ifdef PN_TCS_TRACE
     long long *tr = blockIdx.x == 0 ? g_tcs_trace : nullptr;
     const int tr_cap = g_tcs_trace_cap;
+#endif
     // A operand of depthwise step (unit i, k-block kb): buffer index and how many times that buffer was used before
     auto a_slot = [&](int i, int kb, int &ai, uint32_t &use) {
         if (g.ring) {
@@ -577,12 +583,13 @@ int septc_prepare(SepTcOp *op, const void *x, const void *pw_w, int n, int h, in
 }
 
 int septc_launch(const SepTcOp *op, const float *dw_w, const float *dw_b, const float *pw_b, void *y, cudaStream_t st) {
-    static bool configured = false;
+    static DeviceOnce once;
+    const int dev = current_device();
     TcsGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    if (!configured) {
+    if (!once.get(dev)) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(septc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCS_SMEM_MAX));
-        configured = true;
+        once.set(dev, 1);
     }
     const long long sms = num_sms();
     const int grid = (int)(g.units < sms ? g.units : sms);
@@ -601,9 +608,11 @@ void septc_describe(const SepTcOp *op, char *out, size_t cap) {
 
 }  // namespace pn
 
-// diagnostics: trace buffer = 6 roles x cap steps x 4 stamps (int64), zero-filled by the caller; (nullptr, 0) turns it off
+#ifdef PN_TCS_TRACE
+// diagnostics build: trace buffer = 6 roles x cap steps x 4 stamps (int64), zero-filled by the caller; (nullptr, 0) turns it off
 extern "C" int pn_debug_tcs_trace(long long *buf, int cap) {
     if (cudaMemcpyToSymbol(pn::g_tcs_trace, &buf, sizeof(buf)) != cudaSuccess) return -2;
     if (cudaMemcpyToSymbol(pn::g_tcs_trace_cap, &cap, sizeof(cap)) != cudaSuccess) return -2;
     return 0;
 }
+#endif

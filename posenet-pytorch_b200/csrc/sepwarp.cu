@@ -303,16 +303,17 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
     memcpy(&g, op->geom, sizeof(g));
     const long long ctas = ((long long)g.items + SWP_WARPS - 1) / SWP_WARPS;
     const int grid = (int)(ctas < num_sms() ? ctas : num_sms());
-    auto launch = [&](auto kern, bool &configured) -> int {
-        if (!configured) {
+    const int dev = current_device();
+    auto launch = [&](auto kern, DeviceOnce &once) -> int {
+        if (!once.get(dev)) {
             PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SWP_SMEM));
-            configured = true;
+            once.set(dev, 1);
         }
         PN_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(SWP_THREADS), SWP_SMEM, st, *reinterpret_cast<const CUtensorMap *>(op->tmap_x), dw_w, dw_b,
                                  (const __nv_bfloat16 *)pw_w, pw_b, (__nv_bfloat16 *)y, g));
         return PN_OK;
     };
-    static bool c28 = false, c26 = false, c14 = false, c00 = false;
+    static DeviceOnce c28, c26, c14, c00;
     if (g.ks == 2 && g.nt == 8) return launch(sepwarp_kernel<2, 8>, c28);      // 32 -> 64 (model 100 / 101)
     if (g.ks == 2 && g.nt == 6) return launch(sepwarp_kernel<2, 6>, c26);      // 24 -> 48 (model 75)
     if (g.ks == 1 && g.nt == 4) return launch(sepwarp_kernel<1, 4>, c14);      // 16 -> 32 (model 50)

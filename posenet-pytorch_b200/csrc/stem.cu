@@ -101,7 +101,7 @@ struct StemTcArgs {
     const float *w27, *bias;
     __nv_bfloat16 *y;
     int n, h, w, ho, wo, stride, cout;
-    long long total_px, total_bytes16;     // pixels; image bytes rounded up to 16
+    long long total_px, total_bytes, total_lo16;   // pixels; bytes of the image batch; the same rounded DOWN to 16
     int span_cap;                          // bytes per span buffer (multiple of 16)
 };
 
@@ -134,8 +134,22 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         const long long lo = ((long long)i0 * a.h + iy0) * row_bytes, hi = ((long long)i1 * a.h + iy1 + 1) * row_bytes;
         lo16 = lo & ~15ll;
         long long end = (hi + 15) & ~15ll;
-        if (end > a.total_bytes16) end = a.total_bytes16;
+        if (end > a.total_lo16) end = a.total_lo16;      // the bulk copy never reads past the caller's buffer ...
         size = (uint32_t)(end - lo16);
+    };
+    // ... the <= 15 bytes between total_lo16 and the real end are fetched with ordinary byte loads by the issuing thread,
+    // BEFORE its arrive.expect_tx (release) on the slot's barrier, so the consumers' wait (acquire) also covers them.
+    // Only the batch's last tile can have such a tail.
+    auto issue_span = [&](int slot, long long t) {
+        long long lo16; uint32_t size;
+        span_of(t, lo16, size);
+        span_lo[slot] = lo16;
+        const uint32_t dst = sSpan + (uint32_t)slot * (uint32_t)a.span_cap;
+        if (lo16 + size == a.total_lo16)
+            for (long long b = a.total_lo16; b < a.total_bytes; ++b)
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst + (uint32_t)(b - lo16)), "r"((uint32_t)a.img[b]) : "memory");
+        mbar_expect_tx(bars + 8u * slot, size);
+        if (size) bulk_load_1d(dst, a.img + lo16, size, bars + 8u * slot);
     };
 
     if (tid == 0) {
@@ -167,11 +181,13 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
             for (int k = 0; k < 27; ++k) sum += a.w27[k * a.cout + tid];
         sBias[tid] = tid < a.cout ? a.bias[tid] + sum * (float)(1.0 / 255.0) : 0.f;
     }
-    pdl_launch_dependents();
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // only now may the next kernel's CTAs start their prologue on this SM: the TMEM allocation above has been made (a dependent
+    // that allocated first could leave this CTA blocked in tcgen05.alloc while it waits in griddepcontrol.wait for this grid)
+    pdl_launch_dependents();
     const uint32_t tmem = *tmem_slot;
     pdl_wait();                                                   // (ptx.cuh) whatever produced the image / used the output buffer is done
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -181,11 +197,7 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         for (int i = 0; i < STC_NBUF - 1; ++i) {
             const long long t = tile + (long long)i * gridDim.x;
             if (t >= num_tiles) break;
-            long long lo16; uint32_t size;
-            span_of(t, lo16, size);
-            span_lo[i] = lo16;
-            mbar_expect_tx(bars + 8u * i, size);
-            bulk_load_1d(sSpan + (uint32_t)i * (uint32_t)a.span_cap, a.img + lo16, size, bars + 8u * i);
+            issue_span(i, t);
         }
     }
     uint32_t span_phase = 0, mma_phase = 0;             // bit b of span_phase = parity of ring slot b
@@ -265,11 +277,7 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
             const long long next = tile + (long long)(STC_NBUF - 1) * gridDim.x;
             if (next < num_tiles) {                              // refill the slot the previous tile has just released
                 const int nb = (buf + STC_NBUF - 1) % STC_NBUF;
-                long long nlo; uint32_t nsize;
-                span_of(next, nlo, nsize);
-                span_lo[nb] = nlo;
-                mbar_expect_tx(bars + 8u * nb, nsize);
-                bulk_load_1d(sSpan + (uint32_t)nb * (uint32_t)a.span_cap, a.img + nlo, nsize, bars + 8u * nb);
+                issue_span(nb, next);
             }
             tc_fence_after();
             tc_mma_bf16(tmem, stc_smem_desc(sA), stc_smem_desc(sW), IDESC, 0u);
@@ -330,7 +338,8 @@ static int launch_stem_tc(const uint8_t *img, const float *w, const float *b, vo
     a.n = n; a.h = h; a.w = wd; a.ho = ho; a.wo = wo; a.stride = stride; a.cout = cout;
     a.total_px = (long long)n * ho * wo;
     if (a.total_px >= (1ll << 31) - 256) return 1;                // 32-bit pixel indexing inside the kernel
-    a.total_bytes16 = ((long long)n * h * wd * 3 + 15) & ~15ll;
+    a.total_bytes = (long long)n * h * wd * 3;
+    a.total_lo16 = a.total_bytes & ~15ll;
     // input rows a 128-pixel tile can touch: it covers at most 128/wo + 2 output rows (across an image boundary too), i.e.
     // (rows_out - 1) * stride + 3 contiguous input rows (tight: checked by brute force over every tile of 28 geometries)
     const long long rows_out = 128 / wo + 2;
@@ -339,10 +348,11 @@ static int launch_stem_tc(const uint8_t *img, const float *w, const float *b, vo
     const long long smem = STC_A_BYTES + STC_W_BYTES + STC_NBUF * span + 128 + 128 + 1024;
     if (smem > 200 * 1024) return 1;                              // does not fit: caller falls back to the SIMT kernel
     a.span_cap = (int)span;
-    static int configured = 0;
-    if (configured < smem) {
+    static DeviceOnce once;                                       // largest dynamic shared memory size configured, per device
+    const int dev = current_device();
+    if (once.get(dev) < (int)smem) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = (int)smem;
+        once.set(dev, (int)smem);
     }
     const long long tiles = (a.total_px + 127) / 128;
     int per_sm = (int)((220 * 1024) / smem);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("POSENET_B200_LIB", os.path.join(_PKG_ROOT, "lib", "li
 PN_OK = 0
 PN_F32, PN_BF16 = 0, 1
 NUM_PARTS, NUM_EDGES, HEAD_CHANNELS, HEAD_ROWS = 17, 16, 115, 128
-ABI_VERSION = 4
+ABI_VERSION = 5
 PLAN_UNFUSED = 1
 
 
@@ -60,10 +60,6 @@ _SIGNATURES = {
     "pn_sepconv_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pn_sepconv_describe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]),
-    "pn_dwtc_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "pn_debug_tcs_trace": (C.c_int, [C.c_void_p, C.c_int]),
-    "pn_debug_umma_cost": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "pn_heads_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "pn_candidates": (C.c_int, [C.POINTER(Map), C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p,
@@ -71,6 +67,11 @@ _SIGNATURES = {
     "pn_decode_greedy": (C.c_int, [C.POINTER(Map), C.POINTER(Map), C.POINTER(Map), C.POINTER(Map), C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(DecodeParams), C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pn_traverse_to_targ_keypoint": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(Map), C.POINTER(Map),
+                                               C.POINTER(Map), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "pn_decode_pose": (C.c_int, [C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(Map), C.POINTER(Map), C.POINTER(Map),
+                                 C.POINTER(Map), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "pn_scale_keypoint_coords": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
     "pn_plan_query": (C.c_int, [C.POINTER(NetDesc), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pn_plan_create": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "pn_plan_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

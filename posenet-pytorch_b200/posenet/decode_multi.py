@@ -49,8 +49,15 @@ def decode_multiple_poses_batch(scores, offsets, displacements_fwd, displacement
     are views of one packed buffer (``out``: optional preallocated float64 [N*P*86], fully overwritten).
     """
     nat.require_device()
-    lib = nat.load()
     dev = scores.device if torch.is_tensor(scores) and scores.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(dev):                               # buffers, launches and the stream belong to the tensors' GPU
+        return _decode_batch_on(dev, scores, offsets, displacements_fwd, displacements_bwd, output_stride, max_pose_detections,
+                                score_threshold, nms_radius, min_pose_score, workspace, out)
+
+
+def _decode_batch_on(dev, scores, offsets, displacements_fwd, displacements_bwd, output_stride, max_pose_detections,
+                     score_threshold, nms_radius, min_pose_score, workspace, out):
+    lib = nat.load()
     heat = _as_maps(scores, 17, dev)
     off = _as_maps(offsets, 34, dev)
     fwd = _as_maps(displacements_fwd, 32, dev)

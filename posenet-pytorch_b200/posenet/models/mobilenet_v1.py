@@ -250,12 +250,15 @@ class MobileNetV1(nn.Module):
         if not x.is_cuda or self._device().type != "cuda":
             raise nat.NativeError("MobileNetV1 runs on a CUDA device only: move the model and the input with "
                                   ".cuda() (there is no CPU fallback)")
-        plan = self._plan(n, h, w, input_u8)
-        if out is None:
-            oh, ow = plan.out_h, plan.out_w
-            out = tuple(torch.empty((n, ch, oh, ow), dtype=torch.float32, device=x.device)
-                        for ch in _HEAD_CHANNELS.values())
-        plan.run(x, out)
+        if x.device != self._device():
+            raise nat.NativeError("input on %s, model on %s" % (x.device, self._device()))
+        with torch.cuda.device(x.device):                        # plans, launches and the stream are those of the model's GPU
+            plan = self._plan(n, h, w, input_u8)
+            if out is None:
+                oh, ow = plan.out_h, plan.out_w
+                out = tuple(torch.empty((n, ch, oh, ow), dtype=torch.float32, device=x.device)
+                            for ch in _HEAD_CHANNELS.values())
+            plan.run(x, out)
         return out
 
     def forward(self, x, out=None):

@@ -36,10 +36,11 @@ def process_input_gpu(source_img, scale_factor=1.0, output_stride=16, out=None):
     scale = np.array([h / th, w / tw])
     dev = img.device if img.is_cuda else torch.device("cuda", torch.cuda.current_device())
     img = img.to(dev).contiguous()
-    if out is None:
-        out = torch.empty((n, 3, th, tw), dtype=torch.float32, device=dev)
-    nat.check(nat.load().pn_preprocess_u8(C.c_void_p(img.data_ptr()), n, h, w, th, tw, C.c_void_p(out.data_ptr()),
-                                          nat.stream_ptr()), "pn_preprocess_u8")
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((n, 3, th, tw), dtype=torch.float32, device=dev)
+        nat.check(nat.load().pn_preprocess_u8(C.c_void_p(img.data_ptr()), n, h, w, th, tw, C.c_void_p(out.data_ptr()),
+                                              nat.stream_ptr()), "pn_preprocess_u8")
     return out, scale
 
 
@@ -57,11 +58,12 @@ def resize_u8_gpu(source_img, scale_factor=1.0, output_stride=16, out=None):
     scale = np.array([h / th, w / tw])
     dev = img.device if img.is_cuda else torch.device("cuda", torch.cuda.current_device())
     img = img.to(dev).contiguous()
-    if out is None:
-        out = torch.empty((n, th, tw, 3), dtype=torch.uint8, device=dev)
-    assert tuple(out.shape) == (n, th, tw, 3) and out.dtype == torch.uint8 and out.is_contiguous()
-    nat.check(nat.load().pn_resize_u8(C.c_void_p(img.data_ptr()), n, h, w, th, tw, C.c_void_p(out.data_ptr()), nat.stream_ptr()),
-              "pn_resize_u8")
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((n, th, tw, 3), dtype=torch.uint8, device=dev)
+        assert tuple(out.shape) == (n, th, tw, 3) and out.dtype == torch.uint8 and out.is_contiguous()
+        nat.check(nat.load().pn_resize_u8(C.c_void_p(img.data_ptr()), n, h, w, th, tw, C.c_void_p(out.data_ptr()), nat.stream_ptr()),
+                  "pn_resize_u8")
     return out, scale
 
 

@@ -7,6 +7,30 @@ import torch
 from posenet import _native as nat
 
 P = lambda t: C.c_void_p(t.data_ptr())
+
+_diag = None
+
+
+def load_diag():
+    """libposenet_b200_diag.so (include/posenet_b200_diag.h): hardware probes, not part of the product library."""
+    global _diag
+    if _diag is None:
+        import os
+        lib = C.CDLL(os.path.join(os.path.dirname(nat.LIB_PATH), "libposenet_b200_diag.so"))
+        lib.pn_diag_last_error_string.restype = C.c_char_p
+        lib.pn_dwtc_probe.restype = C.c_int
+        lib.pn_dwtc_probe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.pn_debug_umma_cost.restype = C.c_int
+        lib.pn_debug_umma_cost.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+        _diag = lib
+    return _diag
+
+
+def check_diag(rc, what):
+    if rc != 0:
+        raise nat.NativeError("%s failed (%d): %s" % (what, rc, (load_diag().pn_diag_last_error_string() or b"?").decode()))
+
 TORCH_DT = {nat.PN_F32: torch.float32, nat.PN_BF16: torch.bfloat16}
 
 

@@ -30,7 +30,8 @@ import posenet.decode_multi as ref_dm      # noqa: E402
 from oracle import net as onet             # noqa: E402
 from oracle import synth                   # noqa: E402
 sys.path.insert(0, HERE)
-from make_golden_cases import DEC_CASES, NET_CASES, PRE_CASES, heads_for as _heads  # noqa: E402
+from make_golden_cases import DEC_CASES, NET_CASES, POSE_CASES, PRE_CASES, heads_for as _heads  # noqa: E402
+import posenet.decode as ref_dec           # noqa: E402
 
 assert os.path.realpath(ref.__file__).startswith(os.path.realpath(REF)), ref.__file__
 
@@ -118,6 +119,51 @@ def make_decode():
     np.savez_compressed(os.path.join(HERE, "decode.npz"), **out)
 
 
+# ----------------------------------------------------------------------------- decode_pose / traverse on their own
+def pose_roots(heat, off, stride, thr, n_roots):
+    """Roots for the stand-alone decode_pose fixtures: the n best candidates in the oracle's order (score desc, flat index
+    asc -- no reference sort involved), then one root with score 0.0 and one with a negative score."""
+    from oracle import decode as odec
+    cs, ci = odec.part_candidates(heat, thr)
+    h, w = heat.shape[1:]
+    offs = off.reshape(2, -1, h, w).transpose(1, 2, 3, 0)
+    roots = []
+    for s_, (k, y, x) in list(zip(cs, ci))[:n_roots]:
+        roots.append((np.float32(s_), int(k), np.array([y, x]) * stride + offs[k, y, x]))
+    if roots:
+        roots.append((np.float32(0.0), roots[0][1], roots[0][2]))
+        roots.append((np.float32(-0.25), roots[-1][1], roots[-1][2]))
+    return roots
+
+
+def make_decode_pose():
+    out = {"n": np.array(len(POSE_CASES))}
+    for ci_, (di, n_roots) in enumerate(POSE_CASES):
+        kind, h, w, stride, people, seed, P, thr, rad, minp, patch, extra = DEC_CASES[di]
+        heat, off, fwd, bwd = _heads(kind, h, w, stride, people, seed, extra)
+        split = lambda a: a.reshape(2, -1, h, w).transpose((1, 2, 3, 0))            # decode_multi.py:89-97
+        offs, fwd_t, bwd_t = split(off), split(fwd), split(bwd)
+        roots = pose_roots(heat, off, stride, thr, n_roots)
+        ks, kc, ko, tr = [], [], [], []
+        for rs, rid, rxy in roots:
+            a, b, c = ref_dec.decode_pose(rs, rid, rxy, heat, offs, stride, fwd_t, bwd_t)
+            ks.append(a); kc.append(b); ko.append(c)
+            # one hop along every edge in both directions from this root's coordinates (decode.py:9-63)
+            for e, (parent, child) in enumerate(ref.PARENT_CHILD_TUPLES):
+                for tgt, disp in ((child, fwd_t), (parent, bwd_t)):
+                    sc, xy, dv, ov = ref_dec.traverse_to_targ_keypoint(e, rxy, tgt, heat, offs, stride, disp)
+                    assert sc.dtype == np.float32 and xy.dtype == np.float64 and dv.dtype == np.float32 and ov.dtype == np.float32
+                    tr.append(np.concatenate([[sc], xy, dv, ov]).astype(np.float64))
+        out["in_sha_%d" % ci_] = np.array(sha(np.concatenate([heat.ravel(), off.ravel(), fwd.ravel(), bwd.ravel()])))
+        out["roots_%d" % ci_] = np.array([[r[0], r[1], r[2][0], r[2][1]] for r in roots], dtype=np.float64).reshape(-1, 4)
+        out["ks_%d" % ci_] = np.array(ks).reshape(-1, 17)
+        out["kc_%d" % ci_] = np.array(kc).reshape(-1, 17, 2)
+        out["ko_%d" % ci_] = np.array(ko).reshape(-1, 17, 2)
+        out["tr_%d" % ci_] = np.array(tr).reshape(-1, 7)
+        print("decode_pose case %d (decode case %d): %d roots, %d hops" % (ci_, di, len(roots), len(tr)))
+    np.savez_compressed(os.path.join(HERE, "decode_pose.npz"), **out)
+
+
 def make_converter_names():
     """The reference's TF.js -> torch variable-name mapping (converter/tfjs2pytorch.py:15-43) on every variable name of a
     PoseNet MobileNetV1 manifest (14 conv layers, 4 heads, plus names the converter must skip) -> converter_names.json.
@@ -169,4 +215,5 @@ if __name__ == "__main__":
     make_preprocess()
     make_net()
     make_decode()
+    make_decode_pose()
     make_converter_names()

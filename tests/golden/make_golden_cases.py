@@ -36,7 +36,15 @@ DEC_CASES = [  # (kind, h, w, stride, people|0, seed, P, thr, radius, min_pose, 
     ("random", 9, 9, 32, 0, 11, 30, 0.0, 5, 0.0, True, {"tie_levels": 4, "zero_frac": 0.2}),
     ("random", 1, 1, 16, 0, 12, 10, 0.0, 20, 0.0, False, {}),
     ("random", 5, 3, 16, 0, 13, 10, 1.5, 20, 0.5, False, {}),          # empty: threshold above all scores
+    # more accepted poses than the decoder caches in shared memory (DEC_ACC = 64 in csrc/decode.cu): 100 of 120 people
+    # (the cap is reached), and 90 people with the cap out of reach
+    ("people", 91, 161, 8, 120, 20, 100, 0.5, 20, 0.25, False, {}),
+    ("people", 91, 161, 8, 90, 21, 100, 0.5, 20, 0.25, False, {}),
 ]
+
+# decode_pose / traverse_to_targ_keypoint called on their own (posenet/decode.py:9-63,131-182): (index into DEC_CASES,
+# number of best candidates used as roots).  make_golden.py adds, per case, roots with a zero and a negative score.
+POSE_CASES = [(0, 6), (3, 8), (8, 8), (9, 12), (11, 6)]
 
 
 def heads_for(kind, h, w, stride, people, seed, extra):

@@ -107,11 +107,16 @@ def test_pipeline_decode_on_model_outputs_is_exact():
                                      min_pose_score=0.25)
     for a, b in zip(res, ref):
         assert np.array_equal(a, b)
-    # and against the oracle end to end: same pose count, coordinates within 1e-3 px (fp32 mode)
+    # north_star's "keypoint coordinates within 1e-3 px" is a same-head-tensor statement: above it holds with 0 px to spare.
+    # End to end (oracle heads vs GPU fp32 heads) the two decoders see DIFFERENT head tensors (1e-3 relative tolerance), so a
+    # coordinate may differ by that much of an offset / displacement -- and by a whole cell if a rounding flips.  This seed
+    # has no flip: same pose count, same root cells (same part, same stride cell), coordinates within 0.05 px.
     oh = onet.forward(sd, 101, 16, x)
     ref2 = odec.decode_multiple_poses(*[t.squeeze(0).numpy() for t in oh], 16, max_pose_detections=10, min_pose_score=0.25)
-    if int((ref2[0] != 0).sum()) == int((res[0] != 0).sum()):
-        assert np.abs(res[2] - ref2[2]).max() < 1e-3 or True   # informative only: cell flips are legitimate
+    n_got, n_ref = int((res[0] != 0).sum()), int((ref2[0] != 0).sum())
+    assert n_got == n_ref and n_got > 0
+    assert np.array_equal(np.round(res[2][:n_got] / 16), np.round(ref2[2][:n_got] / 16))
+    assert np.abs(res[2] - ref2[2]).max() < 0.05 and np.abs(res[1] - ref2[1]).max() < 1e-3
 
 
 def test_load_model_roundtrip_and_api(tmp_path):
@@ -173,10 +178,14 @@ def test_batch_pipeline_resizes_webcam_frames():
         ref = posenet.decode_multiple_poses_batch(*m.forward_u8(x), output_stride=8, **kw)[:4]
         for a, b in zip(rec, ref):
             assert np.array_equal(a, b.cpu().numpy())
-    # image_demo.py:50 for a whole batch: coordinates mapped back to the 180 x 320 frames
-    scaled = list(pipe.run(frames, source_coords=True))
+    # image_demo.py:50 for a whole batch, on the device (pn_scale_keypoint_coords inside the step's graph): coordinates mapped
+    # back to the 180 x 320 frames, bit-identical with numpy's `keypoint_coords *= output_scale`
+    pipe_s = posenet.BatchPipeline(m, N, H, W, depth=2, output_stride=8, source_coords=True, **kw)
+    scaled = list(pipe_s.run(frames))
     for a, b in zip(scaled, got):
         assert np.array_equal(a[2], b[2] * pipe.scale) and np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+    with pytest.raises(AssertionError):
+        pipe.result(pipe.submit(frames[0]), source_coords=True)     # not a per-call option: the scaling runs before the D2H copy
 
 
 def test_image_stream_feeds_the_pipeline(tmp_path):
@@ -206,3 +215,42 @@ def test_image_stream_feeds_the_pipeline(tmp_path):
                 assert np.array_equal(a[j], b[0].cpu().numpy())
             k += 1
     assert k == 10
+
+
+def test_mixed_size_image_directory(tmp_path):
+    """benchmark.py:24-29 / image_demo.py:33-35 pre-process every file of a directory at its own size.  ImageStream(mixed=True)
+    + BatchPipeline(mixed=True) batch such a directory: every frame is resized on the GPU (pn_resize_u8, cv2-exact) from its
+    own size to the pipeline's network resolution, and with source_coords=True the coordinates come back in each file's own
+    pixel grid -- the same records as the per-image path cv2.imread -> cv2-exact resize -> forward_u8 -> decode -> *= scale."""
+    import cv2
+    sd = onet.init_params(50, seed=5, scheme="scaled", gain=0.8)
+    m = build(50, 16, sd, "bf16")
+    sizes = [(129, 161), (100, 140), (161, 129), (64, 64), (129, 161), (150, 200), (33, 47)]
+    paths = []
+    for i, (h, w) in enumerate(sizes):
+        p = str(tmp_path / ("f%02d.png" % i))
+        assert cv2.imwrite(p, synth.smooth_image(h, w, 70 + i))
+        paths.append(p)
+    N, H, W = 3, 161, 200                                   # the largest frame in each direction
+    kw = dict(max_pose_detections=6, min_pose_score=0.1)
+    with pytest.raises(ValueError):
+        list(posenet.ImageStream(paths, batch=N, height=129, width=161).batches())         # uniform stream: sizes differ
+    stream = posenet.ImageStream(paths, batch=N, height=H, width=W, mixed=True)
+    pipe = posenet.BatchPipeline(m, N, H, W, depth=2, mixed=True, source_coords=True, **kw)
+    th, tw = pipe.th, pipe.tw
+    assert (th, tw) == (161, 193)
+    got = list(pipe.run((b, shapes) for b, _, shapes in stream.batches()))
+    assert len(got) == 3
+    k = 0
+    for rec, nv in zip(got, stream.valid_counts()):
+        for j in range(nv):
+            img = cv2.imread(paths[k])
+            x = torch.from_numpy(opre.resize_linear_u8(img, tw, th)[None]).to(DEV)           # utils.py:21 on this file's own size
+            ref = [t.cpu().numpy() for t in posenet.decode_multiple_poses_batch(*m.forward_u8(x), output_stride=16, **kw)[:4]]
+            ref[2] = ref[2] * np.array([img.shape[0] / th, img.shape[1] / tw])               # utils.py:19 + image_demo.py:50
+            for a, b in zip(rec, ref):
+                assert np.array_equal(a[j], b[0]), (k, img.shape)
+            k += 1
+        for j in range(nv, N):                              # rows without a file decode as black frames, deterministically
+            assert np.isfinite(rec[0][j]).all()
+    assert k == len(paths)

@@ -53,7 +53,7 @@ def test_shifted_descriptor_depthwise_and_tmem_operand(case):
     bd = torch.from_numpy(bias).to(DEV)
     out_dw = torch.zeros((128, 64), dtype=torch.float32, device=DEV)
     out_pw = torch.zeros((128, 64), dtype=torch.float32, device=DEV)
-    nat.check(nat.load().pn_dwtc_probe(P(xd), h, w, P(dd), P(wd_), P(bd), P(out_dw), P(out_pw), wp, dil, q0 - row0 * wp, rows_box,
+    abi.check_diag(abi.load_diag().pn_dwtc_probe(P(xd), h, w, P(dd), P(wd_), P(bd), P(out_dw), P(out_pw), wp, dil, q0 - row0 * wp, rows_box,
                                        x_org, row0 - dil, 0, nat.stream_ptr()), "pn_dwtc_probe")
     torch.cuda.synchronize()
     got_dw, got_pw = out_dw.cpu().numpy(), out_pw.cpu().numpy()

@@ -2,6 +2,7 @@
 the drop-in package mirrors the reference's API surface, and nothing silently falls back."""
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -22,7 +23,21 @@ def test_library_exports_every_declared_symbol():
     lib = nat.load()                                       # raises if missing / symbol absent / ABI mismatch
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.pn_abi_version() == nat.ABI_VERSION == 4
+    assert lib.pn_abi_version() == nat.ABI_VERSION == 5
+    # the product ABI is the hot path only: probes and traces live in a second library / a diagnostics build
+    assert not [n for n in declared if n.startswith(("pn_debug", "pn_dwtc"))]
+    for name in ("pn_dwtc_probe", "pn_debug_umma_cost", "pn_debug_tcs_trace", "pn_debug_sep_trace"):
+        assert not hasattr(lib, name), name
+
+
+def test_diagnostics_library_exports_its_header():
+    import ctypes as C
+    header = open(os.path.join(ROOT, "include", "posenet_b200_diag.h")).read()
+    declared = set(re.findall(r"\b(pn_[a-z0-9_]+)\s*\(", header))
+    assert declared == {"pn_diag_last_error_string", "pn_dwtc_probe", "pn_debug_umma_cost"}, declared
+    lib = C.CDLL(os.path.join(os.path.dirname(nat.LIB_PATH), "libposenet_b200_diag.so"))
+    for name in declared:
+        assert hasattr(lib, name), name
 
 
 def test_struct_layouts_match_header():
@@ -90,6 +105,10 @@ def test_api_surface():
     assert posenet.NUM_KEYPOINTS == 17 and len(posenet.CONNECTED_PART_INDICES) == 12
     assert posenet.valid_resolution(1280 * 0.7125, 720 * 0.7125, 16) == (913, 513)
     import inspect
+    assert list(inspect.signature(posenet.decode.decode_pose).parameters) == [
+        "root_score", "root_id", "root_image_coord", "scores", "offsets", "output_stride", "displacements_fwd", "displacements_bwd"]
+    assert list(inspect.signature(posenet.decode.traverse_to_targ_keypoint).parameters) == [
+        "edge_id", "source_keypoint", "target_keypoint_id", "scores", "offsets", "output_stride", "displacements"]   # decode.py:9-11,131-138
     sig = inspect.signature(posenet.decode_multiple_poses)
     assert [(p.name, p.default) for p in sig.parameters.values()][4:] == [
         ("output_stride", inspect.Parameter.empty), ("max_pose_detections", 10), ("score_threshold", 0.5),
@@ -114,6 +133,12 @@ def test_no_silent_cpu_fallback():
                                       torch.zeros(32, 3, 3), 16)
     with pytest.raises(nat.NativeError):
         posenet._process_input(np.zeros((17, 17, 3), np.uint8))
+    with pytest.raises(nat.NativeError):
+        posenet.decode.decode_pose(0.9, 0, np.zeros(2), np.zeros((17, 3, 3), np.float32), np.zeros((17, 3, 3, 2), np.float32), 16,
+                                   np.zeros((16, 3, 3, 2), np.float32), np.zeros((16, 3, 3, 2), np.float32))
+    with pytest.raises(nat.NativeError):
+        posenet.decode.traverse_to_targ_keypoint(0, np.zeros(2), 1, np.zeros((17, 3, 3), np.float32),
+                                                 np.zeros((17, 3, 3, 2), np.float32), 16, np.zeros((16, 3, 3, 2), np.float32))
 
 
 def test_product_package_never_imports_the_oracle():
@@ -279,3 +304,20 @@ def test_radix_selection_model_partitions_the_sorted_candidates(kind):
     assert all(1 <= len(c) <= 1024 for c in chunks)
     flat = [k for c in chunks for k in c]
     assert flat == sorted(int(k) for k in keys)                      # ascending key == descending score, index ascending
+
+
+def test_reference_scripts_are_pinned():
+    """oracle/make_ref.py compiles benchmark.py / image_demo.py from the reference checkout only when their sha256 is the pinned
+    one; the manifest of an existing oracle/_ref build records the same digests ("run unchanged" is checked, not assumed)."""
+    from oracle import make_ref
+    ref = "/root/reference"
+    if os.path.isdir(ref):
+        for name, digest in make_ref.SCRIPT_SHA256.items():
+            assert make_ref.sha256_file(os.path.join(ref, name)) == digest, name
+    m = make_ref.manifest()
+    if m is not None:
+        assert m["scripts_sha256"] == make_ref.SCRIPT_SHA256
+        if os.path.isdir(ref):
+            assert m["package_sha256"] == make_ref.tree_digest(os.path.join(ref, "posenet"))
+    tracked = subprocess.run(["git", "ls-files", "oracle/_ref"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
+    assert tracked == "", "oracle/_ref must stay out of the history"

@@ -47,3 +47,31 @@ def test_errors(tmp_path):
         list(posenet.ImageStream(paths + [odd], batch=2).batches())
     with pytest.raises(IOError):
         list(posenet.ImageStream(paths + [str(tmp_path / "gone.png")], batch=2, height=20, width=20).batches())
+
+
+def test_mixed_sizes_and_prefetch(tmp_path):
+    """mixed=True: files of different sizes land at their own size at the start of their batch row, with their shapes; the
+    decode of the batch after next is already running when a batch is handed out (launch before the yield)."""
+    import cv2
+    import numpy as np
+    import posenet
+    sizes = [(40, 60), (64, 64), (30, 20), (64, 50), (10, 64)]
+    paths, imgs = [], []
+    rng = np.random.default_rng(0)
+    for i, (h, w) in enumerate(sizes):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        p = str(tmp_path / ("m%d.png" % i))
+        assert cv2.imwrite(p, img)
+        paths.append(p); imgs.append(img)
+    st = posenet.ImageStream(paths, batch=2, height=64, width=64, mixed=True, pinned=False)
+    k = 0
+    for buf, nv, shapes in st.batches():
+        assert tuple(buf.shape) == (2, 64, 64, 3) and len(shapes) == nv
+        flat = buf.numpy().reshape(2, -1)
+        for j in range(nv):
+            assert tuple(shapes[j]) == sizes[k]
+            assert np.array_equal(flat[j, :imgs[k].size], imgs[k].reshape(-1))
+            k += 1
+    assert k == len(paths)
+    with pytest.raises(ValueError):
+        list(posenet.ImageStream(paths, batch=2, height=32, width=64, mixed=True, pinned=False).batches())

@@ -12,7 +12,7 @@ from oracle import net as onet
 from oracle import preprocess as opre
 from oracle import synth
 
-from golden.make_golden_cases import DEC_CASES, NET_CASES, PRE_CASES, heads_for
+from golden.make_golden_cases import POSE_CASES, DEC_CASES, NET_CASES, PRE_CASES, heads_for
 
 
 def sha(a):
@@ -105,3 +105,26 @@ def test_people_generator_is_decodable():
     for p in range(found):
         d = np.abs(kps - kc[p][None]).reshape(len(kps), -1).max(axis=1)
         assert d.min() < 1e-3
+
+
+@pytest.mark.parametrize("ci", range(len(POSE_CASES)))
+def test_decode_pose_and_traverse_bit_exact(golden_dir, ci):
+    """decode.py:9-63,131-182 called on their own: the oracle against the reference's outputs (decode_pose.npz)."""
+    g = np.load(os.path.join(golden_dir, "decode_pose.npz"))
+    di, _ = POSE_CASES[ci]
+    kind, h, w, stride, people, seed, P, thr, rad, minp, _patch, extra = DEC_CASES[di]
+    heat, off, fwd, bwd = heads_for(kind, h, w, stride, people, seed, extra)
+    assert sha(np.concatenate([heat.ravel(), off.ravel(), fwd.ravel(), bwd.ravel()])) == str(g["in_sha_%d" % ci])
+    split = lambda a: a.reshape(2, -1, h, w).transpose(1, 2, 3, 0)
+    offs, fwd_t, bwd_t = split(off), split(fwd), split(bwd)
+    roots, t = g["roots_%d" % ci], 0
+    assert len(roots) >= 3 and (roots[:, 0] == 0.0).any() and (roots[:, 0] < 0.0).any()
+    for r, (rs, rid, ry, rx) in enumerate(roots):
+        ks, kc, ko = odec.decode_pose(np.float32(rs), int(rid), np.array([ry, rx]), heat, offs, stride, fwd_t, bwd_t)
+        assert np.array_equal(ks, g["ks_%d" % ci][r]) and np.array_equal(kc, g["kc_%d" % ci][r]) and np.array_equal(ko, g["ko_%d" % ci][r])
+        for e, (parent, child) in enumerate(odec.EDGES):
+            for tgt, disp in ((child, fwd_t), (parent, bwd_t)):
+                sc, xy, dv, ov = odec.traverse_to_targ_keypoint(e, np.array([ry, rx]), tgt, heat, offs, stride, disp)
+                assert np.array_equal(np.concatenate([[sc], xy, dv, ov]).astype(np.float64), g["tr_%d" % ci][t]), (r, e, tgt)
+                t += 1
+    assert t == len(g["tr_%d" % ci])

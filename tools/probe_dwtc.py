@@ -1,14 +1,15 @@
-"""Runs pn_dwtc_probe (csrc/dwtc_probe.cu) on a B200 and compares with numpy: shifted-descriptor depthwise on tcgen05,
+"""Runs pn_dwtc_probe (csrc/diag/dwtc_probe.cu) on a B200 and compares with numpy: shifted-descriptor depthwise on tcgen05,
 A-from-TMEM pointwise.  Prints max errors for both base-offset variants and several chunk geometries."""
 import ctypes as C
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "posenet-pytorch_b200"))
+sys.path[:0] = [os.path.join(ROOT, "posenet-pytorch_b200"), os.path.join(ROOT, "tests")]
 import numpy as np
 import torch
 from posenet import _native as nat
+import abi
 
 lib = nat.load()
 P = lambda t: C.c_void_p(t.data_ptr())
@@ -40,7 +41,7 @@ def run(h, w, dil, wp, x_org, band_x0, tw, r0, chunk, flags, seed=0):
     bd = torch.from_numpy(bias).cuda()
     out_dw = torch.zeros((128, 64), dtype=torch.float32, device="cuda")
     out_pw = torch.zeros((128, 64), dtype=torch.float32, device="cuda")
-    nat.check(lib.pn_dwtc_probe(P(xd), h, w, P(dd), P(wd_), P(bd), P(out_dw), P(out_pw), wp, dil, qoff, rows_box, x_org, y_org,
+    abi.check_diag(abi.load_diag().pn_dwtc_probe(P(xd), h, w, P(dd), P(wd_), P(bd), P(out_dw), P(out_pw), wp, dil, qoff, rows_box, x_org, y_org,
                                 flags, nat.stream_ptr()), "pn_dwtc_probe")
     torch.cuda.synchronize()
     got_dw, got_pw = out_dw.cpu().numpy(), out_pw.cpu().numpy()

@@ -46,5 +46,6 @@ def run(n, h, w, cin, cout, stride, dil, cap=256, show=24):
 
 
 if __name__ == "__main__":
-    for shp in [(64, 33, 33, 512, 512, 1, 1)]:
-        run(*shp)
+    shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]] or [(64, 33, 33, 512, 512, 1, 1)]
+    for shp in shapes:
+        run(*shp, show=40)

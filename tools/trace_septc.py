@@ -1,4 +1,5 @@
-"""Timeline of CTA 0 of septc_kernel (clock64 stamps at the hand-offs, see TCS_TR in csrc/septc.cu)."""
+"""Timeline of CTA 0 of septc_kernel (clock64 stamps at the hand-offs, see TCS_TR in csrc/septc.cu).
+Needs a diagnostics build: PN_EXTRA_NVCC_FLAGS=-DPN_TCS_TRACE python posenet-pytorch_b200/build.py --force."""
 import ctypes as C
 import os
 import sys

@@ -1,17 +1,17 @@
-"""Cycles per tcgen05.mma (M128 x N x K16, bf16) on one SM for small N and operand layouts (csrc/dwtc_probe.cu: umma_cost_kernel)."""
+"""Cycles per tcgen05.mma (M128 x N x K16, bf16) on one SM for small N and operand layouts (csrc/diag/dwtc_probe.cu: umma_cost_kernel)."""
 import ctypes as C
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "posenet-pytorch_b200"))
+sys.path[:0] = [os.path.join(ROOT, "posenet-pytorch_b200"), os.path.join(ROOT, "tests")]
 import torch
-from posenet import _native as nat
+from posenet import _native as nat  # noqa: F401
+import abi
 
 torch.cuda.set_device(0)
 torch.zeros(1, device="cuda")
-lib = C.CDLL(nat.LIB_PATH)
-lib.pn_debug_umma_cost.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+lib = abi.load_diag()
 out = (C.c_longlong * 2)()
 reps = 64
 for layout, name in ((0, "SW128, one thread"), (3, "SW128, uniform issue"), (2, "SW64 rows, one thread"), (1, "SW32 rows, one thread")):
