@@ -162,7 +162,7 @@ def cpu_reference_run(workload, images_per_step, steps, warmup):
     imgs = [synth.noise_image(sh, sw, s) for s in range(4)]
     if make_ref.available():
         assert "posenet" not in sys.modules, "the reference arm needs a process that has not imported the product package"
-        sys.path.insert(0, make_ref.REF_DIR)
+        sys.path.insert(0, make_ref.IMPORT_PATH)
         import posenet as ref
         import posenet.decode_multi as ref_dm
         assert os.path.realpath(ref.__file__).startswith(os.path.realpath(make_ref.REF_DIR)), ref.__file__

@@ -5,18 +5,20 @@
 The reference is pure Python; "building" it means byte-compiling its sources WHERE THEY LIE under /root/reference into
 CPython bytecode files (no reference source text is copied into this repository):
 
-    /root/reference/posenet/**/*.py   -> oracle/_ref/posenet/**/*.pyc    (sourceless package: the CPU arm of bench.py imports it)
-    /root/reference/benchmark.py      -> oracle/_ref/scripts/benchmark.pyc
-    /root/reference/image_demo.py     -> oracle/_ref/scripts/image_demo.pyc
+    /root/reference/posenet/**/*.py   -> oracle/_ref/reference.zip : posenet/**/*.pyc   (sourceless package, imported through zipimport)
+    /root/reference/benchmark.py      -> oracle/_ref/scripts.zip   : benchmark.pyc
+    /root/reference/image_demo.py     -> oracle/_ref/scripts.zip   : image_demo.pyc
 
-``oracle/_ref/`` is git-ignored but NOT gpurun-ignored, so it travels to the GPU box with the working tree like the built
-``.so`` files (same image, same interpreter: the bytecode loads there).  Two consumers, both test / measurement infrastructure:
+(two uncompressed zip archives rather than loose ``.pyc`` files: the gpurun snapshot leaves ``*.pyc`` behind).  ``oracle/_ref/`` is
+git-ignored but NOT gpurun-ignored, so it travels to the GPU box with the working tree like the built ``.so`` files (same
+image, same interpreter: the bytecode loads there).  Two consumers, both test / measurement infrastructure:
 
-* ``bench.py --impl reference`` and the ``cpu_baseline`` leg import ``oracle/_ref/posenet`` (``kind: "reference"``) and time
+* ``bench.py --impl reference`` and the ``cpu_baseline`` leg put ``oracle/_ref/reference.zip`` on ``sys.path`` (``IMPORT_PATH``), import
+  the reference's ``posenet`` from it (``kind: "reference"``) and time
   the reference's own code on the host cores; without ``oracle/_ref`` they fall back to the oracle port (``kind: "port"``).
-* ``tests/test_gpu_ref_scripts.py`` runs the two scripts UNCHANGED (their bytecode, ``python benchmark.pyc ...``) as
-  subprocesses against the product package (``PYTHONPATH=posenet-pytorch_b200``).  The scripts sit in their own directory so
-  that ``import posenet`` inside them resolves to the product package and not to the reference package next to them.
+* ``tests/test_gpu_ref_scripts.py`` runs the two scripts UNCHANGED (their bytecode, extracted with ``extract_scripts`` and run as
+  ``python benchmark.pyc ...``) as subprocesses against the product package (``PYTHONPATH=posenet-pytorch_b200``).  The scripts
+  live in their own archive so that ``import posenet`` inside them resolves to the product package, not to the reference.
 
 ``SCRIPT_SHA256`` pins the script SOURCES the bytecode was compiled from: the recipe refuses to compile anything else and
 records the digests it saw in ``oracle/_ref/MANIFEST.json``; ``tests/test_host_cpu.py`` checks them against ``/root/reference``
@@ -28,6 +30,8 @@ import os
 import py_compile
 import shutil
 import sys
+import tempfile
+import zipfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
@@ -57,9 +61,12 @@ def tree_digest(root):
     return h.hexdigest()
 
 
+IMPORT_PATH = os.path.join(REF_DIR, "reference.zip")          # put this on sys.path to import the reference's `posenet`
+SCRIPTS_ZIP = os.path.join(REF_DIR, "scripts.zip")
+
+
 def available():
-    return os.path.exists(os.path.join(REF_DIR, "posenet", "__init__.pyc")) and \
-        all(os.path.exists(os.path.join(REF_DIR, "scripts", s + "c")) for s in SCRIPTS)
+    return os.path.exists(IMPORT_PATH) and os.path.exists(SCRIPTS_ZIP) and os.path.exists(os.path.join(REF_DIR, "MANIFEST.json"))
 
 
 def manifest():
@@ -67,9 +74,24 @@ def manifest():
     return json.load(open(path)) if os.path.exists(path) else None
 
 
-def _compile(src, dst, shown_as):
-    os.makedirs(os.path.dirname(dst), exist_ok=True)
-    py_compile.compile(src, cfile=dst, dfile=shown_as, doraise=True, invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+def extract_scripts(dst_dir):
+    """Unpack benchmark.pyc / image_demo.pyc into ``dst_dir`` (a scratch directory) and return their paths by script name."""
+    os.makedirs(dst_dir, exist_ok=True)
+    out = {}
+    with zipfile.ZipFile(SCRIPTS_ZIP) as z:
+        for s in SCRIPTS:
+            z.extract(s + "c", dst_dir)
+            out[s] = os.path.join(dst_dir, s + "c")
+    return out
+
+
+def _compile(src, shown_as):
+    """Bytecode of ``src`` as the bytes of a .pyc file (unchecked-hash invalidation: independent of source mtimes)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        dst = os.path.join(tmp, "x.pyc")
+        py_compile.compile(src, cfile=dst, dfile=shown_as, doraise=True, invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+        with open(dst, "rb") as f:
+            return f.read()
 
 
 def make(reference="/root/reference", quiet=False):
@@ -79,20 +101,23 @@ def make(reference="/root/reference", quiet=False):
         return available()
     if os.path.isdir(REF_DIR):
         shutil.rmtree(REF_DIR)
+    os.makedirs(REF_DIR)
     n = 0
     src_pkg = os.path.join(reference, "posenet")
-    for d, dirs, files in os.walk(src_pkg):
-        dirs[:] = sorted(x for x in dirs if x != "__pycache__")
-        for f in sorted(files):
-            if f.endswith(".py"):
-                rel = os.path.relpath(os.path.join(d, f), reference)
-                _compile(os.path.join(d, f), os.path.join(REF_DIR, rel + "c"), "<reference>/" + rel)
-                n += 1
+    with zipfile.ZipFile(IMPORT_PATH, "w", zipfile.ZIP_STORED) as z:
+        for d, dirs, files in os.walk(src_pkg):
+            dirs[:] = sorted(x for x in dirs if x != "__pycache__")
+            for f in sorted(files):
+                if f.endswith(".py"):
+                    rel = os.path.relpath(os.path.join(d, f), reference)
+                    z.writestr(rel + "c", _compile(os.path.join(d, f), "<reference>/" + rel))
+                    n += 1
     seen = {}
-    for s in SCRIPTS:
-        seen[s] = sha256_file(os.path.join(reference, s))
-        assert seen[s] == SCRIPT_SHA256[s], "%s changed upstream: %s" % (s, seen[s])
-        _compile(os.path.join(reference, s), os.path.join(REF_DIR, "scripts", s + "c"), "<reference>/" + s)
+    with zipfile.ZipFile(SCRIPTS_ZIP, "w", zipfile.ZIP_STORED) as z:
+        for s in SCRIPTS:
+            seen[s] = sha256_file(os.path.join(reference, s))
+            assert seen[s] == SCRIPT_SHA256[s], "%s changed upstream: %s" % (s, seen[s])
+            z.writestr(s + "c", _compile(os.path.join(reference, s), "<reference>/" + s))
     with open(os.path.join(REF_DIR, "MANIFEST.json"), "w") as f:
         json.dump({"scripts_sha256": seen, "package_sha256": tree_digest(src_pkg), "package_files": n,
                    "python": "%d.%d" % sys.version_info[:2]}, f, indent=1, sort_keys=True)

@@ -430,7 +430,10 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 const int rem = m_tile - img * m_tiles_per_img;
                 const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
                 const int oy = ty * g.th + r_ty, ox = tx * g.tw + r_tx;
-                const bool row_ok = r_ty < g.th && oy < g.ho && ox < g.wo;
+                bool row_ok = r_ty < g.th && oy < g.ho && ox < g.wo;
+#ifdef PN_SEP_EXP
+                if (g.exp & 16) row_ok = false;                           // experiment: the epilogue without its global stores
+#endif
                 const int colg = col_base + n_tile * g.n_tile;            // first global output channel of this accumulator
                 __nv_bfloat16 *yrow = y + (((size_t)img * g.ho + oy) * g.wo + ox) * (size_t)g.nc + colg;
                 const int col_lim = g.nc - colg;                          // columns of this block that exist (ragged N)
@@ -867,9 +870,15 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
                    (long long)pst * g.patch_stage_bytes <= avail;
     };
     int bestp = -1;
-    // PN_SEP_DIRECT=1: the epilogue stores straight from registers (no staging panel, stg = 0); the 16-32 KB go to the rings
-    const bool direct = getenv("PN_SEP_DIRECT") != nullptr && atoi(getenv("PN_SEP_DIRECT")) != 0;
-    const int max_a1 = direct ? 5 : 3;
+    // Direct epilogue (stg = 0): stores straight from registers, no staging panels, no CTA barriers, TMEM loads pipelined; the
+    // 16-32 KB of the panels go to the rings.  It is the default for single-accumulator tiles (n_tile > 256: the epilogue
+    // cannot overlap the next tile's MMAs there, so its barrier hand-offs are pure stall) -- measured on B200, fused block
+    // alone: 256 -> 512 stride 2 at 65x65 95 -> 72 us, 192 -> 384 stride 2 at 33x33 110 -> 94 us, 384 -> 384 at 17x17 128 -> 113 us,
+    // 512 -> 512 at 33x33 68 -> 65 us.  Double-buffered tiles keep the staged TMA-store epilogue (it overlaps the main loop;
+    // direct stores are scattered 32-byte pieces and measured 10 % slower there).  PN_SEP_DIRECT=0 / 1 forces either.
+    bool direct = g.acc_bufs == 1 && g.cl == 1;
+    if (const char *e = getenv("PN_SEP_DIRECT")) direct = atoi(e) != 0;
+    const int max_a1 = direct ? 4 : 3;
     for (int stg = direct ? 0 : 2; stg >= (direct ? 0 : 1); --stg)
         for (int ast = SEP_MAX_A; ast >= 2; --ast) {
             if (g.cl == 1 && ast > max_a1) continue;
@@ -880,8 +889,10 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
                     // (a cluster CTA consumes patches for 1 / cl of the k-blocks only: two stages cover it, A stages matter more)
                     const int want = g.cl > 1 ? (g.subs + 1 > 2 ? g.subs + 1 : 2) : 3 * g.subs > SEP_MAX_P ? SEP_MAX_P : 3 * g.subs;
                     // deep patch prefetch first, then one spare W block, a third A stage, a second staging panel
-                    const int score = (pst >= want ? 1000 : pst * 100) + (wst > min_w + 1 ? min_w + 1 : wst) * 20 + (g.cl > 1 ? (ast > 4 ? 4 : ast) * 16 : ast * 8) + stg * 4 +
-                                      (pst > want ? 1 : 0);
+                    // (direct epilogue: a fourth A stage lets the depthwise warps run further ahead while the accumulator drains;
+                    // it measured better than a fourth W block)
+                    const int score = (pst >= want ? 1000 : pst * 100) + (wst > min_w + (direct ? 0 : 1) ? min_w + (direct ? 0 : 1) : wst) * 20 +
+                                      (g.cl > 1 ? (ast > 4 ? 4 : ast) * 16 : ast * (direct ? 24 : 8)) + stg * 4 + (pst > want ? 1 : 0);
                     if (score > bestp) {
                         bestp = score;
                         g.p_stages = pst; g.w_stages = wst; g.a_stages = ast; g.stg_bufs = stg;

@@ -2,7 +2,7 @@
 benchmark.py run unchanged").
 
 ``oracle/make_ref.py`` byte-compiles ``/root/reference/benchmark.py`` (:16-46) and ``/root/reference/image_demo.py`` (:20-69)
--- sha256-pinned sources -- into ``oracle/_ref/scripts/``; here they run as subprocesses with ``PYTHONPATH`` pointing at
+-- sha256-pinned sources -- into ``oracle/_ref/scripts.zip``; here they are unpacked and run as subprocesses with ``PYTHONPATH`` pointing at
 ``posenet-pytorch_b200`` so that their ``import posenet`` is the product, on a directory of synthetic images of DIFFERENT
 sizes (benchmark.py:24-29 / image_demo.py:33-35 pre-process every file at its own size) and a random-init checkpoint written
 where ``load_model`` looks for it (``./_models``)."""
@@ -37,12 +37,13 @@ def workdir(tmp_path_factory):
         assert cv2.imwrite(str(d / "images" / ("img%d.%s" % (i, ext))), synth.smooth_image(h, w, seed=40 + i))
     for mid in (101, 50):
         posenet.write_random_checkpoint(mid, str(d / "_models"), seed=mid)
+    make_ref.extract_scripts(str(d / "ref_scripts"))
     return d
 
 
 def _run(script, workdir, *args):
     env = dict(os.environ, PYTHONPATH=PKG, PYTHONDONTWRITEBYTECODE="1")
-    r = subprocess.run([sys.executable, os.path.join(make_ref.REF_DIR, "scripts", script + "c")] + list(args), cwd=str(workdir),
+    r = subprocess.run([sys.executable, str(workdir / "ref_scripts" / (script + "c"))] + list(args), cwd=str(workdir),
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, "%s failed:\n%s\n%s" % (script, r.stdout[-2000:], r.stderr[-3000:])
     return r.stdout
