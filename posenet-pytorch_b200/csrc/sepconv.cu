@@ -223,9 +223,8 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    {   // depthwise segment table (strip column | first row << 8 | rows << 16) and the hand-out counter
+    {   // depthwise segment table (strip column | first row << 8 | rows << 16)
         uint32_t *misc = reinterpret_cast<uint32_t *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bar);
-        if (threadIdx.x < 8) misc[SepBars::seg_ctr / 4 + threadIdx.x] = 0u;
         if ((int)threadIdx.x < g.segs_per_sub) misc[SepBars::seg_tab / 4 + threadIdx.x] = g.segtab[threadIdx.x];
     }
     {   // pointwise bias -> shared memory once (the epilogue reads it per panel)
@@ -540,16 +539,19 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const uint32_t lane_off = (uint32_t)(hsel * S) * PIX + (uint32_t)cp * 4u;
         const uint32_t a_lane = (uint32_t)(cp >> 2) << 4 | (uint32_t)(cp & 3) << 2;       // 16 B chunk | byte inside it
         auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
-        int *seg_ctr = reinterpret_cast<int *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bar + SepBars::seg_ctr);
         const uint32_t tab_addr = bars + (uint32_t)SepBars::seg_tab;
-        const int grabs_per_use = g.segs_per_sub + SEP_DW_WARPS;     // every warp ends an item with one empty-handed grab
 
         // Every warp walks all items -- (tile, k-block, sub-tile), one patch stage each -- in order, so its mbarrier parities
-        // never skip a phase; inside an item the segments are handed out by an atomic counter per patch stage (uses of a
-        // stage cannot interleave: the refill waits for all warps to have left the previous use).  A warp that finds the
-        // item exhausted moves straight on to the next one while the others finish.
-        int ps = 0, as = rank, puse = 0, tr_d = 0;                       // cluster: this CTA fills the A stages s % CL == rank
+        // never skip a phase.  Inside an item the segments are assigned statically: warp w takes segments (w + item) mod
+        // DW_WARPS, + DW_WARPS, ... -- the rotation spreads the short segments (and the warp left without one when there are
+        // 9 segments for 10 warps) over all warps and schedulers.  A shared-memory counter handing the segments out on demand
+        // balanced an item a little better but cost an atomic, a shuffle and two divergent branches per grab, i.e. 10-15 % of
+        // a depthwise warp's time at one ~2000-cycle segment per warp and item (ncu source view: `branch_resolving` and
+        // `short_scoreboard` on the grab, 6 % of the kernel on four shapes).  A warp without work in an item moves straight on
+        // to the next one while the others finish.
+        int ps = 0, as = rank, tr_d = 0;                                 // cluster: this CTA fills the A stages s % CL == rank
         uint32_t pph = 0, aph = 0;
+        int rot = warp - SEP_FIRST_DW_WARP;                              // this warp's first segment in the current item
         (void)tr_d;
         const bool tracer = (warp == SEP_FIRST_DW_WARP && lane == 0);
         (void)tracer;
@@ -563,14 +565,9 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               mbar_wait(bar(SepBars::patch_full, ps), pph);
               if (tracer && sub == 0) SEP_TRACE(0, tr_d, 2);
               const uint32_t stage = p_addr(ps);
-              const int grab_base = puse * grabs_per_use;
               float2 wk[9], bias2;
               bool have_w = false;
-              for (;;) {
-                int seg = 0;
-                if (lane == 0) seg = atomicAdd(seg_ctr + ps, 1) - grab_base;
-                seg = __shfl_sync(0xFFFFFFFFu, seg, 0);
-                if (seg >= g.segs_per_sub) break;
+              for (int seg = rot; seg < g.segs_per_sub; seg += SEP_DW_WARPS) {
                 if (!have_w) {
                     const uint32_t wsm = stage + g.wgt_off + (uint32_t)cp * 8u;
 #pragma unroll
@@ -671,7 +668,8 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               }   // segments of this item
               __syncwarp();
               if (lane == 0) mbar_arrive(bar(SepBars::patch_empty, ps));   // this warp no longer reads the patch
-              if (++ps == g.p_stages) { ps = 0; pph ^= 1; ++puse; }
+              if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
+              if (++rot == SEP_DW_WARPS) rot = 0;
             }
             fence_async_smem();                                       // A-tile writes -> visible to the tensor core
             __syncwarp();
