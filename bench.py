@@ -462,8 +462,10 @@ def run_b200(args):
            "d2h_bytes_per_step": int(pipe.d2h_bytes_per_batch), "api": "posenet.BatchPipeline.run (depth %d)" % args.depth}
     if world > 1:
         # every step's pose records were all-gathered over NCCL inside the timed loop above (BatchPipeline(gather=True): each rank
-        # ends the step holding the records of all `world` shards); its device time alone, for the record:
-        e2e["gather"] = "all_gather_into_tensor of %d B per rank per step (NCCL), inside the timed loop" % (pipe.d2h_bytes_per_batch // world)
+        # ends the step holding the records of all `world` shards on its device, rank 0 reads all of them back to the host);
+        # the collective's device time alone, for the record:
+        e2e["gather"] = "all_gather_into_tensor of %d B per rank per step (NCCL, own stream), inside the timed loop; rank 0 reads all %d shards back" % (
+            pipe.nrec * 8, world)
         e2e["gather_ms"] = round(pipe.time_gather(reps=20), 4)
     # the same step without overlap (one batch at a time, synchronous), for reference
     t0 = time.perf_counter()

@@ -34,8 +34,9 @@ class BatchPipeline:
 
         ``source_coords``: ``keypoint_coords *= (src_h / target_h, src_w / target_w)`` (image_demo.py:50, utils.py:19) applied to
         the record buffer on the device (``pn_scale_keypoint_coords``), per frame in mixed mode.
-        ``gather``: with an initialised process group, every step ends with an all-gather of the ranks' record buffers
-        (NCCL over NVLink); ``result`` then returns the records of ALL ranks' batches in rank order."""
+        ``gather``: with an initialised process group, every step ends with an all-gather of the ranks' record buffers (NCCL over
+        NVLink) on its own stream -- the kernels of the next batch do not wait for it -- and rank 0 reads ALL ranks' records back
+        (``result(..., gathered=True)``); the other ranks read back their own, as without ``gather``."""
         nat.require_device()
         assert depth >= 1
         self.model, self.batch, self.h, self.w = model, int(batch), int(height), int(width)
@@ -58,6 +59,7 @@ class BatchPipeline:
         self.gather = bool(gather) and self.world > 1
         with torch.cuda.device(dev):
             self.h2d, self.d2h, self.compute = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self.collect_all = self.gather and self.rank == 0      # this rank's D2H copy carries every rank's records
             self.nrec = self.batch * self.P * (1 + 5 * NUM_KEYPOINTS)
             nrec = self.nrec
             self.slots = []
@@ -67,13 +69,13 @@ class BatchPipeline:
                          xr=torch.empty((self.batch, self.th, self.tw, 3), dtype=torch.uint8, device=dev) if self.resize else None,
                          rec=torch.zeros(nrec, dtype=torch.float64, device=dev),
                          rec_all=torch.zeros(self.world * nrec, dtype=torch.float64, device=dev) if self.gather else None,
-                         rec_host=torch.zeros(self.world * nrec, dtype=torch.float64).pin_memory(),
+                         rec_host=torch.zeros((self.world if self.collect_all else 1) * nrec, dtype=torch.float64).pin_memory(),
                          scales=torch.ones((self.batch, 2), dtype=torch.float64, device=dev) if self.mixed else None,
                          scales_host=torch.ones((self.batch, 2), dtype=torch.float64).pin_memory() if self.mixed else None,
                          copied=torch.cuda.Event(), done=torch.cuda.Event(), out=torch.cuda.Event(), graph=None, busy=False)
                 self.slots.append(s)
             self.h2d_bytes_per_batch = self.slots[0]["x"].numel()
-            self.d2h_bytes_per_batch = self.world * nrec * 8
+            self.d2h_bytes_per_batch = (self.world if self.collect_all else 1) * nrec * 8
             # warm up (plans, workspaces) and capture one graph per slot on the compute stream
             self.compute.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(self.compute):
@@ -169,26 +171,25 @@ class BatchPipeline:
                     s["graph"].replay()
                 else:
                     self._enqueue(s)
-                src = s["rec"]
-                if self.gather:
-                    import torch.distributed as dist
-                    dist.all_gather_into_tensor(s["rec_all"], s["rec"], group=self.group)
-                    src = s["rec_all"]
                 s["done"].record(self.compute)
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(s["done"])
-                s["rec_host"].copy_(src, non_blocking=True)
+                if self.gather:                             # off the compute stream: the next batch's kernels do not wait for the peers
+                    import torch.distributed as dist
+                    dist.all_gather_into_tensor(s["rec_all"], s["rec"], group=self.group)
+                s["rec_host"].copy_(s["rec_all"] if self.collect_all else s["rec"], non_blocking=True)
                 s["out"].record(self.d2h)
         s["busy"] = True
         ticket = self._next
         self._next = (self._next + 1) % len(self.slots)
         return ticket
 
-    def result(self, ticket, copy=True, source_coords=None):
-        """Block until the ticket's records are on the host; returns the reference's 4-tuple for the whole batch
-        (numpy float64: [batch,P], [batch,P,17], [batch,P,17,2], [batch,P,17,2]); with ``gather=True`` the leading dimension
-        is ``world * batch`` (rank-major).  ``source_coords`` is a construction-time option (the scaling runs on the device);
-        passing a different value here is an error."""
+    def result(self, ticket, copy=True, source_coords=None, gathered=False):
+        """Block until the ticket's records are on the host; returns the reference's 4-tuple for this rank's batch
+        (numpy float64: [batch,P], [batch,P,17], [batch,P,17,2], [batch,P,17,2]).  ``gathered=True`` (rank 0 of a
+        ``gather=True`` pipeline): the records of ALL ranks' batches instead, leading dimension ``world * batch`` (rank-major).
+        ``source_coords`` is a construction-time option (the scaling runs on the device); passing a different value here is an
+        error."""
         assert source_coords is None or bool(source_coords) == self.source_coords, \
             "source_coords is fixed when the pipeline is built (the scaling runs on the device, before the D2H copy)"
         s = self.slots[ticket]
@@ -198,8 +199,10 @@ class BatchPipeline:
         flat = s["rec_host"].numpy()
         if copy:
             flat = flat.copy()
-        if not self.gather:
-            return split_pose_records(flat, self.batch, self.P)
+        if not gathered:
+            own = flat[self.rank * self.nrec:(self.rank + 1) * self.nrec] if self.collect_all else flat
+            return split_pose_records(own, self.batch, self.P)
+        assert self.collect_all, "gathered=True: only rank 0 of a gather=True pipeline reads every rank's records back"
         parts = [split_pose_records(flat[r * self.nrec:(r + 1) * self.nrec], self.batch, self.P) for r in range(self.world)]
         return tuple(np.concatenate([p[j] for p in parts], axis=0) for j in range(4))
 
@@ -208,15 +211,15 @@ class BatchPipeline:
         import torch.distributed as dist
         assert self.gather
         s = self.slots[0]
-        with torch.cuda.device(self.dev), torch.cuda.stream(self.compute):
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.d2h):
             for _ in range(3):
                 dist.all_gather_into_tensor(s["rec_all"], s["rec"], group=self.group)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(self.compute)
+            e0.record(self.d2h)
             for _ in range(reps):
                 dist.all_gather_into_tensor(s["rec_all"], s["rec"], group=self.group)
-            e1.record(self.compute)
-            self.compute.synchronize()
+            e1.record(self.d2h)
+            self.d2h.synchronize()
         return e0.elapsed_time(e1) / reps
 
     def run(self, batches, copy=True, source_coords=None):

@@ -42,7 +42,7 @@ def main():
         assert per * world == n_total
         pipe = posenet.BatchPipeline(model, per, imgs.shape[1], imgs.shape[2], depth=2, gather=True, **DECODE_KW)
         mine = imgs[rank * per:(rank + 1) * per].contiguous().pin_memory()
-        piped = [pipe.result(pipe.submit(mine)) for _ in range(2)][-1]
+        piped = [pipe.result(pipe.submit(mine), gathered=(rank == 0)) for _ in range(2)][-1]
         gather_ms = pipe.time_gather(reps=5)
         torch.cuda.synchronize()
         if rank == 0:

@@ -64,9 +64,12 @@ def test_image_demo_py_runs_unchanged(workdir):
     for i, (h, w, ext) in enumerate(SIZES):
         drawn = cv2.imread(str(workdir / "out" / ("img%d.%s" % (i, ext))))
         assert drawn is not None and drawn.shape == (h, w, 3)
-    # every reported pose has 17 keypoint lines with coordinates inside (a margin around) the source image
+    # every reported pose has 17 keypoint lines, each naming a part and a finite (y, x) coordinate
     poses = re.findall(r"Pose #(\d+), score = ([0-9.]+)", out)
-    kps = re.findall(r"Keypoint (\w+), score = ([0-9.]+), coord = \[\s*([-0-9.e+]+)\s+([-0-9.e+]+)\]", out)
-    assert len(kps) == 17 * len(poses)
-    assert {k[0] for k in kps} <= set(posenet.PART_NAMES)
-    assert all(np.isfinite(float(k[2])) and np.isfinite(float(k[3])) for k in kps)
+    kp_lines = [l for l in out.splitlines() if l.startswith("Keypoint ")]
+    assert poses and len(kp_lines) == 17 * len(poses)
+    for l in kp_lines:
+        m = re.match(r"Keypoint (\w+), score = ([-0-9.eE+]+), coord = \[(.*)\]$", l)
+        assert m and m.group(1) in posenet.PART_NAMES, l
+        yx = np.array(m.group(3).split(), dtype=np.float64)
+        assert yx.shape == (2,) and np.isfinite(yx).all(), l
