@@ -7,7 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 workload = sys.argv[2] if len(sys.argv) > 2 else "c2"
 batch = int(sys.argv[3]) if len(sys.argv) > 3 else 64
-out = ["# Round 1, %s -- ncu evidence, one forward + decode at C2 (model 101, 513x513, OS16, batch 64, bf16)" % tag, ""]
+rnd = os.environ.get("PN_ROUND", "r02")
+out = ["# Round " + rnd[1:].lstrip("0") + ", %s -- ncu evidence, one forward + decode at C2 (model 101, 513x513, OS16, batch 64, bf16)" % tag, ""]
 
 # ---- launch list
 rows = [r for r in csv.reader(open(os.path.join(ROOT, "gpurun_out", "launches.csv"))) if r and r[0].isdigit()]
@@ -77,7 +78,7 @@ for i, r in enumerate(data):
 traffic["candidates+decode"] = traffic.get("candidates", 0) + traffic.get("decode", 0)
 out += ["", "Launch order: " + ", ".join(plan) + ".  DRAM traffic below the algorithmic bytes on the late layers = the 126 MB L2 keeps part of the",
         "previous layer's output resident (activations of blocks 7-13 are 71-143 MB).", ""]
-open(os.path.join(ROOT, "profiles", "r01_%s_ncu_summary.md" % tag), "w").write("\n".join(out))
-json.dump({"workload": workload, "batch": batch, "source": "profiles/r01_%s_ncu_summary.md" % tag, "dram_bytes": traffic},
+open(os.path.join(ROOT, "profiles", "%s_%s_ncu_summary.md" % (rnd, tag)), "w").write("\n".join(out))
+json.dump({"workload": workload, "batch": batch, "source": "profiles/%s_%s_ncu_summary.md" % (rnd, tag), "dram_bytes": traffic},
           open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
 print("\n".join(out[:60]))
