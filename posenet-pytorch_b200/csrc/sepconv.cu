@@ -56,7 +56,8 @@ struct SepGeom {
     int kblocks;
     int half, cbox;                       // K <= 32: two pixel columns per warp (16 lanes each), 32-channel patch box
     int cl;                               // CTAs per cluster (1, 2, 4): each owns 256 output channels and 1 / cl of the k-blocks
-    int exp;                              // PN_SEP_EXP build only: experiment flags (1 no dw math, 2 no epilogue work, 4 no MMA, 8 no W loads)
+    int exp;                              // PN_SEP_EXP build only: experiment flags (1 no dw math, 2 no (staged) epilogue work, 4 no MMA, 8 no W loads,
+                                          // 16 direct epilogue without stores, 32 no patch loads, 64 no weight loads / segments, 128 no proxy fence)
     unsigned epi_sleep_ns;                // sleep between the epilogue's polls of its accumulator barrier (PN_SEP_EPI_SLEEP, default 200)
     int p_stages, w_stages, a_stages, stg_bufs;
     unsigned patch_stage_bytes, patch_box_bytes, wgt_off, w_stage_bytes;
@@ -154,6 +155,8 @@ template <int S, int D, bool HALF> struct SepDwCfg {
 #ifdef PN_SEP_TRACE
 __device__ long long *g_sep_trace = nullptr;
 __device__ int g_sep_trace_cap = 0;
+#endif
+#if defined(PN_SEP_TRACE) && !defined(PN_SEP_PHASES)
 #define SEP_TRACE(role, idx, what)                                                                               \
     do {                                                                                                         \
         if (blockIdx.x == 0 && g_sep_trace && (idx) < g_sep_trace_cap)                                           \
@@ -161,6 +164,18 @@ __device__ int g_sep_trace_cap = 0;
     } while (0)
 #else
 #define SEP_TRACE(role, idx, what) do { } while (0)
+#endif
+
+// Phase timers of the depthwise warps (debug build: -DPN_SEP_TRACE -DPN_SEP_PHASES, tools/phases_sep.py): cycle sums per phase kept
+// in registers (a clock read costs a few cycles, nothing goes to memory until the kernel ends), written by block 0 into the
+// trace buffer, one row of 8 per depthwise warp: [wait A, wait patch, weights + table, window preload, rows, patch arrive,
+// fence + A arrive, between items].
+#ifdef PN_SEP_PHASES
+#define SEP_PH_DECL long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ph_t = clock64()
+#define SEP_PH(i) do { const long long ph_n = clock64(); ph_acc[i] += ph_n - ph_t; ph_t = ph_n; } while (0)
+#else
+#define SEP_PH_DECL do { } while (0)
+#define SEP_PH(i) do { } while (0)
 #endif
 
 template <int S, int D, bool HALF, int CL>
@@ -288,11 +303,17 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     if (mbar_test(bar(SepBars::patch_empty, ps), pph ^ 1)) {
                         const uint32_t full = bar(SepBars::patch_full, ps);
                         SEP_TRACE(3, tr_p, 0);
+#ifdef PN_SEP_EXP
+                        if (g.exp & 32) mbar_arrive(full); else {                          // experiment: no patch / weight loads
+#endif
                         mbar_expect_tx(full, g.patch_box_bytes + SEP_WGT_BYTES);
                         tma_load_4d(p_addr(ps), &tmap_x, full, p_kb * CB, p_tx * g.tw * S - g.pad,
                                     (p_ty * g.th + p_sub * g.ths) * S - g.pad, p_img);
                         tma_load_2d(p_addr(ps) + g.wgt_off, &tmap_dww, full, p_kb * CB, 0);
                         tma_load_2d(p_addr(ps) + g.wgt_off + 9 * 64 * 4, &tmap_dwb, full, p_kb * CB, 0);
+#ifdef PN_SEP_EXP
+                        }
+#endif
                         SEP_TRACE(3, tr_p, 1);
                         ++tr_p;
                         if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
@@ -555,19 +576,27 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         (void)tr_d;
         const bool tracer = (warp == SEP_FIRST_DW_WARP && lane == 0);
         (void)tracer;
+        SEP_PH_DECL;
         for (long long tile = tile_first; tile < g.tiles; tile += tile_step) {
           for (int kb = rank; kb < g.kblocks; kb += CL) {
+            SEP_PH(7);
             if (tracer) SEP_TRACE(0, tr_d, 0);
             mbar_wait(bar(SepBars::a_empty, as), aph ^ 1);            // the MMAs that read this A stage have retired
             if (tracer) SEP_TRACE(0, tr_d, 1);
+            SEP_PH(0);
             const uint32_t a_stage = a_addr(as);
             for (int sub = 0; sub < g.subs; ++sub) {
               mbar_wait(bar(SepBars::patch_full, ps), pph);
               if (tracer && sub == 0) SEP_TRACE(0, tr_d, 2);
+              SEP_PH(1);
               const uint32_t stage = p_addr(ps);
               float2 wk[9], bias2;
               bool have_w = false;
-              for (int seg = rot; seg < g.segs_per_sub; seg += SEP_DW_WARPS) {
+              for (int seg = rot; seg < g.segs_per_sub
+#ifdef PN_SEP_EXP
+                   && !(g.exp & 64)                                   // experiment: no weight / table loads, no segments
+#endif
+                   ; seg += SEP_DW_WARPS) {
                 if (!have_w) {
                     const uint32_t wsm = stage + g.wgt_off + (uint32_t)cp * 8u;
 #pragma unroll
@@ -579,6 +608,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 const int s_col = (int)(tab & 0xffu), s_r0 = (int)((tab >> 8) & 0xffu), s_n = (int)(tab >> 16);
                 const int orow0 = sub * g.ths + s_r0;
                 const int nrows = min(s_n, (g.th - orow0 + RSTEP - 1) / RSTEP);     // rows of this segment inside the tile
+                SEP_PH(2);
                 if (nrows > 0
 #ifdef PN_SEP_EXP
                     && !(g.exp & 1)
@@ -606,6 +636,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                 for (int c = 0; c < NCOLS; ++c) nxt[n][c] = lds_u32(src + (uint32_t)(PRE + n) * rowb + (uint32_t)c * PIX);
                         }
                     }
+                    SEP_PH(3);
     #pragma unroll 1
                     for (int t0 = 0; t0 < nrows; t0 += NR) {
     #pragma unroll
@@ -665,20 +696,30 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         }
                     }
                 }
+                SEP_PH(4);
               }   // segments of this item
               __syncwarp();
               if (lane == 0) mbar_arrive(bar(SepBars::patch_empty, ps));   // this warp no longer reads the patch
+              SEP_PH(5);
               if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
               if (++rot == SEP_DW_WARPS) rot = 0;
             }
+#ifdef PN_SEP_EXP
+            if (!(g.exp & 128))                                       // experiment: no generic -> async proxy fence
+#endif
             fence_async_smem();                                       // A-tile writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(SepBars::a_full, as));
+            SEP_PH(6);
             if (tracer) { SEP_TRACE(0, tr_d, 3); ++tr_d; }
             as += CL;
             if (as >= g.a_stages) { as -= g.a_stages; aph ^= 1; }
           }
         }
+#ifdef PN_SEP_PHASES
+        if (blockIdx.x == 0 && lane == 0 && g_sep_trace && warp - SEP_FIRST_DW_WARP < g_sep_trace_cap)
+            for (int i = 0; i < 8; ++i) g_sep_trace[(warp - SEP_FIRST_DW_WARP) * 8 + i] = ph_acc[i];
+#endif
     }
 
 
