@@ -56,6 +56,7 @@ struct SepGeom {
     int kblocks;
     int half, cbox;                       // K <= 32: two pixel columns per warp (16 lanes each), 32-channel patch box
     int cl;                               // CTAs per cluster (1, 2, 4): each owns 256 output channels and 1 / cl of the k-blocks
+    int teams;                            // depthwise warp teams (1, 2): a team owns whole items, the teams work on alternate items
     int exp;                              // PN_SEP_EXP build only: experiment flags (1 no dw math, 2 no (staged) epilogue work, 4 no MMA, 8 no W loads,
                                           // 16 direct epilogue without stores, 32 no patch loads, 64 no weight loads / segments, 128 no proxy fence)
     unsigned epi_sleep_ns;                // sleep between the epilogue's polls of its accumulator barrier (PN_SEP_EPI_SLEEP, default 200)
@@ -215,7 +216,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         tma_prefetch_desc(&tmap_y);
         for (int s = 0; s < g.p_stages; ++s) {
             mbar_init(bar(SepBars::patch_full, s), 1);
-            mbar_init(bar(SepBars::patch_empty, s), SEP_DW_WARPS);
+            mbar_init(bar(SepBars::patch_empty, s), SEP_DW_WARPS / g.teams);
         }
         for (int s = 0; s < g.w_stages; ++s) {
             mbar_init(bar(SepBars::w_full, s), 1);
@@ -223,7 +224,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
         for (int s = 0; s < g.a_stages; ++s) {
             // a stage produced by a peer is filled by its bulk copy (one expect_tx arrival + the bytes)
-            mbar_init(bar(SepBars::a_full, s), (!CLUSTER || s % CL == rank) ? SEP_DW_WARPS : 1);
+            mbar_init(bar(SepBars::a_full, s), (!CLUSTER || s % CL == rank) ? SEP_DW_WARPS / g.teams : 1);
             mbar_init(bar(SepBars::a_empty, s), CL);            // every CTA's MMAs have read the stage (multicast commits)
         }
         for (int s = 0; s < 2; ++s) {
@@ -570,22 +571,38 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         // a depthwise warp's time at one ~2000-cycle segment per warp and item (ncu source view: `branch_resolving` and
         // `short_scoreboard` on the grab, 6 % of the kernel on four shapes).  A warp without work in an item moves straight on
         // to the next one while the others finish.
-        int ps = 0, as = rank, tr_d = 0;                                 // cluster: this CTA fills the A stages s % CL == rank
+        //
+        // Teams (g.teams == 2): the hand-off protocol of an item -- two mbarrier probes, the proxy fence, two arrives, the weight
+        // loads: ~1.5k cycles of fixed round trips through the shared-memory unit against ~1.4k cycles of stencil work per
+        // warp (tools/phases_sep.py) -- is paid by every warp that takes part in the item.  So the ten warps form two teams of
+        // five that own WHOLE items, even items one team, odd items the other: a warp does two segments per hand-off instead
+        // of one, the barriers count five arrivals, and two items are in flight at once (the rings are deep enough where
+        // sep_geometry turns this on).  Every warp still walks all items in order so that its stage cursors and parities
+        // follow the rings; it just steps over the other team's items.
+        const int n_teams = g.teams, team_warps = SEP_DW_WARPS / n_teams, team = (warp - SEP_FIRST_DW_WARP) / team_warps;
+        const int n_subs = g.subs, n_pst = g.p_stages, n_ast = g.a_stages, n_kb = g.kblocks;
+        const int item_step = CLUSTER ? CL : n_teams;                    // items (k-blocks in tile order) between two of this warp's
+        int tr_d = 0;
+        // cursors of this warp's first item: item `rank` of a cluster CTA, item `team` otherwise (its stages follow the first
+        // team's: both rings are deeper than one item)
+        int ps = CLUSTER ? 0 : team * n_subs, as = CLUSTER ? rank : team, kb = CLUSTER ? rank : team;
         uint32_t pph = 0, aph = 0;
-        int rot = warp - SEP_FIRST_DW_WARP;                              // this warp's first segment in the current item
+        int rot = (warp - SEP_FIRST_DW_WARP) - team * team_warps;        // this warp's first segment in the current item
+        long long tile = tile_first;
+        while (!CLUSTER && kb >= n_kb) { kb -= n_kb; tile += tile_step; }    // (single-k-block tiles: the second team starts one tile on)
         (void)tr_d;
         const bool tracer = (warp == SEP_FIRST_DW_WARP && lane == 0);
         (void)tracer;
         SEP_PH_DECL;
-        for (long long tile = tile_first; tile < g.tiles; tile += tile_step) {
-          for (int kb = rank; kb < g.kblocks; kb += CL) {
+        while (tile < g.tiles) {
+          {
             SEP_PH(7);
             if (tracer) SEP_TRACE(0, tr_d, 0);
             mbar_wait(bar(SepBars::a_empty, as), aph ^ 1);            // the MMAs that read this A stage have retired
             if (tracer) SEP_TRACE(0, tr_d, 1);
             SEP_PH(0);
             const uint32_t a_stage = a_addr(as);
-            for (int sub = 0; sub < g.subs; ++sub) {
+            for (int sub = 0; sub < n_subs; ++sub) {
               mbar_wait(bar(SepBars::patch_full, ps), pph);
               if (tracer && sub == 0) SEP_TRACE(0, tr_d, 2);
               SEP_PH(1);
@@ -596,7 +613,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #ifdef PN_SEP_EXP
                    && !(g.exp & 64)                                   // experiment: no weight / table loads, no segments
 #endif
-                   ; seg += SEP_DW_WARPS) {
+                   ; seg += team_warps) {
                 if (!have_w) {
                     const uint32_t wsm = stage + g.wgt_off + (uint32_t)cp * 8u;
 #pragma unroll
@@ -701,8 +718,8 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               __syncwarp();
               if (lane == 0) mbar_arrive(bar(SepBars::patch_empty, ps));   // this warp no longer reads the patch
               SEP_PH(5);
-              if (++ps == g.p_stages) { ps = 0; pph ^= 1; }
-              if (++rot == SEP_DW_WARPS) rot = 0;
+              if (++ps == n_pst) { ps = 0; pph ^= 1; }
+              if (++rot == team_warps) rot = 0;
             }
 #ifdef PN_SEP_EXP
             if (!(g.exp & 128))                                       // experiment: no generic -> async proxy fence
@@ -712,8 +729,16 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
             if (lane == 0) mbar_arrive(bar(SepBars::a_full, as));
             SEP_PH(6);
             if (tracer) { SEP_TRACE(0, tr_d, 3); ++tr_d; }
-            as += CL;
-            if (as >= g.a_stages) { as -= g.a_stages; aph ^= 1; }
+            // on to this warp's next item: over the other team's patch stages and A stage, item_step k-blocks ahead
+            if (n_teams == 2) {
+                ps += n_subs;
+                if (ps >= n_pst) { ps -= n_pst; pph ^= 1; }
+            }
+            as += item_step;
+            if (as >= n_ast) { as -= n_ast; aph ^= 1; }
+            kb += item_step;
+            if (CLUSTER) { if (kb >= n_kb) { kb = rank; tile += tile_step; } }
+            else while (kb >= n_kb) { kb -= n_kb; tile += tile_step; }
           }
         }
 #ifdef PN_SEP_PHASES
@@ -953,6 +978,14 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
 #ifdef PN_SEP_EXP
     if (const char *e = getenv("PN_SEP_EXP")) g.exp = atoi(e);
 #endif
+    // Depthwise warp teams (see the kernel): two items in flight need a patch stage per team and sub-tile plus one ahead, an A
+    // stage per team plus the one the MMAs read, and -- for the parity of a barrier a team returns to -- a patch ring at least as
+    // deep as the A ring (an item whose A stage is free has had the patch stage's previous user consumed).  PN_SEP_TEAMS=1 / 2.
+    g.teams = (g.cl == 1 && SEP_DW_WARPS % 2 == 0 && g.p_stages >= 2 * g.subs + 1 && g.a_stages >= 3 && g.p_stages >= g.a_stages) ? 2 : 1;
+    if (const char *e = getenv("PN_SEP_TEAMS")) {
+        const int v = atoi(e);
+        if (v == 1 || (v == 2 && g.cl == 1 && SEP_DW_WARPS % 2 == 0 && g.p_stages >= 2 * g.subs && g.a_stages >= 2 && g.p_stages >= g.a_stages)) g.teams = v;
+    }
     g.epi_sleep_ns = 200;
     if (const char *e = getenv("PN_SEP_EPI_SLEEP")) g.epi_sleep_ns = (unsigned)atoi(e);
     static_assert(SepBars::total <= 640, "barrier block exceeds its reserve");
@@ -1096,8 +1129,8 @@ void sep_describe(const SepOp *op, char *out, size_t cap) {
     }
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    snprintf(out, cap, "%s%stile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d stages p%d w%d a%d stg%d smem %d tiles %lld",
-             g.half ? "half " : "", g.cl == 2 ? "cluster2 " : g.cl == 4 ? "cluster4 " : "", g.th, g.tw, g.subs, g.thi, g.twi, g.segs_per_sub, g.seg_rows, g.n_tile, g.n_halves, g.n_half, g.n_tiles, g.kblocks, g.p_stages,
+    snprintf(out, cap, "%s%stile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d teams %d stages p%d w%d a%d stg%d smem %d tiles %lld",
+             g.half ? "half " : "", g.cl == 2 ? "cluster2 " : g.cl == 4 ? "cluster4 " : "", g.th, g.tw, g.subs, g.thi, g.twi, g.segs_per_sub, g.seg_rows, g.n_tile, g.n_halves, g.n_half, g.n_tiles, g.kblocks, g.teams, g.p_stages,
              g.w_stages, g.a_stages, g.stg_bufs, op->smem_bytes, g.tiles);
 }
 
