@@ -45,6 +45,7 @@ constexpr int SEP_STG_BYTES = 128 * 128;                               // one 12
 constexpr int SEP_MAX_P = 6, SEP_MAX_W = 6;
 constexpr int SEP_WGT_BYTES = 9 * 64 * 4 + 64 * 4;                     // dw weights [9][64] + bias [64] fp32
 constexpr int SEP_SMEM_MAX = 232448;
+constexpr int SEP_DWW_KB_BYTES = 10 * 64 * 4;                          // resident depthwise weights + bias of one k-block
 
 struct SepGeom {
     int k, nc, ho, wo, pad;
@@ -56,6 +57,9 @@ struct SepGeom {
     int kblocks;
     int half, cbox;                       // K <= 32: two pixel columns per warp (16 lanes each), 32-channel patch box
     int cl;                               // CTAs per cluster (1, 2, 4): each owns 256 output channels and 1 / cl of the k-blocks
+    int dww_res;                          // depthwise weights resident in shared memory (off_dww) instead of behind every patch stage
+    int w_res;                            // pointwise weights resident: W stage = k-block * n_halves + column block, loaded once
+    unsigned off_dww;                     // resident depthwise weights [kblocks][10][64] fp32 (SEP_LEAN & 4)
     int teams;                            // depthwise warp teams (1, 2): a team owns whole items, the teams work on alternate items
     int exp;                              // PN_SEP_EXP build only: experiment flags (1 no dw math, 2 no (staged) epilogue work, 4 no MMA, 8 no W loads,
                                           // 16 direct epilogue without stores, 32 no patch loads, 64 no weight loads / segments, 128 no proxy fence)
@@ -184,13 +188,14 @@ __global__ void __launch_bounds__(SEP_THREADS, 1)
 sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dww,
                const __grid_constant__ CUtensorMap tmap_dwb, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_y, const float *__restrict__ pw_bias, __nv_bfloat16 *__restrict__ y,
-               const SepGeom g) {
+               const float *__restrict__ dw_w, const float *__restrict__ dw_b, const SepGeom g) {
     constexpr int CB = 64;                                  // channels per k-block (ragged K is zero-filled by TMA)
     // CL > 1: a cluster of CL CTAs shares every 128-pixel tile.  CTA `rank` owns output channels [rank * 256, +256) --
     // its own pointwise weights, accumulators (double-buffered) and epilogue -- and computes the depthwise result of the
     // k-blocks kb % CL == rank only; the finished A stage is pushed into the peers' shared memory with one DSMEM bulk copy
     // each (completing on their a_full barrier), so the depthwise work, which bounds these blocks, is done once per tile.
     constexpr bool CLUSTER = CL > 1;
+    const bool DWW_RES = !CLUSTER && g.dww_res != 0;         // depthwise weights resident in shared memory (per block: sep_geometry)
     const int rank = CLUSTER ? (int)cluster_rank() : 0;
     const long long tile_first = CLUSTER ? blockIdx.x / CL : blockIdx.x, tile_step = CLUSTER ? gridDim.x / CL : gridDim.x;
     const int col_base = CLUSTER ? rank * g.n_tile : 0;      // first output channel of this CTA
@@ -247,6 +252,14 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         float *sbias = reinterpret_cast<float *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_bias);
         const int ncp = g.n_tiles * g.panels * 64;                // padded so that ragged panels read zeros
         for (int i = threadIdx.x; i < ncp; i += SEP_THREADS) sbias[i] = col_base + i < g.nc ? __ldg(pw_bias + col_base + i) : 0.f;
+    }
+    if (DWW_RES) {   // depthwise weights [9, K] + bias [K] -> [k-block][tap | bias][64] fp32, ragged K zero-filled (never written by the
+                     // preceding kernel, so this may run before griddepcontrol.wait like the bias above)
+        float *sw = reinterpret_cast<float *>(sep_smem_raw + (base - smem_u32(sep_smem_raw)) + g.off_dww);
+        for (int i = threadIdx.x; i < g.kblocks * 640; i += SEP_THREADS) {
+            const int kbi = i / 640, r = i - kbi * 640, t = r >> 6, ch = kbi * 64 + (r & 63);
+            sw[i] = ch < g.k ? (t < 9 ? __ldg(dw_w + (size_t)t * g.k + ch) : __ldg(dw_b + ch)) : 0.f;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -307,11 +320,13 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #ifdef PN_SEP_EXP
                         if (g.exp & 32) mbar_arrive(full); else {                          // experiment: no patch / weight loads
 #endif
-                        mbar_expect_tx(full, g.patch_box_bytes + SEP_WGT_BYTES);
+                        mbar_expect_tx(full, g.patch_box_bytes + (DWW_RES ? 0u : (uint32_t)SEP_WGT_BYTES));
                         tma_load_4d(p_addr(ps), &tmap_x, full, p_kb * CB, p_tx * g.tw * S - g.pad,
                                     (p_ty * g.th + p_sub * g.ths) * S - g.pad, p_img);
-                        tma_load_2d(p_addr(ps) + g.wgt_off, &tmap_dww, full, p_kb * CB, 0);
-                        tma_load_2d(p_addr(ps) + g.wgt_off + 9 * 64 * 4, &tmap_dwb, full, p_kb * CB, 0);
+                        if (!DWW_RES) {
+                            tma_load_2d(p_addr(ps) + g.wgt_off, &tmap_dww, full, p_kb * CB, 0);
+                            tma_load_2d(p_addr(ps) + g.wgt_off + 9 * 64 * 4, &tmap_dwb, full, p_kb * CB, 0);
+                        }
 #ifdef PN_SEP_EXP
                         }
 #endif
@@ -340,7 +355,10 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                         if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
                         if (++w_hf == g.n_halves) {
                             w_hf = 0;
-                            if (++w_kb == g.kblocks) { w_kb = 0; w_tile += tile_step; w_new = true; }
+                            if (++w_kb == g.kblocks) {
+                                w_kb = 0; w_tile += tile_step; w_new = true;
+                                if (g.w_res) w_tile = g.tiles;          // resident W: every (k-block, column block) has its own stage, loaded once
+                            }
                         }
                         progress = true;
                     }
@@ -374,7 +392,11 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                     const int rem_k = g.k - kb * CB;                             // ragged K tail: only the k16 steps that hold channels
                     const int ksteps = rem_k >= CB ? CB / 16 : (rem_k + 15) / 16;
                     for (int hf = 0; hf < g.n_halves; ++hf) {
-                        mbar_wait(bar(SepBars::w_full, ws), wph);
+                        if (g.w_res) {                                // resident W: stage = (k-block, column block); landed once, in phase 0
+                            ws = kb * g.n_halves + hf;
+                            if (tile == tile_first) mbar_wait(bar(SepBars::w_full, ws), 0);
+                        } else
+                            mbar_wait(bar(SepBars::w_full, ws), wph);
                         tc_fence_after();
                         const uint32_t sb = w_addr(ws);
 #pragma unroll
@@ -386,8 +408,10 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                                 )
                                 tc_mma_bf16(d_tmem + (uint32_t)(hf * g.n_half), sep_smem_desc(sa + k * 32), sep_smem_desc(sb + k * 32), idesc,
                                             (uint32_t)((kb | k) != 0));
-                        tc_commit(bar(SepBars::w_empty, ws));
-                        if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
+                        if (!g.w_res) {
+                            tc_commit(bar(SepBars::w_empty, ws));
+                            if (++ws == g.w_stages) { ws = 0; wph ^= 1; }
+                        }
                     }
                     if (CLUSTER) tc_commit_multicast(bar(SepBars::a_empty, as), (uint16_t)((1u << CL) - 1u));
                     else tc_commit(bar(SepBars::a_empty, as));
@@ -594,10 +618,22 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const bool tracer = (warp == SEP_FIRST_DW_WARP && lane == 0);
         (void)tracer;
         SEP_PH_DECL;
+        float2 wk[9], bias2;                                          // this lane's 9 taps + bias of its channel pair
+        int wk_kb = -1;                                               // DWW_RES: k-block whose weights the registers hold
+        (void)wk_kb;
         while (tile < g.tiles) {
           {
             SEP_PH(7);
             if (tracer) SEP_TRACE(0, tr_d, 0);
+            if (DWW_RES && kb != wk_kb) {
+                // resident weights: requested BEFORE the barrier probe so that the two shared-memory round trips overlap; a warp
+                // that keeps its k-block from item to item (k-blocks == teams) loads them once per kernel
+                const uint32_t wsm = base + g.off_dww + (uint32_t)kb * (uint32_t)SEP_DWW_KB_BYTES + (uint32_t)cp * 8u;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) wk[t] = lds_f2(wsm + (uint32_t)t * 256u);
+                bias2 = lds_f2(wsm + 9 * 256u);
+                wk_kb = kb;
+            }
             mbar_wait(bar(SepBars::a_empty, as), aph ^ 1);            // the MMAs that read this A stage have retired
             if (tracer) SEP_TRACE(0, tr_d, 1);
             SEP_PH(0);
@@ -607,8 +643,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               if (tracer && sub == 0) SEP_TRACE(0, tr_d, 2);
               SEP_PH(1);
               const uint32_t stage = p_addr(ps);
-              float2 wk[9], bias2;
-              bool have_w = false;
+              bool have_w = DWW_RES;
               for (int seg = rot; seg < g.segs_per_sub
 #ifdef PN_SEP_EXP
                    && !(g.exp & 64)                                   // experiment: no weight / table loads, no segments
@@ -758,6 +793,10 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
+struct SepTuned { int k, nc, stride, dil, ho, wo, th, tw, subs, p, w, a, stg, teams; };
+static const SepTuned SEP_TUNED[] = {
+#include "sep_tuned.inc"
+    {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
 static int next_pow2_cols(int c) {
     int p = 32;
     while (p < c) p <<= 1;
@@ -844,12 +883,37 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     PN_CHECK_ARG(g.tmem_cols <= 512 && g.panels * 64 <= 512, "pn_sepconv_block: TMEM budget exceeded");
     g.w_stage_bytes = (unsigned)g.n_half * 128u;
 
+    // ---- resident weights (single-CTA kernel).  Depthwise: [k-block][9 taps + bias][64] fp32 loaded once per kernel instead of
+    // travelling behind every patch stage (K <= 256; beyond that 15-20 KB resident would cost a patch stage); a warp fetches its
+    // registers from there while it probes the patch barrier.  Pointwise: where every (k-block, column block) fits a stage of its
+    // own (<= 80 KB in all) the W ring is loaded once and never again -- per tile that is as much L2 -> shared-memory traffic as
+    // the patches themselves, and the MMA thread loses a wait and a commit per k-block.  PN_SEP_DWWRES=0 / PN_SEP_WRES=0 switch
+    // either off (A/B).  Measured on B200 (same tiles): 128 -> 256 s2 @129^2 100.0 -> 96.2 us, 192 -> 192 @33^2 x512 135.7 -> 134.0,
+    // 128 -> 256 @91x161 114.8 -> 110.0; the freed stages matter more where they buy a deeper ring or a larger tile.
+    const char *e_dww = getenv("PN_SEP_DWWRES"), *e_wres = getenv("PN_SEP_WRES");
+    const bool dww_res = !(e_dww && e_dww[0] == '0') && g.cl == 1 && g.kblocks <= 4;
+    const int wgt_stage = dww_res ? 0 : SEP_WGT_BYTES;             // depthwise weight bytes behind each patch stage
+    const int dww_bytes = dww_res ? g.kblocks * SEP_DWW_KB_BYTES : 0;
+    g.dww_res = dww_res ? 1 : 0;
+    g.w_res = (!(e_wres && e_wres[0] == '0') && g.cl == 1 && g.n_tiles == 1 && g.kblocks * g.n_halves <= SEP_MAX_W &&
+               (long long)g.kblocks * g.n_halves * g.w_stage_bytes <= 80 * 1024) ? 1 : 0;
     // ---- tile search: fewest (tiles x per-tile cost); one strip per depthwise thread group per sub-tile
-    const int min_w = g.n_halves >= 2 ? 3 : 2;                     // default W ring entries (column blocks of a k-block, plus one ahead)
+    const int min_w = g.w_res ? g.kblocks * g.n_halves : g.n_halves >= 2 ? 3 : 2;   // default W ring entries (column blocks of a k-block, plus one ahead)
     const int min_a = g.cl > 2 ? g.cl : 2;                         // cluster: the A ring is a multiple of the cluster size
-    const int fixed = min_a * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 640 + 4224;   // minimum non-patch smem
+    const int fixed = min_a * SEP_A_BYTES + SEP_STG_BYTES + min_w * (int)g.w_stage_bytes + 1024 + 640 + 4224 + dww_bytes;   // minimum non-patch smem
     double best = 1e300;
-    int f_th = 0, f_tw = 0, f_subs = 0;                            // tuning / debugging aid: PN_SEP_TILE="th,tw,subs"
+    // Measured choices first (sep_tuned.inc: tools/tune_sep.py timed the tile shapes / ring depths of the blocks of the reference's
+    // standard resolutions on a B200; the cost model below ranks them poorly -- up to 25 % between tiles it scores alike), the
+    // model for every other shape.  PN_SEP_TUNED=0 ignores the table; PN_SEP_TILE="th,tw,subs" / PN_SEP_STAGES / PN_SEP_TEAMS force.
+    const SepTuned *tuned = nullptr;
+    {
+        const char *e = getenv("PN_SEP_TUNED");
+        if (!(e && e[0] == '0') && g.cl == 1)
+            for (const SepTuned &t : SEP_TUNED)
+                if (t.k == k && t.nc == nc && t.stride == stride && t.dil == dil && t.ho == g.ho && t.wo == g.wo) { tuned = &t; break; }
+    }
+    int f_th = 0, f_tw = 0, f_subs = 0;
+    if (tuned) { f_th = tuned->th; f_tw = tuned->tw; f_subs = tuned->subs; }
     if (const char *force = getenv("PN_SEP_TILE"))
         if (sscanf(force, "%d,%d,%d", &f_th, &f_tw, &f_subs) != 3) f_th = f_tw = f_subs = 0;
     for (int th = 1; th <= 64; ++th) {
@@ -864,7 +928,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
                 const int twi = (tw - 1) * stride + 2 * dil + 1;
                 if (thi > 256 || twi > 256) continue;
                 const long long box = (long long)thi * twi * g.cbox * 2;
-                const long long stage = ((box + 127) & ~127ll) + SEP_WGT_BYTES;
+                const long long stage = ((box + 127) & ~127ll) + wgt_stage;
                 // segments: 4-pixel (8 when half) column strips x seg_rows rows.  They are handed out dynamically across
                 // the items in flight (A stages x segments >= 16 keeps the 10 warps busy); ~4-5 rows amortise the window preload
                 const int spr = ceil_div(tw, sw);
@@ -895,7 +959,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
                 double per_kb = dwc > mma ? dwc : mma;
                 if (fill > per_kb) per_kb = fill;
                 per_kb += 0.25 * fill;                                     // halo re-reads load the L2 -> SM path
-                if (pst < 3 * subs) per_kb *= 1.25;                        // shallow prefetch
+                if (pst < 3 * subs) per_kb *= 1.08;                        // shallow prefetch (measured: two stages of a compact tile beat three of a thin one)
                 // per tile: pipeline hand-off + an epilogue whose work is 128 rows x n_tile whatever the tile covers
                 const double cost = (double)tiles * (g.kblocks * per_kb + 400.0 + 200.0 * g.panels);
                 if (cost < best) {
@@ -928,7 +992,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     g.tiles = (long long)n * g.tiles_x * g.tiles_y * g.n_tiles;       // cluster: m tiles (one cluster covers all columns)
     // ---- shared-memory carve-up: W ring, A ring, output staging panels, patch ring, bias, barriers
     const long long bias_bytes = ((long long)g.n_tiles * g.panels * 64 * 4 + 127) & ~127ll;
-    const long long avail = SEP_SMEM_MAX - 1024 - 640 - bias_bytes;   // alignment slack, barrier block (SepBars::total)
+    const long long avail = SEP_SMEM_MAX - 1024 - 640 - bias_bytes - dww_bytes;   // alignment slack, barrier block (SepBars::total)
     auto fits = [&](int pst, int wst, int ast, int stg) {
         return (long long)wst * g.w_stage_bytes + (long long)ast * SEP_A_BYTES + (long long)stg * SEP_STG_BYTES +
                    (long long)pst * g.patch_stage_bytes <= avail;
@@ -947,7 +1011,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
         for (int ast = SEP_MAX_A; ast >= 2; --ast) {
             if (g.cl == 1 && ast > max_a1) continue;
             if (g.cl > 1 && ast % g.cl != 0) continue;
-            for (int wst = SEP_MAX_W; wst >= min_w; --wst)
+            for (int wst = g.w_res ? min_w : SEP_MAX_W; wst >= min_w; --wst)
                 for (int pst = SEP_MAX_P; pst >= 2 && pst >= g.subs + 1; --pst) {
                     if (!fits(pst, wst, ast, stg)) continue;
                     // (a cluster CTA consumes patches for 1 / cl of the k-blocks only: two stages cover it, A stages matter more)
@@ -968,9 +1032,12 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     // short epilogue (two staging panels keep the TMA stores in flight) and a third A stage for the depthwise warps to
     // run ahead into -- worth more than a third patch stage (measured: 84 -> 77 us on the 512 -> 512 blocks)
     if (!direct && g.n_halves == 2 && g.subs == 1 && fits(2, min_w, 3, 2)) { g.p_stages = 2; g.w_stages = min_w; g.a_stages = 3; g.stg_bufs = 2; }
-    if (const char *force = getenv("PN_SEP_STAGES")) {              // tuning aid: "p,w,a,stg"
+    {   // ring depths: the table's (p = 0: the rule above), or forced with PN_SEP_STAGES="p,w,a,stg"
         int fp = 0, fw = 0, fa = 0, fs = 0;
-        if (sscanf(force, "%d,%d,%d,%d", &fp, &fw, &fa, &fs) == 4 && fp >= g.subs + 1 && fp <= SEP_MAX_P && fw >= 2 &&
+        bool have = false;
+        if (tuned && tuned->p > 0 && g.th == tuned->th && g.tw == tuned->tw && g.subs == tuned->subs) { fp = tuned->p; fw = tuned->w; fa = tuned->a; fs = tuned->stg; have = true; }
+        if (const char *force = getenv("PN_SEP_STAGES")) have = sscanf(force, "%d,%d,%d,%d", &fp, &fw, &fa, &fs) == 4;
+        if (have && fp >= g.subs + 1 && fp <= SEP_MAX_P && fw >= 1 &&
             fw <= SEP_MAX_W && fa >= 2 && fa <= SEP_MAX_A && fa % g.cl == 0 && fs >= 0 && fs <= 2 && fits(fp, fw, fa, fs)) {
             g.p_stages = fp; g.w_stages = fw; g.a_stages = fa; g.stg_bufs = fs;
         }
@@ -978,12 +1045,14 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
 #ifdef PN_SEP_EXP
     if (const char *e = getenv("PN_SEP_EXP")) g.exp = atoi(e);
 #endif
+    if (g.w_res && g.w_stages != g.kblocks * g.n_halves) g.w_res = 0;   // (a forced ring depth: back to the ring)
     // Depthwise warp teams (see the kernel): two items in flight need a patch stage per team and sub-tile plus one ahead, an A
     // stage per team plus the one the MMAs read, and -- for the parity of a barrier a team returns to -- a patch ring at least as
     // deep as the A ring (an item whose A stage is free has had the patch stage's previous user consumed).  PN_SEP_TEAMS=1 / 2.
     g.teams = (g.cl == 1 && SEP_DW_WARPS % 2 == 0 && g.p_stages >= 2 * g.subs + 1 && g.a_stages >= 3 && g.p_stages >= g.a_stages) ? 2 : 1;
-    if (const char *e = getenv("PN_SEP_TEAMS")) {
-        const int v = atoi(e);
+    {
+        const char *e = getenv("PN_SEP_TEAMS");
+        const int v = e ? atoi(e) : (tuned && tuned->p > 0 && g.th == tuned->th && g.tw == tuned->tw && g.subs == tuned->subs) ? tuned->teams : 0;
         if (v == 1 || (v == 2 && g.cl == 1 && SEP_DW_WARPS % 2 == 0 && g.p_stages >= 2 * g.subs && g.a_stages >= 2 && g.p_stages >= g.a_stages)) g.teams = v;
     }
     g.epi_sleep_ns = 200;
@@ -993,7 +1062,8 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     g.off_stg = g.off_a + (unsigned)g.a_stages * SEP_A_BYTES;
     g.off_patch = g.off_stg + (unsigned)g.stg_bufs * SEP_STG_BYTES;
     g.off_bias = g.off_patch + (unsigned)g.p_stages * g.patch_stage_bytes;
-    g.off_bar = g.off_bias + (unsigned)bias_bytes;
+    g.off_dww = g.off_bias + (unsigned)bias_bytes;
+    g.off_bar = g.off_dww + (unsigned)dww_bytes;
     op->smem_bytes = (int)(g.off_bar + SepBars::total + 1024);
     PN_CHECK_ARG(op->smem_bytes <= SEP_SMEM_MAX, "pn_sepconv_block: internal smem accounting error (%d)", op->smem_bytes);
     static_assert(sizeof(SepGeom) <= sizeof(op->geom), "SepOp::geom too small");
@@ -1021,6 +1091,7 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
         return septc_prepare(&op->tc, x, pw_w, n, h, wd, k, nc, dil);
     }
     op->y = y;                                                       // the direct-store epilogue writes through the plain pointer
+    op->dw_w = dw_w; op->dw_b = dw_b;                                // (resident depthwise weights are read through plain pointers too)
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
     {   // input patches: (C, W, H, N) bf16, box [cb, twi, thi, 1], no swizzle, OOB -> 0
@@ -1092,7 +1163,7 @@ static int sep_launch_t(const SepOp *op, const SepGeom &g, const float *pw_bias,
     PN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *reinterpret_cast<const CUtensorMap *>(op->tmap_x),
                                      *reinterpret_cast<const CUtensorMap *>(op->tmap_dww), *reinterpret_cast<const CUtensorMap *>(op->tmap_dwb),
                                      *reinterpret_cast<const CUtensorMap *>(op->tmap_w), *reinterpret_cast<const CUtensorMap *>(op->tmap_y),
-                                     pw_bias, reinterpret_cast<__nv_bfloat16 *>(op->y), g));
+                                     pw_bias, reinterpret_cast<__nv_bfloat16 *>(op->y), op->dw_w, op->dw_b, g));
     return PN_OK;
 }
 
@@ -1129,9 +1200,9 @@ void sep_describe(const SepOp *op, char *out, size_t cap) {
     }
     SepGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    snprintf(out, cap, "%s%stile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d teams %d stages p%d w%d a%d stg%d smem %d tiles %lld",
+    snprintf(out, cap, "%s%stile %dx%d subs %d box %dx%d segs %d x %d rows n_tile %d(%dx%d) x%d kblocks %d teams %d stages p%d w%d%s a%d stg%d smem %d tiles %lld",
              g.half ? "half " : "", g.cl == 2 ? "cluster2 " : g.cl == 4 ? "cluster4 " : "", g.th, g.tw, g.subs, g.thi, g.twi, g.segs_per_sub, g.seg_rows, g.n_tile, g.n_halves, g.n_half, g.n_tiles, g.kblocks, g.teams, g.p_stages,
-             g.w_stages, g.a_stages, g.stg_bufs, op->smem_bytes, g.tiles);
+             g.w_stages, g.w_res ? "r" : "", g.a_stages, g.stg_bufs, op->smem_bytes, g.tiles);
 }
 
 }  // namespace pn
