@@ -103,7 +103,9 @@ struct StemTcArgs {
     int n, h, w, ho, wo, stride, cout;
     long long total_px, total_bytes, total_lo16;   // pixels; bytes of the image batch; the same rounded DOWN to 16
     int span_cap;                          // bytes per span buffer (multiple of 16)
+    int seg, piece_cap;                    // segmented spans (wide images): 6 pieces of piece_cap bytes per buffer, see the kernel
 };
+constexpr int STC_PIECES = 6;              // 2 output-row segments x 3 input rows
 
 __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a) {
     extern __shared__ uint8_t stc_raw[];
@@ -119,6 +121,9 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         reinterpret_cast<volatile uint32_t *>(gen + STC_A_BYTES + STC_W_BYTES + STC_NBUF * a.span_cap + 128 + 8 * STC_NBUF + 8);
     // span base (byte offset of the ring slot's first byte in the image batch), written by thread 0 when it issues the load
     volatile long long *span_lo = reinterpret_cast<volatile long long *>(gen + STC_A_BYTES + STC_W_BYTES + STC_NBUF * a.span_cap + 128 + 32);
+    // segmented spans: byte offset of input column byte 0 of piece p's row inside ring slot s (may be negative), written by the
+    // thread that issues the piece
+    volatile int *piece_adj = reinterpret_cast<volatile int *>(gen + STC_A_BYTES + STC_W_BYTES + STC_NBUF * a.span_cap + 128 + 64);
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long row_bytes = (long long)a.w * 3;
     const long long num_tiles = (a.total_px + 127) / 128;
@@ -152,8 +157,42 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         if (size) bulk_load_1d(dst, a.img + lo16, size, bars + 8u * slot);
     };
 
+    // Segmented spans (a.seg: images at least 128 output pixels wide, where whole rows would be several times what the tile
+    // reads -- 19 KB instead of 2.3 KB per tile at 1281 x 721): a 128-pixel tile lies in at most two output rows; per output-row
+    // segment and window row ky ONE bulk copy of just the columns the segment reads (16-byte aligned outwards), issued by thread
+    // p = segment * 3 + ky with its own expect_tx, so the slot's barrier counts STC_PIECES arrivals.
+    auto issue_piece = [&](int slot, long long t, int p) {
+        const uint32_t m0 = (uint32_t)t * 128u, m1 = min(m0 + 127u, (uint32_t)a.total_px - 1u);
+        const uint32_t r0 = m0 / (uint32_t)a.wo, r1 = m1 / (uint32_t)a.wo;        // r1 <= r0 + 1 (wo >= 128)
+        const int sg = p / 3, ky = p - sg * 3;
+        const uint32_t r = r0 + (uint32_t)sg;
+        uint32_t size = 0;
+        const uint32_t bar = bars + 8u * slot;
+        if (r <= r1) {
+            const int img_i = (int)(r / (uint32_t)a.ho), oy = (int)(r - (uint32_t)img_i * (uint32_t)a.ho);
+            const int xa = sg == 0 ? (int)(m0 - r0 * (uint32_t)a.wo) : 0, xb = r == r1 ? (int)(m1 - r1 * (uint32_t)a.wo) : a.wo - 1;
+            const int iy = oy * a.stride - 1 + ky;
+            if (iy >= 0 && iy < a.h) {
+                const long long rowstart = ((long long)img_i * a.h + iy) * row_bytes;
+                const long long lo = rowstart + (long long)max(xa * a.stride - 1, 0) * 3, hi = rowstart + (long long)min(xb * a.stride + 1, a.w - 1) * 3 + 3;
+                const long long lo16 = lo & ~15ll;
+                long long end = (hi + 15) & ~15ll;
+                if (end > a.total_lo16) end = a.total_lo16;
+                size = end > lo16 ? (uint32_t)(end - lo16) : 0u;
+                const uint32_t dst = sSpan + (uint32_t)slot * (uint32_t)a.span_cap + (uint32_t)p * (uint32_t)a.piece_cap;
+                piece_adj[slot * STC_PIECES + p] = p * a.piece_cap - (int)(lo16 - rowstart);
+                for (long long b = max(a.total_lo16, lo16); b < hi; ++b)     // (the batch's last < 16 bytes, see issue_span)
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst + (uint32_t)(b - lo16)), "r"((uint32_t)a.img[b]) : "memory");
+                mbar_expect_tx(bar, size);
+                if (size) bulk_load_1d(dst, a.img + lo16, size, bar);
+                return;
+            }
+        }
+        mbar_arrive(bar);                                          // nothing to fetch for this piece
+    };
+
     if (tid == 0) {
-        for (int i = 0; i < STC_NBUF; ++i) mbar_init(bars + 8u * i, 1);
+        for (int i = 0; i < STC_NBUF; ++i) mbar_init(bars + 8u * i, a.seg ? STC_PIECES : 1);
         mbar_init(mma_bar, 1);
         mbar_fence_init();
     }
@@ -193,11 +232,11 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
     long long tile = blockIdx.x;
-    if (tid == 0) {
+    if (tid < (a.seg ? STC_PIECES : 1)) {
         for (int i = 0; i < STC_NBUF - 1; ++i) {
             const long long t = tile + (long long)i * gridDim.x;
             if (t >= num_tiles) break;
-            issue_span(i, t);
+            if (a.seg) issue_piece(i, t, tid); else issue_span(i, t);
         }
     }
     uint32_t span_phase = 0, mma_phase = 0;             // bit b of span_phase = parity of ring slot b
@@ -231,13 +270,22 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         // interior pixels (all 27 taps inside the image) take a copy of the loop without the padding selects
         const bool interior_px = live && ix0 >= 0 && ix0 + 2 < a.w && iy0 >= 0 && iy0 + 2 < a.h;
         // byte offset of the window's first row / first used column inside the span (32-bit: spans are < 200 KB)
-        const int rowoff0 = (int)(((long long)img_i * a.h + iy0) * row_bytes - lo16) + (ix0 + lead) * 3;
+        int rowoff[3];
+        if (a.seg) {
+            const int sg = live && (uint32_t)m / (uint32_t)a.wo != (uint32_t)(tile * 128) / (uint32_t)a.wo ? 1 : 0;   // second output row of the tile
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) rowoff[ky] = piece_adj[buf * STC_PIECES + sg * 3 + ky] + (ix0 + lead) * 3;
+        } else {
+            const int rowoff0 = (int)(((long long)img_i * a.h + iy0) * row_bytes - lo16) + (ix0 + lead) * 3;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) rowoff[ky] = rowoff0 + ky * (int)row_bytes;
+        }
         auto im2col = [&](const bool interior) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = oy * a.stride - 1 + ky;
             const bool row_ok = live && iy >= 0 && iy < a.h;
-            const uint32_t b0 = row_ok ? (uint32_t)(rowoff0 + ky * (int)row_bytes) : 0u;
+            const uint32_t b0 = row_ok ? (uint32_t)rowoff[ky] : 0u;
             const uint32_t a0 = sp + (b0 & ~3u), sh = (b0 & 3u) * 8u;
             const uint32_t w0 = lds_u32s(a0), w1 = lds_u32s(a0 + 4), w2 = lds_u32s(a0 + 8);
             uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = w2 >> sh;
@@ -273,16 +321,18 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
         fence_async_smem();
         tc_fence_before();
         __syncthreads();                                         // A complete; the previous tile's TMEM reads are done
-        if (tid == 0) {
-            const long long next = tile + (long long)(STC_NBUF - 1) * gridDim.x;
-            if (next < num_tiles) {                              // refill the slot the previous tile has just released
-                const int nb = (buf + STC_NBUF - 1) % STC_NBUF;
-                issue_span(nb, next);
-            }
+        if (tid == 0) {                                          // the MMAs first: every thread of the CTA waits for them ...
             tc_fence_after();
             tc_mma_bf16(tmem, stc_smem_desc(sA), stc_smem_desc(sW), IDESC, 0u);
             tc_mma_bf16(tmem, stc_smem_desc(sA + 32), stc_smem_desc(sW + 32), IDESC, 1u);
             tc_commit(mma_bar);
+        }
+        if (tid < (a.seg ? STC_PIECES : 1)) {                    // ... then refill the slot the previous tile has just released
+            const long long next = tile + (long long)(STC_NBUF - 1) * gridDim.x;
+            if (next < num_tiles) {
+                const int nb = (buf + STC_NBUF - 1) % STC_NBUF;
+                if (a.seg) issue_piece(nb, next, tid); else issue_span(nb, next);
+            }
         }
         mbar_wait(mma_bar, mma_phase);
         mma_phase ^= 1;
@@ -345,6 +395,17 @@ static int launch_stem_tc(const uint8_t *img, const float *w, const float *b, vo
     const long long rows_out = 128 / wo + 2;
     long long span = ((rows_out - 1) * stride + 3) * (long long)wd * 3 + 32;
     span = (span + 127) & ~127ll;
+    // Segmented spans (per piece the columns of <= 128 output pixels + window + alignment slack) where whole rows do not fit the
+    // shared-memory budget (images wider than ~2700 pixels; before, those fell back to the SIMT kernel).  Where both fit whole
+    // rows are faster although they fetch several times the bytes -- one bulk copy per tile instead of six, less address
+    // arithmetic in front of the MMAs: 0.177 vs 0.193 ms at 1281 x 721 x 32, 0.096 vs 0.127 ms at 513 x 513 x 64 (the stem is
+    // bound by its per-tile chain, not by L2 traffic or occupancy).  PN_STEM_SEGMENTS=1 forces segments (tests), =0 forbids them.
+    const long long piece = (((127ll * stride + 3) * 3 + 30) + 15) & ~15ll;
+    const long long smem_rows = STC_A_BYTES + STC_W_BYTES + STC_NBUF * span + 128 + 128 + 1024;
+    const char *e_seg = getenv("PN_STEM_SEGMENTS");
+    a.seg = (wo >= 128 && ((e_seg && e_seg[0] == '1') || (smem_rows > 200 * 1024 && !(e_seg && e_seg[0] == '0')))) ? 1 : 0;
+    a.piece_cap = (int)piece;
+    if (a.seg) span = (STC_PIECES * piece + 127) & ~127ll;
     const long long smem = STC_A_BYTES + STC_W_BYTES + STC_NBUF * span + 128 + 128 + 1024;
     if (smem > 200 * 1024) return 1;                              // does not fit: caller falls back to the SIMT kernel
     a.span_cap = (int)span;

@@ -88,7 +88,9 @@ def test_stem_u8_equals_preprocess_then_stem():
 
 
 @pytest.mark.parametrize("cout,n,h,w", [(32, 2, 513, 513), (16, 1, 721, 1281), (24, 3, 257, 257), (32, 5, 33, 47), (16, 2, 7, 5),
-                                        (32, 1, 1, 1), (24, 4, 2, 300), (32, 3, 129, 64), (16, 1, 64, 2049)])
+                                        (32, 1, 1, 1), (24, 4, 2, 300), (32, 3, 129, 64), (16, 1, 64, 2049),
+                                        # segmented spans (wide images) with a ragged batch tail / tiles that straddle rows and images
+                                        (24, 3, 9, 515), (16, 2, 3, 1283), (32, 5, 4, 259), (16, 1, 3, 6401)])
 def test_stem_u8_tensor_core(cout, n, h, w):
     """Production stem: uint8 BGR image -> bf16 NHWC through the tcgen05 im2col GEMM (normalisation folded into
     the operands) against normalise-then-conv in fp32 (utils.py:23 + mobilenet_v1.py:47-54)."""
@@ -109,6 +111,15 @@ def test_stem_u8_tensor_core(cout, n, h, w):
     assert float((y - ref).abs().mean()) < 3e-3 * float(ref.abs().mean() + 1e-3)
     y2 = abi.stem(torch.from_numpy(img).to(DEV), w27, b.to(DEV), 2, nat.PN_BF16, u8=True).float().cpu()
     assert torch.equal(y, y2)
+    # the two ways of staging the input (whole rows / per-row column segments, the latter for images too wide for whole rows) feed
+    # the same im2col: same bits
+    if (w + 2 - 3) // 2 + 1 >= 128:
+        os.environ["PN_STEM_SEGMENTS"] = "1"
+        try:
+            y3 = abi.stem(torch.from_numpy(img).to(DEV), w27, b.to(DEV), 2, nat.PN_BF16, u8=True).float().cpu()
+        finally:
+            del os.environ["PN_STEM_SEGMENTS"]
+        assert torch.equal(y, y3)
 
 
 # ------------------------------------------------------------------------------------- B3
