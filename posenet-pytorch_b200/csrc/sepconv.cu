@@ -60,7 +60,7 @@ struct SepGeom {
     int dww_res;                          // depthwise weights resident in shared memory (off_dww) instead of behind every patch stage
     int w_res;                            // pointwise weights resident: W stage = k-block * n_halves + column block, loaded once
     unsigned off_dww;                     // resident depthwise weights [kblocks][10][64] fp32 (SEP_LEAN & 4)
-    int teams;                            // depthwise warp teams (1, 2): a team owns whole items, the teams work on alternate items
+    int teams;                            // depthwise warp teams (1, 2, 3): a team owns whole items, the teams take items in turn
     int exp;                              // PN_SEP_EXP build only: experiment flags (1 no dw math, 2 no (staged) epilogue work, 4 no MMA, 8 no W loads,
                                           // 16 direct epilogue without stores, 32 no patch loads, 64 no weight loads / segments, 128 no proxy fence)
     unsigned epi_sleep_ns;                // sleep between the epilogue's polls of its accumulator barrier (PN_SEP_EPI_SLEEP, default 200)
@@ -221,7 +221,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         tma_prefetch_desc(&tmap_y);
         for (int s = 0; s < g.p_stages; ++s) {
             mbar_init(bar(SepBars::patch_full, s), 1);
-            mbar_init(bar(SepBars::patch_empty, s), SEP_DW_WARPS / g.teams);
+            mbar_init(bar(SepBars::patch_empty, s), (SEP_DW_WARPS + g.teams - 1) / g.teams);
         }
         for (int s = 0; s < g.w_stages; ++s) {
             mbar_init(bar(SepBars::w_full, s), 1);
@@ -229,7 +229,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         }
         for (int s = 0; s < g.a_stages; ++s) {
             // a stage produced by a peer is filled by its bulk copy (one expect_tx arrival + the bytes)
-            mbar_init(bar(SepBars::a_full, s), (!CLUSTER || s % CL == rank) ? SEP_DW_WARPS / g.teams : 1);
+            mbar_init(bar(SepBars::a_full, s), (!CLUSTER || s % CL == rank) ? (SEP_DW_WARPS + g.teams - 1) / g.teams : 1);
             mbar_init(bar(SepBars::a_empty, s), CL);            // every CTA's MMAs have read the stage (multicast commits)
         }
         for (int s = 0; s < 2; ++s) {
@@ -603,7 +603,14 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         // of one, the barriers count five arrivals, and two items are in flight at once (the rings are deep enough where
         // sep_geometry turns this on).  Every warp still walks all items in order so that its stage cursors and parities
         // follow the rings; it just steps over the other team's items.
-        const int n_teams = g.teams, team_warps = SEP_DW_WARPS / n_teams, team = (warp - SEP_FIRST_DW_WARP) / team_warps;
+        // Team sizes: 10 warps are 10 / 5 + 5 / 4 + 3 + 3.  Every barrier counts the LARGEST team's arrivals whichever team uses the
+        // stage (stages rotate through the teams), so the first warp of a smaller team arrives twice.
+        const int n_teams = g.teams, dwi = warp - SEP_FIRST_DW_WARP, team_max = (SEP_DW_WARPS + n_teams - 1) / n_teams;
+        const int big_teams = SEP_DW_WARPS - n_teams * (team_max - 1);            // teams that have team_max warps (the first ones)
+        const int team = dwi < big_teams * team_max ? dwi / team_max : big_teams + (dwi - big_teams * team_max) / (team_max - 1);
+        const int team_first = team < big_teams ? team * team_max : big_teams * team_max + (team - big_teams) * (team_max - 1);
+        const int team_warps = team < big_teams ? team_max : team_max - 1;
+        const bool twice = team_warps < team_max && dwi == team_first;            // stands in for the warp this team lacks
         const int n_subs = g.subs, n_pst = g.p_stages, n_ast = g.a_stages, n_kb = g.kblocks;
         const int item_step = CLUSTER ? CL : n_teams;                    // items (k-blocks in tile order) between two of this warp's
         int tr_d = 0;
@@ -611,7 +618,7 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         // team's: both rings are deeper than one item)
         int ps = CLUSTER ? 0 : team * n_subs, as = CLUSTER ? rank : team, kb = CLUSTER ? rank : team;
         uint32_t pph = 0, aph = 0;
-        int rot = (warp - SEP_FIRST_DW_WARP) - team * team_warps;        // this warp's first segment in the current item
+        int rot = dwi - team_first;                                      // this warp's first segment in the current item
         long long tile = tile_first;
         while (!CLUSTER && kb >= n_kb) { kb -= n_kb; tile += tile_step; }    // (single-k-block tiles: the second team starts one tile on)
         (void)tr_d;
@@ -751,7 +758,10 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                 SEP_PH(4);
               }   // segments of this item
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar(SepBars::patch_empty, ps));   // this warp no longer reads the patch
+              if (lane == 0) {                                             // this warp no longer reads the patch
+                  mbar_arrive(bar(SepBars::patch_empty, ps));
+                  if (twice) mbar_arrive(bar(SepBars::patch_empty, ps));
+              }
               SEP_PH(5);
               if (++ps == n_pst) { ps = 0; pph ^= 1; }
               if (++rot == team_warps) rot = 0;
@@ -761,12 +771,15 @@ sepconv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #endif
             fence_async_smem();                                       // A-tile writes -> visible to the tensor core
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(SepBars::a_full, as));
+            if (lane == 0) {
+                mbar_arrive(bar(SepBars::a_full, as));
+                if (twice) mbar_arrive(bar(SepBars::a_full, as));
+            }
             SEP_PH(6);
             if (tracer) { SEP_TRACE(0, tr_d, 3); ++tr_d; }
             // on to this warp's next item: over the other team's patch stages and A stage, item_step k-blocks ahead
-            if (n_teams == 2) {
-                ps += n_subs;
+            if (n_teams > 1) {
+                ps += (n_teams - 1) * n_subs;
                 if (ps >= n_pst) { ps -= n_pst; pph ^= 1; }
             }
             as += item_step;
@@ -1054,6 +1067,8 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
         const char *e = getenv("PN_SEP_TEAMS");
         const int v = e ? atoi(e) : (tuned && tuned->p > 0 && g.th == tuned->th && g.tw == tuned->tw && g.subs == tuned->subs) ? tuned->teams : 0;
         if (v == 1 || (v == 2 && g.cl == 1 && SEP_DW_WARPS % 2 == 0 && g.p_stages >= 2 * g.subs && g.a_stages >= 2 && g.p_stages >= g.a_stages)) g.teams = v;
+        // three teams (4 + 3 + 3 warps): three items in flight
+        if (v == 3 && g.cl == 1 && SEP_DW_WARPS >= 6 && g.p_stages >= 3 * g.subs && g.a_stages >= 3 && g.p_stages >= g.a_stages) g.teams = 3;
     }
     g.epi_sleep_ns = 200;
     if (const char *e = getenv("PN_SEP_EPI_SLEEP")) g.epi_sleep_ns = (unsigned)atoi(e);

@@ -81,6 +81,39 @@ def test_tensor_pipe_depthwise_policy_and_geometry(monkeypatch):
         assert lib.pn_sepconv_describe(*shp, buf, 512) == 0 and b"tensor-pipe" not in buf.value     # stride 2, narrow, wide, ragged
 
 
+def test_measured_tile_table_and_team_policy(monkeypatch):
+    """csrc/sep_tuned.inc: every row is a configuration the geometry code accepts as written (tile, ring depths, teams), it is
+    what the described block gets, PN_SEP_TUNED=0 falls back to the cost model, and forced teams need rings deep enough."""
+    import ctypes as C
+    import re
+    lib, buf = nat.load(), C.create_string_buffer(512)
+    for k in ("PN_SEP_TUNED", "PN_SEP_TILE", "PN_SEP_STAGES", "PN_SEP_TEAMS", "PN_SEP_TC", "PN_SEP_WRES", "PN_SEP_DWWRES"):
+        monkeypatch.delenv(k, raising=False)
+    inc = os.path.join(os.path.dirname(nat.__file__), "..", "csrc", "sep_tuned.inc")
+    rows = [tuple(int(v) for v in m.group(1).split(",")) for m in re.finditer(r"^\s*\{([\d, ]+)\}", open(inc).read(), re.M)]
+    assert len(rows) >= 5
+    pat = re.compile(r"tile (\d+)x(\d+) subs (\d+) .* teams (\d+) stages p(\d+) w(\d+)r? a(\d+) stg(\d+)")
+    for (k, nc, s, d, ho, wo, th, tw, subs, p, w, a, stg, teams) in rows:
+        h, wd = (ho - 1) * s + 1, (wo - 1) * s + 1                   # an input size that gives this output size (pad = dilation for stride 1)
+        assert lib.pn_sepconv_describe(4, h, wd, k, nc, s, d, buf, 512) == 0, lib.pn_last_error_string()
+        got = tuple(int(v) for v in pat.search(buf.value.decode()).groups())
+        assert got == (th, tw, subs, teams, p, w, a, stg), (buf.value, (k, nc, s, d, ho, wo))
+    k, nc, s, d, ho, wo, th, tw, subs = rows[0][:9]
+    monkeypatch.setenv("PN_SEP_TUNED", "0")
+    assert lib.pn_sepconv_describe(4, (ho - 1) * s + 1, (wo - 1) * s + 1, k, nc, s, d, buf, 512) == 0 and b"tile" in buf.value
+    monkeypatch.delenv("PN_SEP_TUNED")
+    # three teams of 4 + 3 + 3 warps only where three items fit the rings (p >= 3 subs, a >= 3, p >= a); otherwise the request is ignored
+    monkeypatch.setenv("PN_SEP_TEAMS", "3")
+    assert lib.pn_sepconv_describe(64, 129, 129, 128, 128, 1, 1, buf, 512) == 0 and b"teams 3" in buf.value
+    assert lib.pn_sepconv_describe(64, 257, 257, 64, 128, 2, 1, buf, 512) == 0 and b"teams 1" in buf.value      # p2 a2
+    # resident pointwise weights: one stage per (k-block, column block), marked "r"; PN_SEP_WRES=0 brings the ring back
+    monkeypatch.delenv("PN_SEP_TEAMS")
+    assert lib.pn_sepconv_describe(64, 129, 129, 128, 128, 1, 1, buf, 512) == 0 and b" w2r " in buf.value
+    assert lib.pn_sepconv_describe(64, 33, 33, 512, 512, 1, 1, buf, 512) == 0 and b"r a" not in buf.value      # 512 KB of W: ring
+    monkeypatch.setenv("PN_SEP_WRES", "0")
+    assert lib.pn_sepconv_describe(64, 129, 129, 128, 128, 1, 1, buf, 512) == 0 and b"r a" not in buf.value
+
+
 @pytest.mark.parametrize("mid", [50, 75, 100, 101])
 @pytest.mark.parametrize("os_", [8, 16, 32])
 def test_layer_table_and_state_dict_mirror_reference(mid, os_):

@@ -13,7 +13,8 @@ N_TILES, N_TOP = int(os.environ.get("TUNE_TILES", "36")), 2
 ENV_KEYS = ("PN_SEP_TILE", "PN_SEP_STAGES", "PN_SEP_TEAMS")
 
 
-def one(shape):
+def make_timer(shape):
+    """(describe(env) -> geometry tuple or None, timeit(env, reps) -> us) for one block shape; tensors allocated once."""
     import ctypes as C
     import torch
     import abi
@@ -66,6 +67,26 @@ def one(shape):
             ts.append(e0.elapsed_time(e1) * 1e3 / reps)
         return min(ts)
 
+    return describe, timeit
+
+
+def ab(shape, envs):
+    """Times explicit configurations: envs = "PN_SEP_TEAMS=3,PN_SEP_STAGES=4.2.4.1;..." ('.' stands for ',' inside a value)."""
+    describe, timeit = make_timer(shape)
+    for spec in [""] + envs.split(";"):
+        env = dict(kv.split("=") for kv in spec.split(",") if kv)
+        env = {k: v.replace(".", ",") for k, v in env.items()}
+        d = describe(env)
+        if d is None:
+            print("  %-60s rejected" % spec, flush=True)
+            continue
+        print("  %-60s %s  %.1f us" % (spec or "(default)", d, timeit(env, reps=20)), flush=True)
+
+
+def one(shape):
+    n, h, w, cin, cout, stride, dil = shape
+    describe, timeit = make_timer(shape)
+    ho, wo = (h + 2 * ((stride - 1 + 2 * dil) // 2) - 2 * dil - 1) // stride + 1, (w + 2 * ((stride - 1 + 2 * dil) // 2) - 2 * dil - 1) // stride + 1
     base_desc = describe({})
     if base_desc is None:
         print("shape %s: not a tile-kind block" % (shape,), flush=True)
@@ -137,6 +158,9 @@ def one(shape):
 if __name__ == "__main__":
     if sys.argv[1] == "--one":
         one([int(v) for v in sys.argv[2].split(",")])
+    elif sys.argv[1] == "--ab":
+        print("shape %s" % sys.argv[2], flush=True)
+        ab([int(v) for v in sys.argv[2].split(",")], sys.argv[3])
     else:
         for a in sys.argv[1:]:
             t0 = time.time()
