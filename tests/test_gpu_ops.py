@@ -120,6 +120,15 @@ def test_stem_u8_tensor_core(cout, n, h, w):
         finally:
             del os.environ["PN_STEM_SEGMENTS"]
         assert torch.equal(y, y3)
+    # the pipelined kernel (default; span rings of 2-4 slots) and the single-chain kernel it replaced run the same MMAs: same bits
+    for env in ({"PN_STEM_PIPE": "0"}, {"PN_STEM_NBUF": "3"}, {"PN_STEM_NBUF": "4", "PN_STEM_CTAS": "1"}):
+        os.environ.update(env)
+        try:
+            y4 = abi.stem(torch.from_numpy(img).to(DEV), w27, b.to(DEV), 2, nat.PN_BF16, u8=True).float().cpu()
+        finally:
+            for k in env:
+                del os.environ[k]
+        assert torch.equal(y, y4), env
 
 
 # ------------------------------------------------------------------------------------- B3
