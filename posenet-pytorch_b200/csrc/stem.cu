@@ -78,10 +78,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const void *__restrict__ xin,
 //     x*(2/255) - 1 = (x - 128)*(2/255) + 1/255,   A = x - 128 (exact, in [-128, 127]),   W' = bf16(w * 2/255),
 //     bias' = b + sum_k w_k / 255,   and a padded tap holds -0.5, which normalises to exactly 0 (the reference's zero
 // padding of the normalised image).  Centring on 128 avoids the cancellation a raw-pixel formulation would have.
-// One CTA = 128 threads = 128 pixels; several CTAs per SM overlap each other's load / MMA / store phases.  The
-// tile's input bytes are one contiguous span of the image batch (whole rows), fetched with a bulk async copy.
-constexpr int STC_THREADS = 128;
-constexpr int STC_NBUF = 2;                          // span ring: the next tile's bytes load while this one is computed
+// One CTA = 128 pixel threads + a control warp; several CTAs per SM.
 
 // K-major SWIZZLE_64B: the stem's K is 32 (27 taps + 5 zero columns) = 64-byte rows, 8-row groups 512 B apart.  Half the shared
 // memory of the 128-byte-row layout for A and W (10 KB instead of 20 KB per CTA), i.e. 7 instead of 5 CTAs per SM.
@@ -104,105 +101,62 @@ struct StemTcArgs {
     long long total_px, total_bytes, total_lo16;   // pixels; bytes of the image batch; the same rounded DOWN to 16
     int span_cap;                          // bytes per span buffer (multiple of 16)
     int seg, piece_cap;                    // segmented spans (wide images): 6 pieces of piece_cap bytes per buffer, see the kernel
-    int nbuf;                              // span ring slots (stem_tcp_kernel)
+    int nbuf;                              // span ring slots (stem_tc_kernel)
 };
 constexpr int STC_PIECES = 6;              // 2 output-row segments x 3 input rows
 
-__global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a) {
+// The CTA is a software pipeline (round 2; the first version ran a tile as one chain -- im2col, CTA barrier, MMA, commit wait,
+// TMEM read, stores -- in which every warp sat out the barrier + MMA round trip, warp 0 additionally walked the refill's span
+// arithmetic with the other three waiting for it, and ~200 of a warp's ~580 instructions per tile were the (image, row, column)
+// divisions of its pixel index: C2 85.9 -> 80.1 us, C3 169.7 -> 126.9 us, C4 202.7 -> 159.0 us, same bits):
+//   * a fifth warp owns the control work: it waits for "A complete" (an mbarrier the 128 pixel threads arrive on), issues the
+//     tile's two MMAs and refills the span slot the tile has just released;
+//   * A and the accumulator are double-buffered, so a pixel warp goes from the im2col of tile i straight to the epilogue of
+//     tile i - 1 (whose MMAs retired long ago) and on to the im2col of tile i + 1: it never waits for a round trip;
+//   * the pixel index advances incrementally (conditional subtractions instead of divisions).
+// Input staging, per tile, into a ring of a.nbuf slots:
+//   * whole rows (default): the tile's input bytes are one contiguous span of the image batch [lo16, lo16 + size), one bulk copy;
+//     the <= 15 bytes between total_lo16 and the real end of the caller's buffer are fetched with ordinary byte loads by the
+//     issuing thread BEFORE its arrive.expect_tx (release) on the slot's barrier, so the consumers' wait (acquire) covers them;
+//   * segments (a.seg: images at least 128 output pixels wide whose whole rows would leave too few CTAs per SM, or do not fit
+//     at all -- 19 KB instead of 2.3 KB per tile at 1281 x 721): a 128-pixel tile lies in at most two output rows; per
+//     output-row segment and window row ky ONE bulk copy of just the columns the segment reads (16-byte aligned outwards),
+//     issued by lane p = segment * 3 + ky with its own expect_tx, so the slot's barrier counts STC_PIECES arrivals.
+constexpr int STP_THREADS = 160;
+constexpr int STP_MAX_NBUF = 4;
+constexpr int STP_CTRL_BYTES = 384;         // bias 128 | span_full[4] a_full[2] mma_done[2] 64 | tmem slot 16 | span_lo[4] 32 | piece_adj[24] 96
+
+__global__ void __launch_bounds__(STP_THREADS) stem_tc_kernel(const StemTcArgs a) {
     extern __shared__ uint8_t stc_raw[];
     const uint32_t base = (smem_u32(stc_raw) + 1023u) & ~1023u;
     uint8_t *gen = stc_raw + (base - smem_u32(stc_raw));
-    const uint32_t sA = base;                         // 128 rows x 64 B (K 0..31), 64B swizzle
-    const uint32_t sW = base + STC_A_BYTES;           // 32 rows x 64 B
-    const uint32_t sSpan = base + STC_A_BYTES + STC_W_BYTES;       // STC_NBUF x span_cap
-    float *sBias = reinterpret_cast<float *>(gen + STC_A_BYTES + STC_W_BYTES + STC_NBUF * a.span_cap);
-    const uint32_t bars = base + STC_A_BYTES + STC_W_BYTES + STC_NBUF * (uint32_t)a.span_cap + 128;   // span_full[NBUF], mma_done, tmem slot
-    const uint32_t mma_bar = bars + 8u * STC_NBUF, tmem_slot_addr = mma_bar + 8u;
-    volatile uint32_t *tmem_slot =
-        reinterpret_cast<volatile uint32_t *>(gen + STC_A_BYTES + STC_W_BYTES + STC_NBUF * a.span_cap + 128 + 8 * STC_NBUF + 8);
-    // span base (byte offset of the ring slot's first byte in the image batch), written by thread 0 when it issues the load
-    volatile long long *span_lo = reinterpret_cast<volatile long long *>(gen + STC_A_BYTES + STC_W_BYTES + STC_NBUF * a.span_cap + 128 + 32);
-    // segmented spans: byte offset of input column byte 0 of piece p's row inside ring slot s (may be negative), written by the
-    // thread that issues the piece
-    volatile int *piece_adj = reinterpret_cast<volatile int *>(gen + STC_A_BYTES + STC_W_BYTES + STC_NBUF * a.span_cap + 128 + 64);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t sA = base;                                     // 2 x (128 rows x 64 B), 64B swizzle
+    const uint32_t sW = base + 2 * STC_A_BYTES;                   // 32 rows x 64 B
+    const uint32_t sSpan = sW + STC_W_BYTES;                      // a.nbuf x span_cap
+    const uint32_t ctrl_off = 2 * STC_A_BYTES + STC_W_BYTES + (uint32_t)a.nbuf * (uint32_t)a.span_cap;
+    float *sBias = reinterpret_cast<float *>(gen + ctrl_off);
+    const uint32_t span_full = base + ctrl_off + 128, a_full = span_full + 32, mma_done = a_full + 16, tmem_slot_addr = mma_done + 16;
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + ctrl_off + 192);
+    volatile long long *span_lo = reinterpret_cast<volatile long long *>(gen + ctrl_off + 208);
+    volatile int *piece_adj = reinterpret_cast<volatile int *>(gen + ctrl_off + 240);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row_bytes = (long long)a.w * 3;
     const long long num_tiles = (a.total_px + 127) / 128;
 
-    // span of tile t: the whole input rows its pixels read, as [lo16, lo16 + size)
-    // (all pixel indices fit 32 bits: the launcher checks total_px < 2^31)
-    auto span_of = [&](long long t, long long &lo16, uint32_t &size) {
-        const uint32_t m0 = (uint32_t)t * 128u, m1 = min(m0 + 127u, (uint32_t)a.total_px - 1u);
-        const uint32_t r0 = m0 / (uint32_t)a.wo, r1 = m1 / (uint32_t)a.wo;        // global output row = img * ho + oy
-        const int i0 = (int)(r0 / (uint32_t)a.ho), i1 = (int)(r1 / (uint32_t)a.ho);
-        const int oy0 = (int)(r0 - (uint32_t)i0 * (uint32_t)a.ho), oy1 = (int)(r1 - (uint32_t)i1 * (uint32_t)a.ho);
-        const int iy0 = max(oy0 * a.stride - 1, 0), iy1 = min(oy1 * a.stride + 1, a.h - 1);
-        const long long lo = ((long long)i0 * a.h + iy0) * row_bytes, hi = ((long long)i1 * a.h + iy1 + 1) * row_bytes;
-        lo16 = lo & ~15ll;
-        long long end = (hi + 15) & ~15ll;
-        if (end > a.total_lo16) end = a.total_lo16;      // the bulk copy never reads past the caller's buffer ...
-        size = (uint32_t)(end - lo16);
-    };
-    // ... the <= 15 bytes between total_lo16 and the real end are fetched with ordinary byte loads by the issuing thread,
-    // BEFORE its arrive.expect_tx (release) on the slot's barrier, so the consumers' wait (acquire) also covers them.
-    // Only the batch's last tile can have such a tail.
-    auto issue_span = [&](int slot, long long t) {
-        long long lo16; uint32_t size;
-        span_of(t, lo16, size);
-        span_lo[slot] = lo16;
-        const uint32_t dst = sSpan + (uint32_t)slot * (uint32_t)a.span_cap;
-        if (lo16 + size == a.total_lo16)
-            for (long long b = a.total_lo16; b < a.total_bytes; ++b)
-                asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst + (uint32_t)(b - lo16)), "r"((uint32_t)a.img[b]) : "memory");
-        mbar_expect_tx(bars + 8u * slot, size);
-        if (size) bulk_load_1d(dst, a.img + lo16, size, bars + 8u * slot);
-    };
-
-    // Segmented spans (a.seg: images at least 128 output pixels wide, where whole rows would be several times what the tile
-    // reads -- 19 KB instead of 2.3 KB per tile at 1281 x 721): a 128-pixel tile lies in at most two output rows; per output-row
-    // segment and window row ky ONE bulk copy of just the columns the segment reads (16-byte aligned outwards), issued by thread
-    // p = segment * 3 + ky with its own expect_tx, so the slot's barrier counts STC_PIECES arrivals.
-    auto issue_piece = [&](int slot, long long t, int p) {
-        const uint32_t m0 = (uint32_t)t * 128u, m1 = min(m0 + 127u, (uint32_t)a.total_px - 1u);
-        const uint32_t r0 = m0 / (uint32_t)a.wo, r1 = m1 / (uint32_t)a.wo;        // r1 <= r0 + 1 (wo >= 128)
-        const int sg = p / 3, ky = p - sg * 3;
-        const uint32_t r = r0 + (uint32_t)sg;
-        uint32_t size = 0;
-        const uint32_t bar = bars + 8u * slot;
-        if (r <= r1) {
-            const int img_i = (int)(r / (uint32_t)a.ho), oy = (int)(r - (uint32_t)img_i * (uint32_t)a.ho);
-            const int xa = sg == 0 ? (int)(m0 - r0 * (uint32_t)a.wo) : 0, xb = r == r1 ? (int)(m1 - r1 * (uint32_t)a.wo) : a.wo - 1;
-            const int iy = oy * a.stride - 1 + ky;
-            if (iy >= 0 && iy < a.h) {
-                const long long rowstart = ((long long)img_i * a.h + iy) * row_bytes;
-                const long long lo = rowstart + (long long)max(xa * a.stride - 1, 0) * 3, hi = rowstart + (long long)min(xb * a.stride + 1, a.w - 1) * 3 + 3;
-                const long long lo16 = lo & ~15ll;
-                long long end = (hi + 15) & ~15ll;
-                if (end > a.total_lo16) end = a.total_lo16;
-                size = end > lo16 ? (uint32_t)(end - lo16) : 0u;
-                const uint32_t dst = sSpan + (uint32_t)slot * (uint32_t)a.span_cap + (uint32_t)p * (uint32_t)a.piece_cap;
-                piece_adj[slot * STC_PIECES + p] = p * a.piece_cap - (int)(lo16 - rowstart);
-                for (long long b = max(a.total_lo16, lo16); b < hi; ++b)     // (the batch's last < 16 bytes, see issue_span)
-                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst + (uint32_t)(b - lo16)), "r"((uint32_t)a.img[b]) : "memory");
-                mbar_expect_tx(bar, size);
-                if (size) bulk_load_1d(dst, a.img + lo16, size, bar);
-                return;
-            }
-        }
-        mbar_arrive(bar);                                          // nothing to fetch for this piece
-    };
-
     if (tid == 0) {
-        for (int i = 0; i < STC_NBUF; ++i) mbar_init(bars + 8u * i, a.seg ? STC_PIECES : 1);
-        mbar_init(mma_bar, 1);
+        for (int i = 0; i < a.nbuf; ++i) mbar_init(span_full + 8u * i, a.seg ? STC_PIECES : 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(a_full + 8u * i, 128);
+            mbar_init(mma_done + 8u * i, 1);
+        }
         mbar_fence_init();
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "r"(32u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "r"(64u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // W'[n][k] = bf16(w[k][n] * 2/255) in the swizzled K-major layout; bias' = b + sum_k w_k / 255
-    for (int i = tid; i < 32 * 4; i += STC_THREADS) {               // (row n, 16-byte chunk c) -> 8 k values
+    for (int i = tid; i < 32 * 4; i += STP_THREADS) {               // (row n, 16-byte chunk c) -> 8 k values
         const int nrow = i >> 2, c = i & 3;
         uint32_t pk[4];
 #pragma unroll
@@ -232,226 +186,8 @@ __global__ void __launch_bounds__(STC_THREADS) stem_tc_kernel(const StemTcArgs a
     pdl_wait();                                                   // (ptx.cuh) whatever produced the image / used the output buffer is done
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-    long long tile = blockIdx.x;
-    if (tid < (a.seg ? STC_PIECES : 1)) {
-        for (int i = 0; i < STC_NBUF - 1; ++i) {
-            const long long t = tile + (long long)i * gridDim.x;
-            if (t >= num_tiles) break;
-            if (a.seg) issue_piece(i, t, tid); else issue_span(i, t);
-        }
-    }
-    uint32_t span_phase = 0, mma_phase = 0;             // bit b of span_phase = parity of ring slot b
-    int buf = 0;
-    for (; tile < num_tiles; tile += gridDim.x, buf = (buf + 1) % STC_NBUF) {
-        const long long m = tile * 128 + tid;
-        const bool live = m < a.total_px;
-        int img_i = 0, oy = 0, ox = 0;
-        if (live) {
-            const uint32_t r = (uint32_t)m / (uint32_t)a.wo;
-            ox = (int)((uint32_t)m - r * (uint32_t)a.wo);
-            img_i = (int)(r / (uint32_t)a.ho);
-            oy = (int)(r - (uint32_t)img_i * (uint32_t)a.ho);
-        }
-        mbar_wait(bars + 8u * buf, (span_phase >> buf) & 1u);
-        span_phase ^= 1u << buf;
-        const long long lo16 = span_lo[buf];                     // (published before the load was issued)
-        // ---- im2col: this thread's pixel -> row `tid` of A
-        float f[32];
-#pragma unroll
-        for (int k = 27; k < 32; ++k) f[k] = 0.f;
-        const uint32_t sp = sSpan + (uint32_t)buf * (uint32_t)a.span_cap;
-        // The 9 bytes of a window row (3 pixels x BGR) are contiguous: three aligned 32-bit loads + funnel shifts bring them
-        // to byte 0 (one pixel later when the window starts left of the image), then one PRMT per tap builds 2^23 + x.
-        const int ix0 = ox * a.stride - 1;
-        const int lead = ix0 < 0 ? 1 : 0;                                  // window column 0 is padding (pad = 1)
-        bool okx[3];
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) okx[kx] = live && ix0 + kx >= 0 && ix0 + kx < a.w;
-        const int iy0 = oy * a.stride - 1;
-        // interior pixels (all 27 taps inside the image) take a copy of the loop without the padding selects
-        const bool interior_px = live && ix0 >= 0 && ix0 + 2 < a.w && iy0 >= 0 && iy0 + 2 < a.h;
-        // byte offset of the window's first row / first used column inside the span (32-bit: spans are < 200 KB)
-        int rowoff[3];
-        if (a.seg) {
-            const int sg = live && (uint32_t)m / (uint32_t)a.wo != (uint32_t)(tile * 128) / (uint32_t)a.wo ? 1 : 0;   // second output row of the tile
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) rowoff[ky] = piece_adj[buf * STC_PIECES + sg * 3 + ky] + (ix0 + lead) * 3;
-        } else {
-            const int rowoff0 = (int)(((long long)img_i * a.h + iy0) * row_bytes - lo16) + (ix0 + lead) * 3;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) rowoff[ky] = rowoff0 + ky * (int)row_bytes;
-        }
-        auto im2col = [&](const bool interior) {
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = oy * a.stride - 1 + ky;
-            const bool row_ok = live && iy >= 0 && iy < a.h;
-            const uint32_t b0 = row_ok ? (uint32_t)rowoff[ky] : 0u;
-            const uint32_t a0 = sp + (b0 & ~3u), sh = (b0 & 3u) * 8u;
-            const uint32_t w0 = lds_u32s(a0), w1 = lds_u32s(a0 + 4), w2 = lds_u32s(a0 + 8);
-            uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = w2 >> sh;
-            const uint32_t ls = (uint32_t)lead * 24u;                      // shift the 9 bytes up by one pixel
-            v2 = __funnelshift_l(v1, v2, ls);
-            v1 = __funnelshift_l(v0, v1, ls);
-            v0 = v0 << ls;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const bool ok = row_ok && okx[kx];
-#pragma unroll
-                for (int ci = 0; ci < 3; ++ci) {                           // BGR bytes -> RGB taps; 2^23 + 128 + (x - 128) trick
-                    const int i = kx * 3 + (2 - ci);                       // byte index inside the 9-byte window row
-                    const uint32_t src = i < 4 ? v0 : i < 8 ? v1 : v2;
-                    const uint32_t bits = __byte_perm(src, 0x4B000000u, 0x7540u + (uint32_t)(i & 3));
-                    const float val = __uint_as_float(bits) - 8388736.0f;
-                    f[(ky * 3 + kx) * 3 + ci] = (interior || ok) ? val : -0.5f;   // interior: the select folds away
-                }
-            }
-        }
-        };
-        if (interior_px) im2col(true); else im2col(false);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[c * 8 + 2 * j], f[c * 8 + 2 * j + 1]);
-                pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
-            }
-            st_shared_v4(sA + (uint32_t)tid * 64u + (uint32_t)((c ^ ((tid >> 1) & 3)) << 4), pk[0], pk[1], pk[2], pk[3]);
-        }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();                                         // A complete; the previous tile's TMEM reads are done
-        if (tid == 0) {                                          // the MMAs first: every thread of the CTA waits for them ...
-            tc_fence_after();
-            tc_mma_bf16(tmem, stc_smem_desc(sA), stc_smem_desc(sW), IDESC, 0u);
-            tc_mma_bf16(tmem, stc_smem_desc(sA + 32), stc_smem_desc(sW + 32), IDESC, 1u);
-            tc_commit(mma_bar);
-        }
-        if (tid < (a.seg ? STC_PIECES : 1)) {                    // ... then refill the slot the previous tile has just released
-            const long long next = tile + (long long)(STC_NBUF - 1) * gridDim.x;
-            if (next < num_tiles) {
-                const int nb = (buf + STC_NBUF - 1) % STC_NBUF;
-                if (a.seg) issue_piece(nb, next, tid); else issue_span(nb, next);
-            }
-        }
-        mbar_wait(mma_bar, mma_phase);
-        mma_phase ^= 1;
-        tc_fence_after();
-        uint32_t v[32];
-        tc_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
-        tc_ld_wait();
-        if (live) {
-            // a pixel's cout bf16 values are contiguous (32 / 48 / 64 bytes): 256-bit stores where the row is 32-byte aligned
-            // (cout 16, 32) -- a warp store then fills whole 32-byte sectors instead of half of 32 of them per request, which is
-            // what kept the LSU data pipe 75 % busy -- 128-bit stores otherwise (cout 24)
-            __nv_bfloat16 *dst = a.y + (size_t)m * a.cout;
-            const bool wide = (a.cout & 15) == 0;
-#pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2) {
-                if (c2 * 16 < a.cout) {
-                    uint32_t o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = c2 * 16 + 2 * j;
-                        o[j] = relu6_bf16x2(fadd2(make_float2(__uint_as_float(v[col]), __uint_as_float(v[col + 1])),
-                                                  *reinterpret_cast<const float2 *>(sBias + col)));
-                    }
-                    if (wide) {
-                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c2 * 16), "r"(o[0]), "r"(o[1]),
-                                     "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
-                                     : "memory");
-                    } else {
-                        *reinterpret_cast<uint4 *>(dst + c2 * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-                        if (c2 * 16 + 8 < a.cout) *reinterpret_cast<uint4 *>(dst + c2 * 16 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
-    }
-}
-
-// ---- the same layer as a software pipeline inside the CTA (the default) ------------------------------------------
-// stem_tc_kernel above runs a tile as one chain -- im2col, CTA barrier, MMA, commit wait, TMEM read, stores -- in which every
-// warp sits out the barrier + MMA round trip, warp 0 additionally walks the refill's span arithmetic (several integer
-// divisions) with the other three waiting for it at the next barrier, and ~200 of a warp's ~580 instructions per tile are the
-// (image, row, column) divisions of its pixel index.  Here
-//   * a fifth warp owns the control work: it waits for "A complete" (an mbarrier the 128 pixel threads arrive on), issues the
-//     tile's two MMAs and refills the span slot the tile has just released;
-//   * A and the accumulator are double-buffered, so a pixel warp goes from the im2col of tile i straight to the epilogue of
-//     tile i - 1 (whose MMAs retired long ago) and on to the im2col of tile i + 1: it never waits for a round trip;
-//   * the pixel index advances incrementally (conditional subtractions instead of divisions).
-// Same operands, same two MMAs per tile, same epilogue arithmetic -> same bits as stem_tc_kernel (PN_STEM_PIPE=0 selects it).
-constexpr int STP_THREADS = 160;
-constexpr int STP_MAX_NBUF = 4;
-constexpr int STP_CTRL_BYTES = 384;         // bias 128 | span_full[4] a_full[2] mma_done[2] 64 | tmem slot 16 | span_lo[4] 32 | piece_adj[24] 96
-
-__global__ void __launch_bounds__(STP_THREADS) stem_tcp_kernel(const StemTcArgs a) {
-    extern __shared__ uint8_t stc_raw[];
-    const uint32_t base = (smem_u32(stc_raw) + 1023u) & ~1023u;
-    uint8_t *gen = stc_raw + (base - smem_u32(stc_raw));
-    const uint32_t sA = base;                                     // 2 x (128 rows x 64 B), 64B swizzle
-    const uint32_t sW = base + 2 * STC_A_BYTES;                   // 32 rows x 64 B
-    const uint32_t sSpan = sW + STC_W_BYTES;                      // a.nbuf x span_cap
-    const uint32_t ctrl_off = 2 * STC_A_BYTES + STC_W_BYTES + (uint32_t)a.nbuf * (uint32_t)a.span_cap;
-    float *sBias = reinterpret_cast<float *>(gen + ctrl_off);
-    const uint32_t span_full = base + ctrl_off + 128, a_full = span_full + 32, mma_done = a_full + 16, tmem_slot_addr = mma_done + 16;
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(gen + ctrl_off + 192);
-    volatile long long *span_lo = reinterpret_cast<volatile long long *>(gen + ctrl_off + 208);
-    volatile int *piece_adj = reinterpret_cast<volatile int *>(gen + ctrl_off + 240);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long row_bytes = (long long)a.w * 3;
-    const long long num_tiles = (a.total_px + 127) / 128;
-
-    if (tid == 0) {
-        for (int i = 0; i < a.nbuf; ++i) mbar_init(span_full + 8u * i, a.seg ? STC_PIECES : 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(a_full + 8u * i, 128);
-            mbar_init(mma_done + 8u * i, 1);
-        }
-        mbar_fence_init();
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr), "r"(64u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    for (int i = tid; i < 32 * 4; i += STP_THREADS) {               // W' and bias': as in stem_tc_kernel
-        const int nrow = i >> 2, c = i & 3;
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k0 = c * 8 + 2 * j;
-            const float w0 = (nrow < a.cout && k0 < 27) ? a.w27[k0 * a.cout + nrow] * (float)(2.0 / 255.0) : 0.f;
-            const float w1 = (nrow < a.cout && k0 + 1 < 27) ? a.w27[(k0 + 1) * a.cout + nrow] * (float)(2.0 / 255.0) : 0.f;
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(w0, w1);
-            pk[j] = *reinterpret_cast<const uint32_t *>(&h2);
-        }
-        st_shared_v4(sW + (uint32_t)nrow * 64u + (uint32_t)((c ^ ((nrow >> 1) & 3)) << 4), pk[0], pk[1], pk[2], pk[3]);
-    }
-    if (tid < 32) {
-        float sum = 0.f;
-        if (tid < a.cout)
-            for (int k = 0; k < 27; ++k) sum += a.w27[k * a.cout + tid];
-        sBias[tid] = tid < a.cout ? a.bias[tid] + sum * (float)(1.0 / 255.0) : 0.f;
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    pdl_launch_dependents();                                      // after the TMEM allocation is made (see stem_tc_kernel)
-    const uint32_t tmem = *tmem_slot;
-    pdl_wait();
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
     if (warp == 4) {
         // ===================== control warp: span loads, MMA issue =====================
-        // (span_of / issue_span / issue_piece: the staging of stem_tc_kernel, see the comments there)
         auto issue_span = [&](int slot, long long t) {
             const uint32_t m0 = (uint32_t)t * 128u, m1 = min(m0 + 127u, (uint32_t)a.total_px - 1u);
             const uint32_t r0 = m0 / (uint32_t)a.wo, r1 = m1 / (uint32_t)a.wo;
@@ -548,6 +284,8 @@ __global__ void __launch_bounds__(STP_THREADS) stem_tcp_kernel(const StemTcArgs 
             tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + s * 32u, v);
             tc_ld_wait();
             if (livep) {
+                // a pixel's cout bf16 values are contiguous (32 / 48 / 64 bytes): 256-bit stores where the row is 32-byte aligned
+                // (cout 16, 32) -- a warp store then fills whole 32-byte sectors -- 128-bit stores otherwise (cout 24)
                 __nv_bfloat16 *dst = a.y + (size_t)mp * a.cout;
                 const bool wide = (a.cout & 15) == 0;
 #pragma unroll
@@ -597,6 +335,9 @@ __global__ void __launch_bounds__(STP_THREADS) stem_tcp_kernel(const StemTcArgs 
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) rowoff[ky] = rowoff0 + ky * (int)row_bytes;
             }
+            // ---- im2col: this thread's pixel -> row `tid` of A.  The 9 bytes of a window row (3 pixels x BGR) are contiguous: three
+            // aligned 32-bit loads + funnel shifts bring them to byte 0 (one pixel later when the window starts left of the image);
+            // interior pixels (all 27 taps inside the image) take a copy of the loop without the padding selects
             float f[32];
 #pragma unroll
             for (int k = 27; k < 32; ++k) f[k] = 0.f;
@@ -617,7 +358,7 @@ __global__ void __launch_bounds__(STP_THREADS) stem_tcp_kernel(const StemTcArgs 
                     for (int kx = 0; kx < 3; ++kx) {
                         const bool ok = row_ok && okx[kx];
 #pragma unroll
-                        for (int ci = 0; ci < 3; ++ci) {                       // BGR bytes -> RGB taps; 2^23 + 128 + (x - 128) trick
+                        for (int ci = 0; ci < 3; ++ci) {                       // BGR bytes -> RGB taps; one PRMT builds 2^23 + x
                             const int i = kx * 3 + (2 - ci);
                             const uint32_t src = i < 4 ? v0 : i < 8 ? v1 : v2;
                             const uint32_t bits = __byte_perm(src, 0x4B000000u, 0x7540u + (uint32_t)(i & 3));
@@ -687,65 +428,40 @@ static int launch_stem_tc(const uint8_t *img, const float *w, const float *b, vo
     const long long rows_out = 128 / wo + 2;
     long long span = ((rows_out - 1) * stride + 3) * (long long)wd * 3 + 32;
     span = (span + 127) & ~127ll;
-    // Segmented spans (per piece the columns of <= 128 output pixels + window + alignment slack) where whole rows do not fit the
-    // shared-memory budget (images wider than ~2700 pixels; before, those fell back to the SIMT kernel).  Where both fit whole
-    // rows are faster although they fetch several times the bytes -- one bulk copy per tile instead of six, less address
-    // arithmetic in front of the MMAs: 0.177 vs 0.193 ms at 1281 x 721 x 32, 0.096 vs 0.127 ms at 513 x 513 x 64 (the stem is
-    // bound by its per-tile chain, not by L2 traffic or occupancy).  PN_STEM_SEGMENTS=1 forces segments (tests), =0 forbids them.
+    // Whole rows or segments (see the kernel).  Measured with the pipelined kernel (us, whole rows with 2 slots / segments with 3):
+    // 513 x 513 x 64 -> 32: 79.9 / 83.5; 257 x 257 x 512 -> 24: 158.9 / 170.4; 1281 x 721 x 32 -> 16: 137.1 / 126.9 -- one bulk copy
+    // per tile beats six until the whole-row spans (19 KB there) leave only three CTAs per SM.  PN_STEM_SEGMENTS=1 forces
+    // segments (tests), =0 forbids them; PN_STEM_NBUF / PN_STEM_CTAS override the ring depth / CTAs per SM.
     const long long piece = (((127ll * stride + 3) * 3 + 30) + 15) & ~15ll;
-    const long long smem_rows = STC_A_BYTES + STC_W_BYTES + STC_NBUF * span + 128 + 128 + 1024;
+    auto smem_of = [](int nbuf, long long sp) { return 2ll * STC_A_BYTES + STC_W_BYTES + nbuf * sp + STP_CTRL_BYTES + 1024; };
     const char *e_seg = getenv("PN_STEM_SEGMENTS");
-    a.seg = (wo >= 128 && ((e_seg && e_seg[0] == '1') || (smem_rows > 200 * 1024 && !(e_seg && e_seg[0] == '0')))) ? 1 : 0;
+    const bool seg_ok = wo >= 128 && !(e_seg && e_seg[0] == '0');
+    a.seg = (wo >= 128 && e_seg && e_seg[0] == '1') || (seg_ok && smem_of(2, span) > 44 * 1024) ? 1 : 0;
     a.piece_cap = (int)piece;
     if (a.seg) span = (STC_PIECES * piece + 127) & ~127ll;
-    const long long smem = STC_A_BYTES + STC_W_BYTES + STC_NBUF * span + 128 + 128 + 1024;
+    int nbuf = a.seg ? 3 : 2;
+    if (const char *e = getenv("PN_STEM_NBUF")) nbuf = atoi(e);
+    if (nbuf < 2) nbuf = 2;
+    if (nbuf > STP_MAX_NBUF) nbuf = STP_MAX_NBUF;
+    while (nbuf > 2 && smem_of(nbuf, span) > 200 * 1024) --nbuf;
+    const long long smem = smem_of(nbuf, span);
     if (smem > 200 * 1024) return 1;                              // does not fit: caller falls back to the SIMT kernel
     a.span_cap = (int)span;
-    a.nbuf = STC_NBUF;
-    const int dev = current_device();
-    const long long tiles_all = (a.total_px + 127) / 128;
-    const char *e_pipe = getenv("PN_STEM_PIPE");
-    if (!(e_pipe && e_pipe[0] == '0')) {
-        // the pipelined kernel (default): A twice, a span ring of 2-4 slots (PN_STEM_NBUF; 2 is the measured default)
-        int nbuf = 2;
-        if (const char *e = getenv("PN_STEM_NBUF")) nbuf = atoi(e);
-        if (nbuf < 2) nbuf = 2;
-        if (nbuf > STP_MAX_NBUF) nbuf = STP_MAX_NBUF;
-        long long smem_p = 2 * STC_A_BYTES + STC_W_BYTES + nbuf * span + STP_CTRL_BYTES + 1024;
-        while (nbuf > 2 && smem_p > 200 * 1024) {
-            --nbuf;
-            smem_p = 2 * STC_A_BYTES + STC_W_BYTES + nbuf * span + STP_CTRL_BYTES + 1024;
-        }
-        if (smem_p <= 200 * 1024) {
-            a.nbuf = nbuf;
-            static DeviceOnce once_p;
-            if (once_p.get(dev) < (int)smem_p) {
-                PN_CHECK_CUDA(cudaFuncSetAttribute(stem_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-                once_p.set(dev, (int)smem_p);
-            }
-            int per_sm = (int)((220 * 1024) / smem_p);
-            if (per_sm > 8) per_sm = 8;                           // 8 x 64 accumulator columns = all of TMEM
-            if (per_sm < 1) per_sm = 1;
-            if (const char *e = getenv("PN_STEM_CTAS")) per_sm = atoi(e) > 0 && atoi(e) < per_sm ? atoi(e) : per_sm;
-            const long long max_ctas = (long long)num_sms() * per_sm;
-            const int grid = (int)(tiles_all < max_ctas ? tiles_all : max_ctas);
-            PN_CHECK_CUDA(launch_pdl(stem_tcp_kernel, dim3(grid), dim3(STP_THREADS), (size_t)smem_p, st, a));
-            return PN_OK;
-        }
-        a.nbuf = STC_NBUF;                                        // only the single-A kernel fits
-    }
+    a.nbuf = nbuf;
     static DeviceOnce once;                                       // largest dynamic shared memory size configured, per device
+    const int dev = current_device();
     if (once.get(dev) < (int)smem) {
         PN_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         once.set(dev, (int)smem);
     }
     const long long tiles = (a.total_px + 127) / 128;
     int per_sm = (int)((220 * 1024) / smem);
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 8) per_sm = 8;                                   // 8 x 64 accumulator columns = all of TMEM
     if (per_sm < 1) per_sm = 1;
+    if (const char *e = getenv("PN_STEM_CTAS")) per_sm = atoi(e) > 0 && atoi(e) < per_sm ? atoi(e) : per_sm;
     const long long max_ctas = (long long)num_sms() * per_sm;
     const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
-    PN_CHECK_CUDA(launch_pdl(stem_tc_kernel, dim3(grid), dim3(STC_THREADS), (size_t)smem, st, a));
+    PN_CHECK_CUDA(launch_pdl(stem_tc_kernel, dim3(grid), dim3(STP_THREADS), (size_t)smem, st, a));
     return PN_OK;
 }
 

@@ -7,11 +7,8 @@ import abi
 from posenet import _native as nat
 torch.cuda.set_device(0)
 GEO = {"c2": (64, 513, 513, 32), "c3": (32, 721, 1281, 16), "c4": (512, 257, 257, 24)}
-VARIANTS = [("pipe nbuf2", {}), ("pipe nbuf3", {"PN_STEM_NBUF": "3"}), ("pipe nbuf2 ctas4", {"PN_STEM_CTAS": "4"}),
-            ("pipe nbuf2 segments", {"PN_STEM_SEGMENTS": "1"}), ("pipe nbuf3 segments", {"PN_STEM_SEGMENTS": "1", "PN_STEM_NBUF": "3"}),
-            ("pipe nbuf4 segments", {"PN_STEM_SEGMENTS": "1", "PN_STEM_NBUF": "4"}),
-            ("pipe nbuf3 seg ctas6", {"PN_STEM_SEGMENTS": "1", "PN_STEM_NBUF": "3", "PN_STEM_CTAS": "6"}),
-            ("chain (old)", {"PN_STEM_PIPE": "0"})]
+VARIANTS = [("default", {}), ("rows nbuf2", {"PN_STEM_SEGMENTS": "0", "PN_STEM_NBUF": "2"}), ("rows nbuf3", {"PN_STEM_SEGMENTS": "0", "PN_STEM_NBUF": "3"}),
+            ("segments nbuf3", {"PN_STEM_SEGMENTS": "1", "PN_STEM_NBUF": "3"}), ("segments nbuf4", {"PN_STEM_SEGMENTS": "1", "PN_STEM_NBUF": "4"})]
 for name, (n, h, w, cout) in GEO.items():
     xs = [torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda") for _ in range(4)]   # rotate inputs: > L2 with the outputs
     w27 = torch.randn(27, cout, device="cuda") * 0.25
