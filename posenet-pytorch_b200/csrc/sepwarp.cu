@@ -14,6 +14,9 @@
 //     into mma.sync.m16n8k16 fragments (ldmatrix), the pointwise weights come from shared memory the same way, and the
 //     fp32 accumulators get bias + ReLU6 and leave as 16-byte coalesced global stores (whole 128 B pixel rows).
 // The GEMM is 1 % of a tcgen05 tile, so the legacy warp-level tensor path is the right size for it; no TMEM, no CTA barrier.
+// QTR (cin <= 16, model 50's first block): eight lanes cover a pixel's channel pairs, so a quarter-warp owns pixels q and q + 4
+// of the strip instead of a half-warp owning every other pixel with half its lanes on zero-filled channels; the TMA box
+// is 16 channels wide (32-byte pixels, so the four quarters still read 128 contiguous bytes).  Same taps in the same order.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -66,7 +69,7 @@ __device__ __forceinline__ void swp_sts_u32(uint32_t addr, uint32_t v) {
 
 // KS_T / NT_T: compile-time k16 slices and n8 tiles of the pointwise GEMM (0 = take them from the geometry at run time); the
 // common widths get a fully unrolled tensor phase with immediate shared-memory offsets.
-template <int KS_T, int NT_T>
+template <int KS_T, int NT_T, bool QTR = false>
 __global__ void __launch_bounds__(SWP_THREADS, 1)
 sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restrict__ dw_w, const float *__restrict__ dw_b,
                const __nv_bfloat16 *__restrict__ pw_w, const float *__restrict__ pw_b, __nv_bfloat16 *__restrict__ y, const SwpGeom g) {
@@ -98,7 +101,11 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
     pdl_wait();                                                           // the weight staging above overlapped the stem's tail
 
     // ---- per lane: pixel parity, channel pair, the 9 x 2 depthwise weights + bias in registers for the whole kernel
-    const int hsel = lane >> 4, cp = lane & 15;
+    // NP pixels per lane, PSTEP strip pixels apart, NC window columns per row; window column of (pixel p, tap kx) = PSTEP p + kx
+    constexpr int NP = QTR ? 2 : 4, PSTEP = QTR ? 4 : 2, NC = QTR ? 6 : 9;
+    constexpr uint32_t PIXB = QTR ? 32u : (uint32_t)SWP_PIX;          // bytes per patch pixel (TMA box: 16 / 32 channels)
+    constexpr uint32_t CHUNK_TX = SWP_ROWS * SWP_COLS * PIXB;          // bytes a chunk's box delivers
+    const int hsel = QTR ? (lane >> 3) : (lane >> 4), cp = QTR ? (lane & 7) : (lane & 15);
     float2 wk[9], bias2;
     {
         const bool ok = 2 * cp < g.k;                                    // k is a multiple of 8: the pair is in or out as a whole
@@ -108,7 +115,7 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
     }
     auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
     const int ks_n = KS_T ? KS_T : g.ks, nt_n = NT_T ? NT_T : g.nt;
-    const uint32_t lane_off = (uint32_t)hsel * SWP_PIX + (uint32_t)cp * 4u;
+    const uint32_t lane_off = (uint32_t)hsel * PIXB + (uint32_t)cp * 4u;
     const uint32_t a_lane_addr = sA + (uint32_t)hsel * SWP_A_STRIDE + (uint32_t)cp * 4u;                 // + (half * 8 + 2 p) rows
     const uint32_t a_ld_addr = sA + (uint32_t)(lane & 15) * SWP_A_STRIDE + (uint32_t)(lane >> 4) * 16u;    // ldmatrix row / k-chunk
     const uint32_t w_ld_addr = sW + (uint32_t)(lane & 7) * SWP_W_STRIDE + (uint32_t)(lane >> 3) * 16u;     // + nt * 8 rows
@@ -143,7 +150,7 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
         }
         if (p_item >= g.items) return;
         const uint32_t s_ = p_chunks & 1u;
-        mbar_expect_tx(bars + 8u * s_, SWP_CHUNK);
+        mbar_expect_tx(bars + 8u * s_, CHUNK_TX);
         tma_load_4d(sRing + s_ * SWP_CHUNK, &tmap_x, bars + 8u * s_, 0, pit.x0 - 1, pit.y0 - 1 + p_ci * SWP_ROWS, pit.img);
         ++p_chunks;
         ++p_ci;
@@ -165,7 +172,7 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
         char *o_pair = reinterpret_cast<char *>(y) + ((((size_t)img * g.h + y0) * g.w + (x0 + (lane >> 3))) * g.nc + (lane & 7) * 8) * 2;
         const bool ok_lo = (lane & 7) < nt_n && (lane >> 3) < ncol_ok, ok_hi = (lane & 7) < nt_n && (lane >> 3) + 4 < ncol_ok;
         const uint32_t so_lane = sO + (uint32_t)(lane >> 3) * SWP_O_STRIDE + (uint32_t)(lane & 7) * 16u;
-        float2 ring[3][9];
+        float2 ring[3][NC];
         uint32_t stage_addr = 0;
 #pragma unroll 1
         for (int r0 = 0; r0 < rows_in; r0 += 3) {
@@ -181,29 +188,31 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
                     stage_addr = sRing + s * SWP_CHUNK + lane_off;
                 }
                 {   // input row r enters the window
-                    const uint32_t rp = stage_addr + (uint32_t)rr * (SWP_COLS * SWP_PIX);
+                    const uint32_t rp = stage_addr + (uint32_t)rr * (SWP_COLS * PIXB);
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) ring[j][c] = unpack(swp_lds_u32(rp + (uint32_t)c * SWP_PIX));
+                    for (int c = 0; c < NC; ++c) ring[j][c] = unpack(swp_lds_u32(rp + (uint32_t)(QTR ? (c / 3) * 4 + c % 3 : c) * PIXB));
                 }
                 // the chunk's last row is in registers once this row's output is computed: then its stage is refilled
                 const bool refill = (rr == SWP_ROWS - 1 || r == rows_in - 1);
                 if (r < 2) continue;                                      // (rows_in >= 3: no refill point among rows 0, 1)
                 const int t = r - 2;                                      // output row of the block: window rows r-2, r-1, r
-                float2 acc[4] = {bias2, bias2, bias2, bias2};
+                float2 acc[NP];
+#pragma unroll
+                for (int p = 0; p < NP; ++p) acc[p] = bias2;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
                     const int slot = (j + 1 + ky) % 3;                    // rows r-2, r-1, r live in slots (j+1)%3, (j+2)%3, j
 #pragma unroll
-                    for (int c = 0; c < 9; ++c)
+                    for (int c = 0; c < NC; ++c)
 #pragma unroll
-                        for (int p = 0; p < 4; ++p)
+                        for (int p = 0; p < NP; ++p)
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx)
-                                if (2 * p + kx == c) acc[p] = ffma2(ring[slot][c], wk[ky * 3 + kx], acc[p]);
+                                if ((QTR ? 3 * p + kx : 2 * p + kx) == c) acc[p] = ffma2(ring[slot][c], wk[ky * 3 + kx], acc[p]);
                 }
                 const uint32_t arow = a_lane_addr + (uint32_t)((t & 1) * 8) * SWP_A_STRIDE;
 #pragma unroll
-                for (int p = 0; p < 4; ++p) swp_sts_u32(arow + (uint32_t)(2 * p) * SWP_A_STRIDE, relu6_bf16x2(acc[p]));
+                for (int p = 0; p < NP; ++p) swp_sts_u32(arow + (uint32_t)(PSTEP * p) * SWP_A_STRIDE, relu6_bf16x2(acc[p]));
                 if ((t & 1) || t == rows_out - 1) {
                 // ---- two output rows (or the last single one) are staged: 16 pixels x cin -> pointwise GEMM on mma.sync
                 __syncwarp();
@@ -290,7 +299,7 @@ int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, i
     if (rc != PN_OK) return rc;
     const uint64_t dims[4] = {(uint64_t)k, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)k * 2, (uint64_t)wd * k * 2, (uint64_t)h * wd * k * 2};
-    const uint32_t box[4] = {32u, (uint32_t)SWP_COLS, (uint32_t)SWP_ROWS, 1u};
+    const uint32_t box[4] = {k <= 16 ? 16u : 32u, (uint32_t)SWP_COLS, (uint32_t)SWP_ROWS, 1u};   // (k <= 16: the QTR kernel's 32-byte pixels)
     return encode_tmap(op->tmap_x, x, 2, 4, dims, strides, box, 0);
 }
 
@@ -313,10 +322,11 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
                                  (const __nv_bfloat16 *)pw_w, pw_b, (__nv_bfloat16 *)y, g));
         return PN_OK;
     };
-    static DeviceOnce c28, c26, c14, c00;
+    static DeviceOnce c28, c26, c14, c00, c00q;
     if (g.ks == 2 && g.nt == 8) return launch(sepwarp_kernel<2, 8>, c28);      // 32 -> 64 (model 100 / 101)
     if (g.ks == 2 && g.nt == 6) return launch(sepwarp_kernel<2, 6>, c26);      // 24 -> 48 (model 75)
-    if (g.ks == 1 && g.nt == 4) return launch(sepwarp_kernel<1, 4>, c14);      // 16 -> 32 (model 50)
+    if (g.ks == 1 && g.nt == 4) return launch(sepwarp_kernel<1, 4, true>, c14);      // 16 -> 32 (model 50)
+    if (g.k <= 16) return launch(sepwarp_kernel<0, 0, true>, c00q);
     return launch(sepwarp_kernel<0, 0>, c00);
 }
 

@@ -24,7 +24,7 @@ SHAPES = [  # n, h, w, cin, cout, stride, dilation
     (2, 65, 65, 256, 256, 1, 1), (2, 65, 65, 256, 512, 2, 1), (3, 33, 33, 512, 512, 1, 1), (2, 33, 33, 512, 1024, 1, 1),
     (2, 33, 33, 1024, 1024, 1, 2),
     # model 50 @ OS8 (config 3 geometry, reduced) incl. cin 16 / 32 with stride 2, and dilation 2
-    (1, 91, 161, 16, 32, 1, 1), (1, 91, 161, 32, 64, 2, 1), (1, 46, 81, 64, 64, 1, 1), (1, 46, 81, 128, 256, 1, 1),
+    (1, 91, 161, 16, 32, 1, 1), (1, 361, 641, 16, 32, 1, 1), (2, 37, 53, 16, 48, 1, 1), (1, 91, 161, 32, 64, 2, 1), (1, 46, 81, 64, 64, 1, 1), (1, 46, 81, 128, 256, 1, 1),
     (1, 46, 81, 256, 256, 1, 2),
     # model 75 (config 4): channel counts that are not multiples of 64 (ragged K and N tiles)
     (3, 129, 129, 24, 48, 1, 1), (3, 129, 129, 48, 96, 2, 1), (3, 65, 65, 96, 96, 1, 1), (3, 65, 65, 96, 192, 2, 1),
