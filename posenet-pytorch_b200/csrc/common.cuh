@@ -174,14 +174,14 @@ struct GemmTc {
 int gemm_tc_prepare(GemmTc *g, const void *a, const void *w, void *y, int m, int k, int n, int epi);
 int gemm_tc_launch(const GemmTc *g, const EpiParams &ep, cudaStream_t s);
 
-// narrow fused block (cin <= 32, cout <= 64, stride 1, dilation 1): warp-autonomous kernel (sepwarp.cu)
+// narrow fused block (cin <= 32, cout <= 64, dilation 1; stride 1, or stride 2 with cin > 16): warp-autonomous kernel (sepwarp.cu)
 struct SepWarpOp {
     alignas(64) unsigned char tmap_x[128];
     alignas(8) unsigned char geom[64];
 };
 bool sepwarp_supported(int k, int nc, int stride, int dil);
-int sepwarp_geometry(SepWarpOp *op, int n, int h, int wd, int k, int nc);
-int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, int nc);
+int sepwarp_geometry(SepWarpOp *op, int n, int h, int wd, int k, int nc, int stride);
+int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, int nc, int stride);
 int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, const void *pw_w, const float *pw_b, void *y,
                    cudaStream_t s);
 void sepwarp_describe(const SepWarpOp *op, char *out, size_t cap);

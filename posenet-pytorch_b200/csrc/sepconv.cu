@@ -838,7 +838,7 @@ int sep_geometry(SepOp *op, int n, int h, int wd, int k, int nc, int stride, int
     if (sepwarp_supported(k, nc, stride, dil)) {                    // narrow block: warp-autonomous kernel, no tile geometry
         op->warp_kind = true;
         op->stride = stride; op->dil = dil;
-        op->ho = h; op->wo = wd;
+        op->ho = (h - 1) / stride + 1; op->wo = (wd - 1) / stride + 1;
         op->n = n; op->h = h; op->w = wd; op->k = k; op->nc = nc;
         return PN_OK;
     }
@@ -1099,7 +1099,7 @@ int sep_prepare(SepOp *op, const void *x, const float *dw_w, const float *dw_b, 
     if (rc != PN_OK) return rc;
     if (op->warp_kind) {
         op->dw_w = dw_w; op->dw_b = dw_b; op->pw_w = pw_w; op->y = y;
-        return sepwarp_prepare(&op->warp, x, n, h, wd, k, nc);
+        return sepwarp_prepare(&op->warp, x, n, h, wd, k, nc, stride);
     }
     if (op->tc_kind) {
         op->dw_w = dw_w; op->dw_b = dw_b; op->pw_w = pw_w; op->y = y;
@@ -1209,7 +1209,7 @@ void sep_describe(const SepOp *op, char *out, size_t cap) {
     }
     if (op->warp_kind) {
         SepWarpOp w;
-        if (sepwarp_geometry(&w, op->n, op->h, op->w, op->k, op->nc) == PN_OK) sepwarp_describe(&w, out, cap);
+        if (sepwarp_geometry(&w, op->n, op->h, op->w, op->k, op->nc, op->stride) == PN_OK) sepwarp_describe(&w, out, cap);
         else snprintf(out, cap, "warp-autonomous (geometry unavailable)");
         return;
     }

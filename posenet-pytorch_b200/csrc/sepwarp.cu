@@ -1,5 +1,5 @@
-// B3 + B4 fused for the NARROW blocks (cin <= 32, cout <= 64, stride 1, dilation 1 -- the first SeperableConv block of every
-// model, posenet/models/mobilenet_v1.py:57-68), as warp-autonomous pipelines.
+// B3 + B4 fused for the NARROW blocks (cin <= 32, cout <= 64, dilation 1: the first SeperableConv block of every model, stride 1,
+// and model 50's second, 32 -> 64 stride 2; posenet/models/mobilenet_v1.py:57-68), as warp-autonomous pipelines.
 //
 // In these blocks a 128-pixel tile carries so little work (128 x 32 x 9 depthwise MACs, a 128 x 64 x 32 GEMM) that the
 // hand-offs of the CTA-wide pipeline in sepconv.cu (TMA -> depthwise warps -> tcgen05 -> epilogue warps, ~1.3k cycles of
@@ -14,6 +14,10 @@
 //     into mma.sync.m16n8k16 fragments (ldmatrix), the pointwise weights come from shared memory the same way, and the
 //     fp32 accumulators get bias + ReLU6 and leave as 16-byte coalesced global stores (whole 128 B pixel rows).
 // The GEMM is 1 % of a tcgen05 tile, so the legacy warp-level tensor path is the right size for it; no TMEM, no CTA barrier.
+// Stride 2 (S = 2): a strip's 8 output pixels read 17 input columns and every output row two new input rows, so the chunks are
+// 4 input rows x 17 pixels; of an output row's three input rows the last is carried over in registers (unpacked) as the next
+// row's first and the other two pass through once.  (The CTA pipeline of sepconv.cu ran this block with half of every depthwise
+// warp's lanes on zero-filled channels and one item per tile: 0.207 ms at 1281 x 721 x 32.)
 // QTR (cin <= 16, model 50's first block): eight lanes cover a pixel's channel pairs, so a quarter-warp owns pixels q and q + 4
 // of the strip instead of a half-warp owning every other pixel with half its lanes on zero-filled channels; the TMA box
 // is 16 channels wide (32-byte pixels, so the four quarters still read 128 contiguous bytes).  Same taps in the same order.
@@ -30,6 +34,7 @@ constexpr int SWP_WARPS = 16;
 constexpr int SWP_THREADS = SWP_WARPS * 32;
 constexpr int SWP_ROWS = 8;                               // input rows per TMA chunk
 constexpr int SWP_COLS = 10;                              // 8 output pixels + 2 halo columns
+constexpr int SWP_ROWS2 = 4, SWP_COLS2 = 17;              // stride 2: input rows per chunk, 2 * 8 + 1 input columns
 constexpr int SWP_PIX = 64;                               // bytes per patch pixel (32 channels bf16)
 constexpr int SWP_CHUNK = SWP_ROWS * SWP_COLS * SWP_PIX;  // 5120
 constexpr int SWP_A_STRIDE = 80;                          // A staging: 16 pixel rows x (32 ch bf16 + 16 B pad), ldmatrix conflict-free
@@ -40,7 +45,8 @@ constexpr int SWP_SHARED = 64 * SWP_W_STRIDE + 64 * 4;    // weights + bias
 constexpr int SWP_SMEM = SWP_WARPS * SWP_WARP_SMEM + SWP_SHARED + 1024;
 
 struct SwpGeom {
-    int n, h, w, k, nc;
+    int n, h, w, k, nc;            // h, w: OUTPUT rows / columns (= the input's for stride 1)
+    int s;                         // stride (1 | 2)
     int strips, nq, rb;            // 8-pixel column strips per image row, row blocks per strip, output rows per block
     int ks, nt;                    // k16 slices (1 or 2), n8 tiles (cout / 8)
     int items;                     // n * strips * nq (< 2^31: 32-bit index arithmetic in the kernel)
@@ -69,7 +75,7 @@ __device__ __forceinline__ void swp_sts_u32(uint32_t addr, uint32_t v) {
 
 // KS_T / NT_T: compile-time k16 slices and n8 tiles of the pointwise GEMM (0 = take them from the geometry at run time); the
 // common widths get a fully unrolled tensor phase with immediate shared-memory offsets.
-template <int KS_T, int NT_T, bool QTR = false>
+template <int KS_T, int NT_T, bool QTR = false, int S = 1>
 __global__ void __launch_bounds__(SWP_THREADS, 1)
 sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restrict__ dw_w, const float *__restrict__ dw_b,
                const __nv_bfloat16 *__restrict__ pw_w, const float *__restrict__ pw_b, __nv_bfloat16 *__restrict__ y, const SwpGeom g) {
@@ -102,9 +108,15 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
 
     // ---- per lane: pixel parity, channel pair, the 9 x 2 depthwise weights + bias in registers for the whole kernel
     // NP pixels per lane, PSTEP strip pixels apart, NC window columns per row; window column of (pixel p, tap kx) = PSTEP p + kx
-    constexpr int NP = QTR ? 2 : 4, PSTEP = QTR ? 4 : 2, NC = QTR ? 6 : 9;
+    // Stride 2 (S == 2; cin 17..32 -> the second block of model 50): a lane's four output pixels read input columns 4 p + kx
+    // (+ 2 for the odd half), two new input rows per output row, chunks of 4 input rows x 17 columns.
+    static_assert(S == 1 || (S == 2 && !QTR), "stride 2 uses the half-warp layout");
+    constexpr int NP = QTR ? 2 : 4, PSTEP = QTR ? 4 : 2, NC = S == 2 ? 12 : QTR ? 6 : 9;
+    constexpr bool COL4 = QTR || S == 2;                               // window column c sits at pixel (c / 3) * 4 + c % 3 (else at c)
     constexpr uint32_t PIXB = QTR ? 32u : (uint32_t)SWP_PIX;          // bytes per patch pixel (TMA box: 16 / 32 channels)
-    constexpr uint32_t CHUNK_TX = SWP_ROWS * SWP_COLS * PIXB;          // bytes a chunk's box delivers
+    constexpr int ROWS = S == 2 ? SWP_ROWS2 : SWP_ROWS, COLS = S == 2 ? SWP_COLS2 : SWP_COLS;
+    constexpr uint32_t CHUNK_TX = ROWS * COLS * PIXB;                  // bytes a chunk's box delivers
+    static_assert(SWP_ROWS2 * SWP_COLS2 * SWP_PIX <= SWP_CHUNK, "a stride-2 chunk fits the ring stage");
     const int hsel = QTR ? (lane >> 3) : (lane >> 4), cp = QTR ? (lane & 7) : (lane & 15);
     float2 wk[9], bias2;
     {
@@ -115,7 +127,7 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
     }
     auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
     const int ks_n = KS_T ? KS_T : g.ks, nt_n = NT_T ? NT_T : g.nt;
-    const uint32_t lane_off = (uint32_t)hsel * PIXB + (uint32_t)cp * 4u;
+    const uint32_t lane_off = (uint32_t)(hsel * S) * PIXB + (uint32_t)cp * 4u;
     const uint32_t a_lane_addr = sA + (uint32_t)hsel * SWP_A_STRIDE + (uint32_t)cp * 4u;                 // + (half * 8 + 2 p) rows
     const uint32_t a_ld_addr = sA + (uint32_t)(lane & 15) * SWP_A_STRIDE + (uint32_t)(lane >> 4) * 16u;    // ldmatrix row / k-chunk
     const uint32_t w_ld_addr = sW + (uint32_t)(lane & 7) * SWP_W_STRIDE + (uint32_t)(lane >> 3) * 16u;     // + nt * 8 rows
@@ -134,7 +146,7 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
         t.y0 = (rest % g.nq) * g.rb;
         t.img = rest / g.nq;
         t.rows_out = min(g.rb, g.h - t.y0);
-        t.nchunks = t.rows_out > 0 ? (t.rows_out + 2 + SWP_ROWS - 1) / SWP_ROWS : 0;
+        t.nchunks = t.rows_out > 0 ? (S * t.rows_out + 3 - S + ROWS - 1) / ROWS : 0;     // input rows: S (rows_out - 1) + 3
         return t;
     };
     // Lane 0 runs a producer cursor two chunks ahead of the consumer, across item boundaries, so the ring does not drain
@@ -151,7 +163,7 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
         if (p_item >= g.items) return;
         const uint32_t s_ = p_chunks & 1u;
         mbar_expect_tx(bars + 8u * s_, CHUNK_TX);
-        tma_load_4d(sRing + s_ * SWP_CHUNK, &tmap_x, bars + 8u * s_, 0, pit.x0 - 1, pit.y0 - 1 + p_ci * SWP_ROWS, pit.img);
+        tma_load_4d(sRing + s_ * SWP_CHUNK, &tmap_x, bars + 8u * s_, 0, S * pit.x0 - 1, S * pit.y0 - 1 + p_ci * ROWS, pit.img);
         ++p_chunks;
         ++p_ci;
     };
@@ -164,7 +176,7 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
         const Item it = decode(item);
         const int x0 = it.x0, y0 = it.y0, img = it.img, rows_out = it.rows_out;
         if (rows_out <= 0) continue;
-        const int rows_in = rows_out + 2;
+        const int rows_in = S * (rows_out - 1) + 3;
         const int ncol_ok = g.w - x0;                                     // strip pixels px < ncol_ok exist
         // output addressing for the 16-byte stores of the tensor phase: lane -> (pixel lane >> 3 (+4), 8 channels lane & 7); one
         // 64-bit pointer per lane, advanced by two output rows per phase
@@ -172,90 +184,117 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
         char *o_pair = reinterpret_cast<char *>(y) + ((((size_t)img * g.h + y0) * g.w + (x0 + (lane >> 3))) * g.nc + (lane & 7) * 8) * 2;
         const bool ok_lo = (lane & 7) < nt_n && (lane >> 3) < ncol_ok, ok_hi = (lane & 7) < nt_n && (lane >> 3) + 4 < ncol_ok;
         const uint32_t so_lane = sO + (uint32_t)(lane >> 3) * SWP_O_STRIDE + (uint32_t)(lane & 7) * 16u;
-        float2 ring[3][NC];
         uint32_t stage_addr = 0;
+        // input row r of the item: wait for its chunk when it is the chunk's first row; returns the lane's address of the row
+        auto enter_row = [&](const int r) {
+            const int ci = r / ROWS, rr = r % ROWS;
+            if (rr == 0) {
+                const uint32_t s_ = (chunk_ctr + (uint32_t)ci) & 1u;
+                mbar_wait(bars + 8u * s_, (phase_bits >> s_) & 1u);
+                phase_bits ^= 1u << s_;
+                stage_addr = sRing + s_ * SWP_CHUNK + lane_off;
+            }
+            return stage_addr + (uint32_t)rr * (COLS * PIXB);
+        };
+        // ... and once the chunk's last row is in registers (its FMAs issued by every lane) the stage is refilled
+        auto leave_row = [&](const int r) {
+            if (r % ROWS == ROWS - 1 || r == rows_in - 1) {
+                __syncwarp();
+                if (lane == 0) issue_next();                              // (of this item or the next)
+            }
+        };
+        auto load_row = [&](const uint32_t rp, float2 (&row)[NC]) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) row[c] = unpack(swp_lds_u32(rp + (uint32_t)(COL4 ? (c / 3) * 4 + c % 3 : c) * PIXB));
+        };
+        auto fma_row = [&](const float2 (&row)[NC], const int ky, float2 (&acc)[NP]) {   // taps (ky, 0..2) of every pixel, kx ascending
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+                        if ((COL4 ? 3 * p + kx : 2 * p + kx) == c) acc[p] = ffma2(row[c], wk[ky * 3 + kx], acc[p]);
+        };
+        // depthwise row t of the item -> A staging; after two rows (or the last single one): 16 pixels x cin -> pointwise GEMM on
+        // mma.sync -> output staging -> 16-byte coalesced stores
+        auto finish_row = [&](const int t, const float2 (&acc)[NP]) {
+            const uint32_t arow = a_lane_addr + (uint32_t)((t & 1) * 8) * SWP_A_STRIDE;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) swp_sts_u32(arow + (uint32_t)(PSTEP * p) * SWP_A_STRIDE, relu6_bf16x2(acc[p]));
+            if (!((t & 1) || t == rows_out - 1)) return;
+            __syncwarp();
+            uint32_t a0[4], a1[4] = {0u, 0u, 0u, 0u};
+            ldmatrix_x4(a_ld_addr, a0);
+            if (ks_n > 1) ldmatrix_x4(a_ld_addr + 32u, a1);
+            auto tile_n = [&](const int nt) {
+                uint32_t b[4];
+                ldmatrix_x4(w_ld_addr + (uint32_t)(nt * 8) * SWP_W_STRIDE, b);
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_bf16_16816(d, a0, b[0], b[1]);
+                if (ks_n > 1) mma_bf16_16816(d, a1, b[2], b[3]);
+                float2 bv;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bv.x), "=f"(bv.y) : "r"(sBias + (uint32_t)(nt * 8 + 2 * qq) * 4u));
+                const uint32_t o = sO + (uint32_t)gq * SWP_O_STRIDE + (uint32_t)(nt * 16 + qq * 4);
+                swp_sts_u32(o, relu6_bf16x2(fadd2(make_float2(d[0], d[1]), bv)));
+                swp_sts_u32(o + 8u * SWP_O_STRIDE, relu6_bf16x2(fadd2(make_float2(d[2], d[3]), bv)));
+            };
+            if (NT_T) {
+#pragma unroll
+                for (int nt = 0; nt < (NT_T ? NT_T : 1); ++nt) tile_n(nt);
+            } else {
+#pragma unroll 2
+                for (int nt = 0; nt < nt_n; ++nt) tile_n(nt);
+            }
+            __syncwarp();
+            // 8 lanes cover one pixel's channels, 4 pixels per instruction (staging row = output-row parity * 8 + pixel); the
+            // second row exists when the pair is complete
+            const bool two = (t & 1) != 0;
+            char *o1 = o_pair + 4 * pix_bytes, *o2 = o_pair + row_bytes, *o3 = o2 + 4 * pix_bytes;
+            swp_stg_v4_if(o_pair, ld_shared_v4(so_lane), ok_lo);
+            swp_stg_v4_if(o1, ld_shared_v4(so_lane + 4u * SWP_O_STRIDE), ok_hi);
+            swp_stg_v4_if(o2, ld_shared_v4(so_lane + 8u * SWP_O_STRIDE), ok_lo && two);
+            swp_stg_v4_if(o3, ld_shared_v4(so_lane + 12u * SWP_O_STRIDE), ok_hi && two);
+            o_pair += 2 * row_bytes;
+            __syncwarp();                                                 // staging buffers are rewritten by the next rows
+        };
+        if constexpr (S == 1) {
+            float2 ring[3][NC];                                           // input rows r-2, r-1, r live in slots (j+1)%3, (j+2)%3, j
 #pragma unroll 1
-        for (int r0 = 0; r0 < rows_in; r0 += 3) {
+            for (int r0 = 0; r0 < rows_in; r0 += 3) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int r = r0 + j;
-                if (r >= rows_in) break;
-                const int ci = r >> 3, rr = r & 7;
-                if (rr == 0) {                                            // entering a new chunk: wait for its bytes
-                    const uint32_t s = (chunk_ctr + (uint32_t)ci) & 1u;
-                    mbar_wait(bars + 8u * s, (phase_bits >> s) & 1u);
-                    phase_bits ^= 1u << s;
-                    stage_addr = sRing + s * SWP_CHUNK + lane_off;
-                }
-                {   // input row r enters the window
-                    const uint32_t rp = stage_addr + (uint32_t)rr * (SWP_COLS * PIXB);
+                for (int j = 0; j < 3; ++j) {
+                    const int r = r0 + j;
+                    if (r >= rows_in) break;
+                    load_row(enter_row(r), ring[j]);
+                    if (r < 2) continue;                                  // (rows_in >= 3: no refill point among rows 0, 1)
+                    float2 acc[NP];
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) ring[j][c] = unpack(swp_lds_u32(rp + (uint32_t)(QTR ? (c / 3) * 4 + c % 3 : c) * PIXB));
+                    for (int p = 0; p < NP; ++p) acc[p] = bias2;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) fma_row(ring[(j + 1 + ky) % 3], ky, acc);
+                    finish_row(r - 2, acc);
+                    leave_row(r);
                 }
-                // the chunk's last row is in registers once this row's output is computed: then its stage is refilled
-                const bool refill = (rr == SWP_ROWS - 1 || r == rows_in - 1);
-                if (r < 2) continue;                                      // (rows_in >= 3: no refill point among rows 0, 1)
-                const int t = r - 2;                                      // output row of the block: window rows r-2, r-1, r
+            }
+        } else {
+            // output row t reads input rows 2t, 2t + 1, 2t + 2: the last one is carried over (unpacked) as the next row's first,
+            // the other two pass through registers once.  Same tap order as every other depthwise kernel (ky outer, kx inner).
+            float2 carry[NC], tmp[NC];
+            load_row(enter_row(0), carry);
+#pragma unroll 1
+            for (int t = 0; t < rows_out; ++t) {
                 float2 acc[NP];
 #pragma unroll
                 for (int p = 0; p < NP; ++p) acc[p] = bias2;
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int slot = (j + 1 + ky) % 3;                    // rows r-2, r-1, r live in slots (j+1)%3, (j+2)%3, j
-#pragma unroll
-                    for (int c = 0; c < NC; ++c)
-#pragma unroll
-                        for (int p = 0; p < NP; ++p)
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx)
-                                if ((QTR ? 3 * p + kx : 2 * p + kx) == c) acc[p] = ffma2(ring[slot][c], wk[ky * 3 + kx], acc[p]);
-                }
-                const uint32_t arow = a_lane_addr + (uint32_t)((t & 1) * 8) * SWP_A_STRIDE;
-#pragma unroll
-                for (int p = 0; p < NP; ++p) swp_sts_u32(arow + (uint32_t)(PSTEP * p) * SWP_A_STRIDE, relu6_bf16x2(acc[p]));
-                if ((t & 1) || t == rows_out - 1) {
-                // ---- two output rows (or the last single one) are staged: 16 pixels x cin -> pointwise GEMM on mma.sync
-                __syncwarp();
-                uint32_t a0[4], a1[4] = {0u, 0u, 0u, 0u};
-                ldmatrix_x4(a_ld_addr, a0);
-                if (ks_n > 1) ldmatrix_x4(a_ld_addr + 32u, a1);
-                auto tile_n = [&](const int nt) {
-                    uint32_t b[4];
-                    ldmatrix_x4(w_ld_addr + (uint32_t)(nt * 8) * SWP_W_STRIDE, b);
-                    float d[4] = {0.f, 0.f, 0.f, 0.f};
-                    mma_bf16_16816(d, a0, b[0], b[1]);
-                    if (ks_n > 1) mma_bf16_16816(d, a1, b[2], b[3]);
-                    float2 bv;
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bv.x), "=f"(bv.y) : "r"(sBias + (uint32_t)(nt * 8 + 2 * qq) * 4u));
-                    const uint32_t o = sO + (uint32_t)gq * SWP_O_STRIDE + (uint32_t)(nt * 16 + qq * 4);
-                    swp_sts_u32(o, relu6_bf16x2(fadd2(make_float2(d[0], d[1]), bv)));
-                    swp_sts_u32(o + 8u * SWP_O_STRIDE, relu6_bf16x2(fadd2(make_float2(d[2], d[3]), bv)));
-                };
-                if (NT_T) {
-#pragma unroll
-                    for (int nt = 0; nt < (NT_T ? NT_T : 1); ++nt) tile_n(nt);
-                } else {
-#pragma unroll 2
-                    for (int nt = 0; nt < nt_n; ++nt) tile_n(nt);
-                }
-                __syncwarp();
-                // 16-byte coalesced stores: 8 lanes cover one pixel's channels, 4 pixels per instruction (staging row =
-                // output-row parity * 8 + pixel); the second row exists when the pair is complete
-                {
-                    const bool two = (t & 1) != 0;
-                    char *o1 = o_pair + 4 * pix_bytes, *o2 = o_pair + row_bytes, *o3 = o2 + 4 * pix_bytes;
-                    swp_stg_v4_if(o_pair, ld_shared_v4(so_lane), ok_lo);
-                    swp_stg_v4_if(o1, ld_shared_v4(so_lane + 4u * SWP_O_STRIDE), ok_hi);
-                    swp_stg_v4_if(o2, ld_shared_v4(so_lane + 8u * SWP_O_STRIDE), ok_lo && two);
-                    swp_stg_v4_if(o3, ld_shared_v4(so_lane + 12u * SWP_O_STRIDE), ok_hi && two);
-                    o_pair += 2 * row_bytes;
-                }
-                __syncwarp();                                             // staging buffers are rewritten by the next rows
-                }
-                if (refill) {                                             // every lane has consumed the chunk (its FMAs are issued)
-                    __syncwarp();
-                    if (lane == 0) issue_next();                          // (of this item or the next)
-                }
+                fma_row(carry, 0, acc);
+                load_row(enter_row(2 * t + 1), tmp);
+                fma_row(tmp, 1, acc);
+                leave_row(2 * t + 1);
+                load_row(enter_row(2 * t + 2), carry);
+                fma_row(carry, 2, acc);
+                finish_row(t, acc);
+                leave_row(2 * t + 2);
             }
         }
         chunk_ctr += (uint32_t)it.nchunks;
@@ -264,28 +303,34 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
 
 // ---- host side ---------------------------------------------------------------------------------------------
 bool sepwarp_supported(int k, int nc, int stride, int dil) {
-    return stride == 1 && dil == 1 && k >= 8 && k <= 32 && k % 8 == 0 && nc >= 8 && nc <= 64 && nc % 8 == 0 &&
-           getenv("PN_NO_SEPWARP") == nullptr;
+    if (!(dil == 1 && k >= 8 && k <= 32 && k % 8 == 0 && nc >= 8 && nc <= 64 && nc % 8 == 0 && getenv("PN_NO_SEPWARP") == nullptr)) return false;
+    if (stride == 1) return true;
+    // stride 2: cin 17..32 (the half-warp layout; narrower blocks would idle half its lanes).  PN_SEPWARP_S2=0 sends these blocks
+    // back to the CTA pipeline of sepconv.cu.
+    const char *e = getenv("PN_SEPWARP_S2");
+    return stride == 2 && k > 16 && !(e && e[0] == '0');
 }
 
-// strips / row blocks / item count: pure host arithmetic (no CUDA calls beyond the cached SM count)
-int sepwarp_geometry(SepWarpOp *op, int n, int h, int wd, int k, int nc) {
-    PN_CHECK_ARG(n > 0 && h > 0 && wd > 0 && sepwarp_supported(k, nc, 1, 1), "pn_sepconv_block: bad narrow-block shape");
+// strips / row blocks / item count: pure host arithmetic (no CUDA calls beyond the cached SM count); h, wd: the INPUT map
+int sepwarp_geometry(SepWarpOp *op, int n, int h, int wd, int k, int nc, int stride) {
+    PN_CHECK_ARG(n > 0 && h > 0 && wd > 0 && sepwarp_supported(k, nc, stride, 1), "pn_sepconv_block: bad narrow-block shape");
     memset(op, 0, sizeof(*op));
     SwpGeom g;
     memset(&g, 0, sizeof(g));
-    g.n = n; g.h = h; g.w = wd; g.k = k; g.nc = nc;
-    g.strips = ceil_div(wd, 8);
+    g.n = n; g.k = k; g.nc = nc; g.s = stride;
+    g.h = (h - 1) / stride + 1;                                            // 3x3, pad 1: floor((h + 2 - 3) / s) + 1
+    g.w = (wd - 1) / stride + 1;
+    g.strips = ceil_div(g.w, 8);
     g.ks = ceil_div(k, 16);
     g.nt = nc / 8;
     // row blocks: about six items per warp of a full grid, at least 8 output rows each
     const long long warps = (long long)num_sms() * SWP_WARPS;
     long long nq = (6 * warps + (long long)n * g.strips - 1) / ((long long)n * g.strips);
-    const int max_nq = ceil_div(h, 8);
+    const int max_nq = ceil_div(g.h, 8);
     if (nq > max_nq) nq = max_nq;
     if (nq < 1) nq = 1;
-    g.rb = ceil_div(h, (int)nq);
-    g.nq = ceil_div(h, g.rb);
+    g.rb = ceil_div(g.h, (int)nq);
+    g.nq = ceil_div(g.h, g.rb);
     const long long items = (long long)n * g.strips * g.nq;
     PN_CHECK_ARG(items + (long long)num_sms() * SWP_WARPS < (1ll << 31), "pn_sepconv_block: problem too large for one launch");
     g.items = (int)items;
@@ -294,12 +339,14 @@ int sepwarp_geometry(SepWarpOp *op, int n, int h, int wd, int k, int nc) {
     return PN_OK;
 }
 
-int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, int nc) {
-    int rc = sepwarp_geometry(op, n, h, wd, k, nc);
+int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, int nc, int stride) {
+    int rc = sepwarp_geometry(op, n, h, wd, k, nc, stride);
     if (rc != PN_OK) return rc;
     const uint64_t dims[4] = {(uint64_t)k, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
     const uint64_t strides[3] = {(uint64_t)k * 2, (uint64_t)wd * k * 2, (uint64_t)h * wd * k * 2};
-    const uint32_t box[4] = {k <= 16 ? 16u : 32u, (uint32_t)SWP_COLS, (uint32_t)SWP_ROWS, 1u};   // (k <= 16: the QTR kernel's 32-byte pixels)
+    // (k <= 16, stride 1: the QTR kernel's 32-byte pixels; stride 2: chunks of 4 input rows x 17 columns)
+    const uint32_t box[4] = {(k <= 16 && stride == 1) ? 16u : 32u, (uint32_t)(stride == 2 ? SWP_COLS2 : SWP_COLS),
+                             (uint32_t)(stride == 2 ? SWP_ROWS2 : SWP_ROWS), 1u};
     return encode_tmap(op->tmap_x, x, 2, 4, dims, strides, box, 0);
 }
 
@@ -322,7 +369,11 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
                                  (const __nv_bfloat16 *)pw_w, pw_b, (__nv_bfloat16 *)y, g));
         return PN_OK;
     };
-    static DeviceOnce c28, c26, c14, c00, c00q;
+    static DeviceOnce c28, c26, c14, c00, c00q, s28, s00;
+    if (g.s == 2) {
+        if (g.ks == 2 && g.nt == 8) return launch(sepwarp_kernel<2, 8, false, 2>, s28);   // 32 -> 64 stride 2 (model 50)
+        return launch(sepwarp_kernel<0, 0, false, 2>, s00);
+    }
     if (g.ks == 2 && g.nt == 8) return launch(sepwarp_kernel<2, 8>, c28);      // 32 -> 64 (model 100 / 101)
     if (g.ks == 2 && g.nt == 6) return launch(sepwarp_kernel<2, 6>, c26);      // 24 -> 48 (model 75)
     if (g.ks == 1 && g.nt == 4) return launch(sepwarp_kernel<1, 4, true>, c14);      // 16 -> 32 (model 50)
@@ -333,8 +384,8 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
 void sepwarp_describe(const SepWarpOp *op, char *out, size_t cap) {
     SwpGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    snprintf(out, cap, "warp-autonomous strips %d x %d row blocks of %d rows, k16 slices %d, n8 tiles %d, items %d, smem %d", g.strips,
-             g.nq, g.rb, g.ks, g.nt, g.items, SWP_SMEM);
+    snprintf(out, cap, "warp-autonomous%s strips %d x %d row blocks of %d rows, k16 slices %d, n8 tiles %d, items %d, smem %d",
+             g.s == 2 ? " stride 2" : "", g.strips, g.nq, g.rb, g.ks, g.nt, g.items, SWP_SMEM);
 }
 
 }  // namespace pn

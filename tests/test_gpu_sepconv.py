@@ -26,6 +26,8 @@ SHAPES = [  # n, h, w, cin, cout, stride, dilation
     # model 50 @ OS8 (config 3 geometry, reduced) incl. cin 16 / 32 with stride 2, and dilation 2
     (1, 91, 161, 16, 32, 1, 1), (1, 361, 641, 16, 32, 1, 1), (2, 37, 53, 16, 48, 1, 1), (1, 91, 161, 32, 64, 2, 1), (1, 46, 81, 64, 64, 1, 1), (1, 46, 81, 128, 256, 1, 1),
     (1, 46, 81, 256, 256, 1, 2),
+    # stride 2 on the warp-autonomous path (cin 17..32): the real frame size, even / odd / degenerate maps, ragged cout
+    (1, 361, 641, 32, 64, 2, 1), (2, 38, 54, 24, 48, 2, 1), (3, 9, 9, 32, 32, 2, 1), (1, 2, 2, 32, 64, 2, 1), (1, 1, 1, 32, 64, 2, 1),
     # model 75 (config 4): channel counts that are not multiples of 64 (ragged K and N tiles)
     (3, 129, 129, 24, 48, 1, 1), (3, 129, 129, 48, 96, 2, 1), (3, 65, 65, 96, 96, 1, 1), (3, 65, 65, 96, 192, 2, 1),
     (3, 33, 33, 192, 384, 2, 1), (5, 17, 17, 384, 384, 1, 1),
