@@ -47,6 +47,7 @@ constexpr int SWP_SMEM = SWP_WARPS * SWP_WARP_SMEM + SWP_SHARED + 1024;
 struct SwpGeom {
     int n, h, w, k, nc;            // h, w: OUTPUT rows / columns (= the input's for stride 1)
     int s;                         // stride (1 | 2)
+    int full;                      // full-warp layout (cin 33..64, sepwarpf_kernel): strips of 4 pixels
     int strips, nq, rb;            // 8-pixel column strips per image row, row blocks per strip, output rows per block
     int ks, nt;                    // k16 slices (1 or 2), n8 tiles (cout / 8)
     int items;                     // n * strips * nq (< 2^31: 32-bit index arithmetic in the kernel)
@@ -187,18 +188,18 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
         uint32_t stage_addr = 0;
         // input row r of the item: wait for its chunk when it is the chunk's first row; returns the lane's address of the row
         auto enter_row = [&](const int r) {
-            const int ci = r / ROWS, rr = r % ROWS;
+            const uint32_t ci = (uint32_t)r / (uint32_t)ROWS, rr = (uint32_t)r % (uint32_t)ROWS;    // (ROWS is a power of two)
             if (rr == 0) {
-                const uint32_t s_ = (chunk_ctr + (uint32_t)ci) & 1u;
+                const uint32_t s_ = (chunk_ctr + ci) & 1u;
                 mbar_wait(bars + 8u * s_, (phase_bits >> s_) & 1u);
                 phase_bits ^= 1u << s_;
                 stage_addr = sRing + s_ * SWP_CHUNK + lane_off;
             }
-            return stage_addr + (uint32_t)rr * (COLS * PIXB);
+            return stage_addr + rr * (uint32_t)(COLS * PIXB);
         };
         // ... and once the chunk's last row is in registers (its FMAs issued by every lane) the stage is refilled
         auto leave_row = [&](const int r) {
-            if (r % ROWS == ROWS - 1 || r == rows_in - 1) {
+            if (((uint32_t)r & (uint32_t)(ROWS - 1)) == (uint32_t)(ROWS - 1) || r == rows_in - 1) {
                 __syncwarp();
                 if (lane == 0) issue_next();                              // (of this item or the next)
             }
@@ -301,8 +302,233 @@ sepwarp_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restri
     }
 }
 
+// ---- full-warp layout: cin 33..64 -------------------------------------------------------------------------------------
+// The same warp-autonomous pipeline for blocks whose channel pairs fill a whole warp (lane = channel pair, like dwwarp.cu):
+// a strip is 4 output pixels wide, four output rows form the m16 tile, the GEMM has KS k16 slices and NT n8 tiles (all
+// compile-time: one instantiation per block shape that measured faster than the CTA pipeline of sepconv.cu -- 48 -> 96
+// stride 2, the second block of model 75, which ran there with a quarter of its depthwise lanes on zero-filled channels:
+// 0.293 -> 0.272 ms at 129 x 129 x 512).  Chunks are 4 input rows; the TMA box is as wide as cin rounded up to 16
+// channels, so a 48-channel pixel is 96 bytes.  Same taps in the same order as every other depthwise kernel.
+template <int KS, int NT, int S> struct SwfCfg {
+    static constexpr int PIXB = KS * 32;                       // bytes per patch pixel
+    static constexpr int ROWS = 4, COLS = S == 2 ? 9 : 6;      // input rows per chunk; 4 output pixels -> 2 * 4 + 1 | 4 + 2 input columns
+    static constexpr int CHUNK = ROWS * COLS * PIXB;           // (a multiple of 128: KS * 32 * 4 = KS * 128)
+    static constexpr int A_STRIDE = PIXB + 16, O_STRIDE = NT * 16 + 16, W_STRIDE = PIXB + 16;   // odd numbers of 16-byte chunks: conflict-free
+    static constexpr int WARP_SMEM = (2 * CHUNK + 16 * A_STRIDE + 16 * O_STRIDE + 16 + 127) / 128 * 128;
+    static constexpr int SHARED = NT * 8 * W_STRIDE + NT * 8 * 4;
+    static constexpr int SMEM = SWP_WARPS * WARP_SMEM + SHARED + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+};
+
+template <int KS, int NT, int S>
+__global__ void __launch_bounds__(SWP_THREADS, 1)
+sepwarpf_kernel(const __grid_constant__ CUtensorMap tmap_x, const float *__restrict__ dw_w, const float *__restrict__ dw_b,
+                const __nv_bfloat16 *__restrict__ pw_w, const float *__restrict__ pw_b, __nv_bfloat16 *__restrict__ y, const SwpGeom g) {
+    using Cfg = SwfCfg<KS, NT, S>;
+    constexpr uint32_t PIXB = Cfg::PIXB, CHUNK = Cfg::CHUNK, A_STRIDE = Cfg::A_STRIDE, O_STRIDE = Cfg::O_STRIDE, W_STRIDE = Cfg::W_STRIDE;
+    constexpr int ROWS = Cfg::ROWS, COLS = Cfg::COLS, NC = COLS;
+    extern __shared__ uint8_t swp_raw[];
+    const uint32_t base = (smem_u32(swp_raw) + 1023u) & ~1023u;
+    uint8_t *gen = swp_raw + (base - smem_u32(swp_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sW = base + SWP_WARPS * Cfg::WARP_SMEM, sBias = sW + NT * 8 * W_STRIDE;
+    const uint32_t mine = base + (uint32_t)warp * Cfg::WARP_SMEM;
+    const uint32_t sRing = mine, sA = mine + 2 * CHUNK, sO = sA + 16 * A_STRIDE, bars = sO + 16 * O_STRIDE;
+
+    // ---- CTA-wide, once: pointwise weights [cout][k] -> padded rows (channels beyond cin zero), bias; per warp: its ring barriers
+    for (int i = threadIdx.x; i < NT * 8 * KS * 2; i += SWP_THREADS) {   // (row n, 16-byte chunk c) = 8 input channels
+        const int nrow = i / (KS * 2), c = i - nrow * (KS * 2);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (nrow < g.nc && c * 8 < g.k) v = *reinterpret_cast<const uint4 *>(pw_w + (size_t)nrow * g.k + c * 8);
+        *reinterpret_cast<uint4 *>(gen + SWP_WARPS * Cfg::WARP_SMEM + nrow * W_STRIDE + c * 16) = v;
+    }
+    if (threadIdx.x < NT * 8) reinterpret_cast<float *>(gen + SWP_WARPS * Cfg::WARP_SMEM + NT * 8 * W_STRIDE)[threadIdx.x] =
+        (int)threadIdx.x < g.nc ? pw_b[threadIdx.x] : 0.f;
+    if (lane == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 8, 1);
+        mbar_fence_init();
+        if (warp == 0) tma_prefetch_desc(&tmap_x);
+    }
+    pdl_launch_dependents();
+    __syncthreads();
+    pdl_wait();
+
+    // ---- per lane: its channel pair's 9 x 2 depthwise weights + bias; lanes beyond cin / 2 compute on channel pair 0 and store nothing
+    const bool lane_on = 2 * lane < g.k;
+    const int cp = lane_on ? lane : 0;
+    float2 wk[9], bias2;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wk[t] = *reinterpret_cast<const float2 *>(dw_w + (size_t)t * g.k + 2 * cp);
+    bias2 = *reinterpret_cast<const float2 *>(dw_b + 2 * cp);
+    auto unpack = [](uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); };
+    const uint32_t lane_off = (uint32_t)cp * 4u;
+    const uint32_t a_lane_addr = sA + (uint32_t)cp * 4u;                                                  // + (4 (t & 3) + p) rows
+    const uint32_t a_ld_addr = sA + (uint32_t)(lane & 15) * A_STRIDE + (uint32_t)(lane >> 4) * 16u;         // ldmatrix row / k-chunk
+    const uint32_t w_ld_addr = sW + (uint32_t)(lane & 7) * W_STRIDE + (uint32_t)(lane >> 3) * 16u;          // + nt * 8 rows
+    const int gq = lane >> 2, qq = lane & 3;                              // accumulator fragment: rows gq / gq + 8, columns 2 qq (+1)
+
+    uint32_t phase_bits = 0, chunk_ctr = 0;
+    const int total_warps = (int)gridDim.x * SWP_WARPS, first_item = (int)blockIdx.x * SWP_WARPS + warp;
+    struct Item { int x0, y0, img, rows_out, nchunks; };
+    auto decode = [&](int it) {
+        Item t;
+        const int xs = it % g.strips, rest = it / g.strips;
+        t.x0 = xs * 4;
+        t.y0 = (rest % g.nq) * g.rb;
+        t.img = rest / g.nq;
+        t.rows_out = min(g.rb, g.h - t.y0);
+        t.nchunks = t.rows_out > 0 ? (S * t.rows_out + 3 - S + ROWS - 1) / ROWS : 0;     // input rows: S (rows_out - 1) + 3
+        return t;
+    };
+    int p_item = first_item, p_ci = 0;
+    uint32_t p_chunks = 0;
+    Item pit = p_item < g.items ? decode(p_item) : Item{0, 0, 0, 0, 0};
+    auto issue_next = [&]() {                                             // lane 0: the next chunk in (item, chunk) order, if any
+        while (p_item < g.items && p_ci >= pit.nchunks) {
+            p_item += total_warps;
+            p_ci = 0;
+            if (p_item < g.items) pit = decode(p_item);
+        }
+        if (p_item >= g.items) return;
+        const uint32_t s_ = p_chunks & 1u;
+        mbar_expect_tx(bars + 8u * s_, CHUNK);
+        tma_load_4d(sRing + s_ * CHUNK, &tmap_x, bars + 8u * s_, 0, S * pit.x0 - 1, S * pit.y0 - 1 + p_ci * ROWS, pit.img);
+        ++p_chunks;
+        ++p_ci;
+    };
+    if (lane == 0) {
+        issue_next();
+        issue_next();
+    }
+
+    for (int item = first_item; item < g.items; item += total_warps) {
+        const Item it = decode(item);
+        const int x0 = it.x0, y0 = it.y0, img = it.img, rows_out = it.rows_out;
+        if (rows_out <= 0) continue;
+        const int rows_in = S * (rows_out - 1) + 3;
+        const int ncol_ok = g.w - x0;                                     // strip pixels px < ncol_ok exist
+        const size_t pix_bytes = (size_t)g.nc * 2, row_bytes = (size_t)g.w * pix_bytes;
+        // output stores of the tensor phase: 16-byte chunk q = i * 32 + lane of the 16 x NT chunks of an m16 tile belongs to staging
+        // row q / NT (= 4 * tile row + pixel) and channels 8 (q % NT) ..; the pointer advances by four output rows per phase
+        char *o_tile = reinterpret_cast<char *>(y) + (((size_t)img * g.h + y0) * g.w + x0) * pix_bytes;
+        uint32_t stage_addr = 0;
+        auto enter_row = [&](const int r) {
+            const uint32_t ci = (uint32_t)r / (uint32_t)ROWS, rr = (uint32_t)r % (uint32_t)ROWS;    // (ROWS is a power of two)
+            if (rr == 0) {
+                const uint32_t s_ = (chunk_ctr + ci) & 1u;
+                mbar_wait(bars + 8u * s_, (phase_bits >> s_) & 1u);
+                phase_bits ^= 1u << s_;
+                stage_addr = sRing + s_ * CHUNK + lane_off;
+            }
+            return stage_addr + rr * (uint32_t)(COLS * PIXB);
+        };
+        auto leave_row = [&](const int r) {
+            if (((uint32_t)r & (uint32_t)(ROWS - 1)) == (uint32_t)(ROWS - 1) || r == rows_in - 1) {
+                __syncwarp();
+                if (lane == 0) issue_next();
+            }
+        };
+        auto load_row = [&](const uint32_t rp, float2 (&row)[NC]) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) row[c] = unpack(swp_lds_u32(rp + (uint32_t)c * PIXB));
+        };
+        auto fma_row = [&](const float2 (&row)[NC], const int ky, float2 (&acc)[4]) {   // taps (ky, 0..2) of every pixel, kx ascending
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+                        if (S * p + kx == c) acc[p] = ffma2(row[c], wk[ky * 3 + kx], acc[p]);
+        };
+        auto finish_row = [&](const int t, const float2 (&acc)[4]) {
+            const uint32_t arow = a_lane_addr + (uint32_t)((t & 3) * 4) * A_STRIDE;
+            if (lane_on) {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) swp_sts_u32(arow + (uint32_t)p * A_STRIDE, relu6_bf16x2(acc[p]));
+            }
+            if (!((t & 3) == 3 || t == rows_out - 1)) return;
+            // ---- four output rows (or the last 1-3) are staged: 16 pixels x cin -> pointwise GEMM on mma.sync
+            __syncwarp();
+            uint32_t a[KS][4];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) ldmatrix_x4(a_ld_addr + (uint32_t)ks * 32u, a[ks]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                uint32_t b[(KS + 1) / 2][4];
+#pragma unroll
+                for (int h2 = 0; h2 < (KS + 1) / 2; ++h2) ldmatrix_x4(w_ld_addr + (uint32_t)(nt * 8) * W_STRIDE + (uint32_t)h2 * 64u, b[h2]);
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) mma_bf16_16816(d, a[ks], b[ks >> 1][(ks & 1) * 2], b[ks >> 1][(ks & 1) * 2 + 1]);
+                float2 bv;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bv.x), "=f"(bv.y) : "r"(sBias + (uint32_t)(nt * 8 + 2 * qq) * 4u));
+                const uint32_t o = sO + (uint32_t)gq * O_STRIDE + (uint32_t)(nt * 16 + qq * 4);
+                swp_sts_u32(o, relu6_bf16x2(fadd2(make_float2(d[0], d[1]), bv)));
+                swp_sts_u32(o + 8u * O_STRIDE, relu6_bf16x2(fadd2(make_float2(d[2], d[3]), bv)));
+            }
+            __syncwarp();
+            const int nrows = (t & 3) + 1;                                // tile rows that exist
+#pragma unroll
+            for (int i = 0; i < (16 * NT + 31) / 32; ++i) {
+                const int q = i * 32 + lane, px = q / NT, ch = q - px * NT, trow = px >> 2, tcol = px & 3;
+                const bool ok = q < 16 * NT && trow < nrows && tcol < ncol_ok;
+                swp_stg_v4_if(o_tile + (size_t)trow * row_bytes + (size_t)tcol * pix_bytes + (size_t)ch * 16,
+                              ld_shared_v4(sO + (uint32_t)px * O_STRIDE + (uint32_t)ch * 16u), ok);
+            }
+            o_tile += 4 * row_bytes;
+            __syncwarp();                                                 // staging buffers are rewritten by the next rows
+        };
+        if constexpr (S == 1) {
+            float2 ring[3][NC];                                           // input rows r-2, r-1, r live in slots (j+1)%3, (j+2)%3, j
+#pragma unroll 1
+            for (int r0 = 0; r0 < rows_in; r0 += 3) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int r = r0 + j;
+                    if (r >= rows_in) break;
+                    load_row(enter_row(r), ring[j]);
+                    if (r < 2) continue;
+                    float2 acc[4] = {bias2, bias2, bias2, bias2};
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) fma_row(ring[(j + 1 + ky) % 3], ky, acc);
+                    finish_row(r - 2, acc);
+                    leave_row(r);
+                }
+            }
+        } else {
+            float2 carry[NC], tmp[NC];                                    // (see sepwarp_kernel: the shared input row is carried over)
+            load_row(enter_row(0), carry);
+#pragma unroll 1
+            for (int t = 0; t < rows_out; ++t) {
+                float2 acc[4] = {bias2, bias2, bias2, bias2};
+                fma_row(carry, 0, acc);
+                load_row(enter_row(2 * t + 1), tmp);
+                fma_row(tmp, 1, acc);
+                leave_row(2 * t + 1);
+                load_row(enter_row(2 * t + 2), carry);
+                fma_row(carry, 2, acc);
+                finish_row(t, acc);
+                leave_row(2 * t + 2);
+            }
+        }
+        chunk_ctr += (uint32_t)it.nchunks;
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
+// block shapes with an instantiation of the full-warp kernel (measured against the CTA pipeline on the blocks of models 75 / 50)
+static bool sepwarp_full_shape(int k, int nc, int stride) {
+    const char *e = getenv("PN_SEPWARP_FULL");
+    if (e && e[0] == '0') return false;
+    // (64 -> 64 stride 1, the third block of model 50, was measured too -- sepwarpf_kernel<4, 8, 1>: 0.164 vs 0.160 ms on the CTA
+    // pipeline at 181 x 321 x 32 -- and stays there)
+    return k == 48 && nc == 96 && stride == 2;
+}
+
 bool sepwarp_supported(int k, int nc, int stride, int dil) {
+    if (dil == 1 && sepwarp_full_shape(k, nc, stride) && getenv("PN_NO_SEPWARP") == nullptr) return true;
     if (!(dil == 1 && k >= 8 && k <= 32 && k % 8 == 0 && nc >= 8 && nc <= 64 && nc % 8 == 0 && getenv("PN_NO_SEPWARP") == nullptr)) return false;
     if (stride == 1) return true;
     // stride 2: cin 17..32 (the half-warp layout; narrower blocks would idle half its lanes).  PN_SEPWARP_S2=0 sends these blocks
@@ -320,7 +546,8 @@ int sepwarp_geometry(SepWarpOp *op, int n, int h, int wd, int k, int nc, int str
     g.n = n; g.k = k; g.nc = nc; g.s = stride;
     g.h = (h - 1) / stride + 1;                                            // 3x3, pad 1: floor((h + 2 - 3) / s) + 1
     g.w = (wd - 1) / stride + 1;
-    g.strips = ceil_div(g.w, 8);
+    g.full = sepwarp_full_shape(k, nc, stride) ? 1 : 0;
+    g.strips = ceil_div(g.w, g.full ? 4 : 8);
     g.ks = ceil_div(k, 16);
     g.nt = nc / 8;
     // row blocks: about six items per warp of a full grid, at least 8 output rows each
@@ -347,6 +574,10 @@ int sepwarp_prepare(SepWarpOp *op, const void *x, int n, int h, int wd, int k, i
     // (k <= 16, stride 1: the QTR kernel's 32-byte pixels; stride 2: chunks of 4 input rows x 17 columns)
     const uint32_t box[4] = {(k <= 16 && stride == 1) ? 16u : 32u, (uint32_t)(stride == 2 ? SWP_COLS2 : SWP_COLS),
                              (uint32_t)(stride == 2 ? SWP_ROWS2 : SWP_ROWS), 1u};
+    if (sepwarp_full_shape(k, nc, stride)) {                             // full-warp layout: cin rounded up to 16 channels, 4-pixel strips, 4-row chunks
+        const uint32_t fbox[4] = {(uint32_t)ceil_div(k, 16) * 16u, (uint32_t)(stride == 2 ? 9 : 6), 4u, 1u};
+        return encode_tmap(op->tmap_x, x, 2, 4, dims, strides, fbox, 0);
+    }
     return encode_tmap(op->tmap_x, x, 2, 4, dims, strides, box, 0);
 }
 
@@ -369,6 +600,21 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
                                  (const __nv_bfloat16 *)pw_w, pw_b, (__nv_bfloat16 *)y, g));
         return PN_OK;
     };
+    if (g.full) {
+        auto launch_f = [&](auto kern, int smem, DeviceOnce &once) -> int {
+            if (!once.get(dev)) {
+                PN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                once.set(dev, 1);
+            }
+            PN_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(SWP_THREADS), (size_t)smem, st, *reinterpret_cast<const CUtensorMap *>(op->tmap_x), dw_w,
+                                     dw_b, (const __nv_bfloat16 *)pw_w, pw_b, (__nv_bfloat16 *)y, g));
+            return PN_OK;
+        };
+        static DeviceOnce f3122;
+        if (g.k == 48 && g.nc == 96 && g.s == 2) return launch_f(sepwarpf_kernel<3, 12, 2>, SwfCfg<3, 12, 2>::SMEM, f3122);   // model 75, block 2
+        set_error("pn_sepconv_block: no full-warp instantiation for %d -> %d stride %d", g.k, g.nc, g.s);
+        return PN_ERR_UNSUPPORTED;
+    }
     static DeviceOnce c28, c26, c14, c00, c00q, s28, s00;
     if (g.s == 2) {
         if (g.ks == 2 && g.nt == 8) return launch(sepwarp_kernel<2, 8, false, 2>, s28);   // 32 -> 64 stride 2 (model 50)
@@ -384,8 +630,8 @@ int sepwarp_launch(const SepWarpOp *op, const float *dw_w, const float *dw_b, co
 void sepwarp_describe(const SepWarpOp *op, char *out, size_t cap) {
     SwpGeom g;
     memcpy(&g, op->geom, sizeof(g));
-    snprintf(out, cap, "warp-autonomous%s strips %d x %d row blocks of %d rows, k16 slices %d, n8 tiles %d, items %d, smem %d",
-             g.s == 2 ? " stride 2" : "", g.strips, g.nq, g.rb, g.ks, g.nt, g.items, SWP_SMEM);
+    snprintf(out, cap, "warp-autonomous%s%s strips %d x %d row blocks of %d rows, k16 slices %d, n8 tiles %d, items %d, smem %d",
+             g.full ? " full-warp" : "", g.s == 2 ? " stride 2" : "", g.strips, g.nq, g.rb, g.ks, g.nt, g.items, SWP_SMEM);
 }
 
 }  // namespace pn

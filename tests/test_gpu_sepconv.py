@@ -31,6 +31,8 @@ SHAPES = [  # n, h, w, cin, cout, stride, dilation
     # model 75 (config 4): channel counts that are not multiples of 64 (ragged K and N tiles)
     (3, 129, 129, 24, 48, 1, 1), (3, 129, 129, 48, 96, 2, 1), (3, 65, 65, 96, 96, 1, 1), (3, 65, 65, 96, 192, 2, 1),
     (3, 33, 33, 192, 384, 2, 1), (5, 17, 17, 384, 384, 1, 1),
+    # full-warp layout of the warp-autonomous kernel (48 -> 96 stride 2): ragged strips / rows, degenerate maps
+    (1, 181, 321, 64, 64, 1, 1), (2, 7, 5, 48, 96, 2, 1), (2, 6, 10, 64, 64, 1, 1), (1, 1, 1, 48, 96, 2, 1), (1, 2, 3, 48, 96, 2, 1),
     # model 101 @ OS8: dilation 4; tiny and degenerate maps
     (1, 33, 33, 1024, 1024, 1, 4), (2, 5, 3, 64, 64, 1, 1), (1, 1, 1, 32, 64, 1, 1), (1, 2, 2, 64, 128, 2, 1), (4, 9, 9, 8, 16, 1, 1),
 ]
