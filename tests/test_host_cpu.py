@@ -93,11 +93,17 @@ def test_measured_tile_table_and_team_policy(monkeypatch):
     rows = [tuple(int(v) for v in m.group(1).split(",")) for m in re.finditer(r"^\s*\{([\d, ]+)\}", open(inc).read(), re.M)]
     assert len(rows) >= 5
     pat = re.compile(r"tile (\d+)x(\d+) subs (\d+) .* teams (\d+) stages p(\d+) w(\d+)r? a(\d+) stg(\d+)")
+    # (two of the table's blocks -- 32 -> 64 and 48 -> 96 stride 2 -- run on the warp-autonomous kernel by default; their rows are what
+    # the CTA pipeline uses when that path is switched off)
+    monkeypatch.setenv("PN_SEPWARP_S2", "0")
+    monkeypatch.setenv("PN_SEPWARP_FULL", "0")
     for (k, nc, s, d, ho, wo, th, tw, subs, p, w, a, stg, teams) in rows:
         h, wd = (ho - 1) * s + 1, (wo - 1) * s + 1                   # an input size that gives this output size (pad = dilation for stride 1)
         assert lib.pn_sepconv_describe(4, h, wd, k, nc, s, d, buf, 512) == 0, lib.pn_last_error_string()
         got = tuple(int(v) for v in pat.search(buf.value.decode()).groups())
         assert got == (th, tw, subs, teams, p, w, a, stg), (buf.value, (k, nc, s, d, ho, wo))
+    monkeypatch.delenv("PN_SEPWARP_S2")
+    monkeypatch.delenv("PN_SEPWARP_FULL")
     k, nc, s, d, ho, wo, th, tw, subs = rows[0][:9]
     monkeypatch.setenv("PN_SEP_TUNED", "0")
     assert lib.pn_sepconv_describe(4, (ho - 1) * s + 1, (wo - 1) * s + 1, k, nc, s, d, buf, 512) == 0 and b"tile" in buf.value
@@ -112,6 +118,33 @@ def test_measured_tile_table_and_team_policy(monkeypatch):
     assert lib.pn_sepconv_describe(64, 33, 33, 512, 512, 1, 1, buf, 512) == 0 and b"r a" not in buf.value      # 512 KB of W: ring
     monkeypatch.setenv("PN_SEP_WRES", "0")
     assert lib.pn_sepconv_describe(64, 129, 129, 128, 128, 1, 1, buf, 512) == 0 and b"r a" not in buf.value
+
+
+def test_warp_autonomous_block_policy(monkeypatch):
+    """csrc/sepwarp.cu: which fused blocks run warp-autonomous -- cin <= 32 / cout <= 64 at stride 1 (quarter-warp layout up to cin
+    16), stride 2 for cin 17..32, the full-warp layout for 48 -> 96 stride 2 -- with their switches, and the output geometry of the
+    stride-2 strips."""
+    import ctypes as C
+    lib, buf = nat.load(), C.create_string_buffer(512)
+    for k in ("PN_NO_SEPWARP", "PN_SEPWARP_S2", "PN_SEPWARP_FULL"):
+        monkeypatch.delenv(k, raising=False)
+    def desc(*shape):
+        assert lib.pn_sepconv_describe(*shape, buf, 512) == 0, lib.pn_last_error_string()
+        return buf.value.decode()
+    assert desc(32, 721, 1281, 16, 32, 1, 1).startswith("warp-autonomous strips 161 x")            # 1281 / 8
+    d = desc(32, 721, 1281, 32, 64, 2, 1)
+    assert d.startswith("warp-autonomous stride 2 strips 81 x") and "k16 slices 2, n8 tiles 8" in d   # output 361 x 641: 641 / 8
+    d = desc(512, 129, 129, 48, 96, 2, 1)
+    assert d.startswith("warp-autonomous full-warp stride 2 strips 17 x") and "k16 slices 3, n8 tiles 12" in d   # output 65 wide: 65 / 4
+    assert desc(32, 181, 321, 64, 64, 1, 1).startswith("tile ")                                       # measured slower there: CTA pipeline
+    assert desc(32, 721, 1281, 16, 32, 2, 1).startswith("tile ")                                      # stride 2 needs cin > 16
+    assert desc(64, 257, 257, 64, 128, 2, 1).startswith("tile ")
+    monkeypatch.setenv("PN_SEPWARP_S2", "0")
+    assert desc(32, 721, 1281, 32, 64, 2, 1).startswith("tile ")
+    monkeypatch.setenv("PN_SEPWARP_FULL", "0")
+    assert desc(512, 129, 129, 48, 96, 2, 1).startswith("tile ")
+    monkeypatch.setenv("PN_NO_SEPWARP", "1")
+    assert desc(64, 257, 257, 32, 64, 1, 1).startswith("half tile ") or desc(64, 257, 257, 32, 64, 1, 1).startswith("tile ")
 
 
 @pytest.mark.parametrize("mid", [50, 75, 100, 101])
