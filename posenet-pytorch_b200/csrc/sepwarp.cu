@@ -25,6 +25,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -570,12 +573,39 @@ int sepwarp_geometry(SepWarpOp *op, int n, int h, int wd, int k, int nc, int str
     g.strips = ceil_div(g.w, g.full ? 4 : 8);
     g.ks = ceil_div(k, 16);
     g.nt = nc / 8;
-    // row blocks: about six items per warp of a full grid, at least 8 output rows each
-    const long long warps = (long long)num_sms() * SWP_WARPS;
-    long long nq = (6 * warps + (long long)n * g.strips - 1) / ((long long)n * g.strips);
+    // Row blocks.  Items go to the warps of a full grid round-robin (item i -> warp i mod W, strips fastest), a warp walks its
+    // items one after the other, and an item costs its input rows (measured: the time of a launch follows the LARGEST per-warp sum
+    // of input rows within 2 % across row-block counts; the per-item overhead is nil).  With only a handful of items per warp the
+    // quantisation of that sum is worth 5-20 %, so every row-block count (blocks of at least 8 output rows) is simulated and the
+    // best one taken: 64 x 257 x 257: 7 -> 10 blocks, 512 x 129 x 129: 2 -> 4, 32 x 361 x 641 stride 2: 11 -> 7.
+    // PN_SWP_ITEMS=n brings back the rule it replaces (about n items per warp).
+    const int warps = num_sms() * SWP_WARPS;
     const int max_nq = ceil_div(g.h, 8);
-    if (nq > max_nq) nq = max_nq;
-    if (nq < 1) nq = 1;
+    long long nq = 1;
+    if (const char *e = getenv("PN_SWP_ITEMS")) {
+        const long long per_warp = atoi(e) > 0 ? atoi(e) : 6;
+        nq = (per_warp * warps + (long long)n * g.strips - 1) / ((long long)n * g.strips);
+        if (nq > max_nq) nq = max_nq;
+        if (nq < 1) nq = 1;
+    } else {
+        std::vector<long long> load((size_t)warps);
+        long long best = -1;
+        for (int cand = 1; cand <= max_nq; ++cand) {
+            const int rb = ceil_div(g.h, cand);
+            if (ceil_div(g.h, rb) != cand) continue;                       // (the same blocks as a smaller count)
+            const long long items_c = (long long)n * g.strips * cand;
+            if (items_c > (1ll << 22)) break;                              // (plan-time work bound; never reached by the reference's sizes)
+            std::fill(load.begin(), load.end(), 0ll);
+            int wi = 0, xs = 0, q = 0;
+            for (long long it = 0; it < items_c; ++it) {
+                load[(size_t)wi] += (long long)(rb < g.h - q * rb ? rb : g.h - q * rb) * stride + (3 - stride);
+                if (++wi == warps) wi = 0;
+                if (++xs == g.strips) { xs = 0; if (++q == cand) q = 0; }
+            }
+            const long long worst = *std::max_element(load.begin(), load.end());
+            if (best < 0 || worst < best) { best = worst; nq = cand; }
+        }
+    }
     g.rb = ceil_div(g.h, (int)nq);
     g.nq = ceil_div(g.h, g.rb);
     const long long items = (long long)n * g.strips * g.nq;
