@@ -126,12 +126,20 @@ def test_warp_autonomous_block_policy(monkeypatch):
     stride-2 strips."""
     import ctypes as C
     lib, buf = nat.load(), C.create_string_buffer(512)
-    for k in ("PN_NO_SEPWARP", "PN_SEPWARP_S2", "PN_SEPWARP_FULL"):
+    for k in ("PN_NO_SEPWARP", "PN_SEPWARP_S2", "PN_SEPWARP_FULL", "PN_SWP_ITEMS"):
         monkeypatch.delenv(k, raising=False)
     def desc(*shape):
         assert lib.pn_sepconv_describe(*shape, buf, 512) == 0, lib.pn_last_error_string()
         return buf.value.decode()
     assert desc(32, 721, 1281, 16, 32, 1, 1).startswith("warp-autonomous strips 161 x")            # 1281 / 8
+    # row blocks: the count that minimises the largest per-warp sum of input rows under the round-robin item assignment (148 SMs x 16
+    # warps); PN_SWP_ITEMS=6 is the rule it replaced
+    assert "strips 33 x 10 row blocks of 26 rows" in desc(64, 257, 257, 32, 64, 1, 1)
+    assert "strips 17 x 4 row blocks of 33 rows" in desc(512, 129, 129, 24, 48, 1, 1)
+    assert "strips 41 x 7 row blocks of 26 rows" in desc(32, 361, 641, 32, 64, 2, 1)
+    monkeypatch.setenv("PN_SWP_ITEMS", "6")
+    assert "strips 33 x 7 row blocks of 37 rows" in desc(64, 257, 257, 32, 64, 1, 1)
+    monkeypatch.delenv("PN_SWP_ITEMS")
     d = desc(32, 721, 1281, 32, 64, 2, 1)
     assert d.startswith("warp-autonomous stride 2 strips 81 x") and "k16 slices 2, n8 tiles 8" in d   # output 361 x 641: 641 / 8
     d = desc(512, 129, 129, 48, 96, 2, 1)
