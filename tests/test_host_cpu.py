@@ -155,6 +155,47 @@ def test_warp_autonomous_block_policy(monkeypatch):
     assert desc(64, 257, 257, 32, 64, 1, 1).startswith("half tile ") or desc(64, 257, 257, 32, 64, 1, 1).startswith("tile ")
 
 
+def test_warp_autonomous_row_blocks_minimise_the_busiest_warp(monkeypatch):
+    """sepwarp_geometry picks the row-block count whose round-robin item assignment leaves the busiest warp the least input rows:
+    a Python model of the same simulation (items strips-fastest over 148 x 16 warps, cost = input rows of the block) agrees with the
+    library on random shapes of the three layouts, and the rows cover the map exactly."""
+    import ctypes as C
+    import re
+    lib, buf = nat.load(), C.create_string_buffer(512)
+    for k in ("PN_NO_SEPWARP", "PN_SEPWARP_S2", "PN_SEPWARP_FULL", "PN_SWP_ITEMS"):
+        monkeypatch.delenv(k, raising=False)
+    warps = 148 * 16
+
+    def model(n, ho, strips, s):
+        best = None
+        for cand in range(1, -(-ho // 8) + 1):
+            rb = -(-ho // cand)
+            if -(-ho // rb) != cand:
+                continue
+            load = [0] * warps
+            for it in range(n * strips * cand):
+                q = (it // strips) % cand
+                load[it % warps] += min(rb, ho - q * rb) * s + (3 - s)
+            if best is None or max(load) < best[0]:
+                best = (max(load), cand, rb)
+        return best[1], best[2]
+
+    rng = np.random.default_rng(5)
+    shapes = [(64, 257, 257, 32, 64, 1), (512, 129, 129, 24, 48, 1), (32, 361, 641, 16, 32, 1), (32, 361, 641, 32, 64, 2), (512, 129, 129, 48, 96, 2)]
+    for _ in range(12):
+        k, nc, s = [(32, 64, 1), (16, 32, 1), (24, 48, 1), (32, 64, 2), (48, 96, 2)][int(rng.integers(0, 5))]
+        shapes.append((int(rng.integers(1, 40)), int(rng.integers(1, 300)), int(rng.integers(1, 300)), k, nc, s))
+    for n, h, w, k, nc, s in shapes:
+        assert lib.pn_sepconv_describe(n, h, w, k, nc, s, 1, buf, 512) == 0, lib.pn_last_error_string()
+        m = re.search(r"strips (\d+) x (\d+) row blocks of (\d+) rows", buf.value.decode())
+        assert m, buf.value
+        strips, nq, rb = (int(v) for v in m.groups())
+        ho, wo = (h - 1) // s + 1, (w - 1) // s + 1
+        assert strips == -(-wo // (4 if (k, nc, s) == (48, 96, 2) else 8))
+        assert (nq - 1) * rb < ho <= nq * rb
+        assert (nq, rb) == model(n, ho, strips, s), (n, h, w, k, nc, s)
+
+
 @pytest.mark.parametrize("mid", [50, 75, 100, 101])
 @pytest.mark.parametrize("os_", [8, 16, 32])
 def test_layer_table_and_state_dict_mirror_reference(mid, os_):
